@@ -1,0 +1,369 @@
+"""CPU oracle for the à trous / WOW hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+This module is a NumPy restatement of the algorithm of watroo 0.0.4 (frederic-auchere/wavelets) for the one
+hot path this repository accelerates.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline
+legs may import it; nothing under ``wavelets_b200/`` does, and the product path raises if its CUDA library is
+missing instead of falling back to this file.
+
+Parity status: PINNED.  ``tests/golden/*.npz`` were produced by running the real reference (``/root/reference``,
+with a 10-line ``numexpr`` shim because numexpr is not installed in this image) through
+``tests/golden/make_golden.py``; ``tests/test_oracle.py`` checks every function below against those vectors, against
+the reference's own known-answer test (constant image -> zero detail planes, ``tests/test_wavelets.py:8-13``), the
+perfect-reconstruction identity, and the README equivalences (``README.md:46-61``).
+
+Third-party arithmetic the reference leans on (not vendored under /root/reference; only lower bounds are pinned in
+``requirements.txt:1-5``; versions below are the ones installed in this image and used to make the goldens):
+  * opencv-python-headless 4.13.0.92  ``cv2.filter2D(..., BORDER_REFLECT)``  (``watroo/wavelets.py:39-45``).
+    Published semantics: *correlation* of the image with the kernel, anchor at the kernel centre, border pixels
+    taken by half-sample symmetric reflection ``fedcba|abcdefgh|hgfedcb``.  For float32 images OpenCV sums in
+    float32 for small kernels and goes through a double-precision DFT for big ones (the result is then the
+    correctly rounded double answer).  The ``numpy`` backend below restates that as: accumulate in float64, round
+    once to the image dtype.  The ``cv2`` backend issues the very same call as the reference.
+  * numexpr (absent here)  ``ne.evaluate('k*exp(-((image - shifted)**2)/bilateral_variance/2)')``
+    (``watroo/wavelets.py:97``): an element-wise expression in the image dtype; restated with ``np.exp``.
+  * scipy 1.18.1 ``special.erf`` (``watroo/wavelets.py:138``), numpy 2.3.5 ``median/std/sum/pad`` with NEP-50
+    promotion (an fp32 array divided by an fp64 NumPy scalar yields fp64 -- this matters for ``significance``).
+"""
+from __future__ import annotations
+
+import copy
+import math
+import warnings
+
+import numpy as np
+from scipy import special
+
+try:  # the reference's own smoothing primitive; optional so the oracle still runs where OpenCV is absent
+    import cv2
+except Exception:  # pragma: no cover
+    cv2 = None
+
+__all__ = [
+    "TAPS", "SIGMA_E_2D", "SIGMA_E_2D_BILATERAL", "reflect_index", "smooth", "local_variance", "bilateral_smooth",
+    "atrous_transform", "get_noise", "significance", "denoise_planes", "denoise", "wow", "compute_noise_weights",
+    "default_backend", "wow_default_scales", "solar_like", "emax",
+]
+
+# ---------------------------------------------------------------------------------------------------------------
+# Constants (watroo/wavelets.py:239-252 Triangle, :268-281 B3spline).  The sigma_e tables are data recorded by the
+# reference authors with compute_noise_weights(); parity of significance/denoise/wow requires the same numbers.
+# ---------------------------------------------------------------------------------------------------------------
+TAPS = {
+    "triangle": np.array([1 / 4, 1 / 2, 1 / 4]),
+    "b3spline": np.array([1 / 16, 1 / 4, 3 / 8, 1 / 4, 1 / 16]),
+}
+SIGMA_E_1D_LEN = {"triangle": 11, "b3spline": 11}  # len(sigma_e_1d): sets the noise-field side (wavelets.py:225)
+SIGMA_E_2D = {
+    "triangle": np.array([0.7999247, 0.27308452, 0.11998217, 0.05793947, 0.0288104, 0.01447795, 0.00733832,
+                          0.0037203, 0.00192882, 0.00098568, 0.00048533]),
+    "b3spline": np.array([8.907e-01, 2.0072e-01, 8.5551e-02, 4.1261e-02, 2.0470e-02, 1.0232e-02, 5.1435e-03,
+                          2.6008e-03, 1.3161e-03, 6.7359e-04, 4.0040e-04]),
+}
+SIGMA_E_2D_BILATERAL = {
+    "triangle": np.array([0.31063172, 0.34575647, 0.23712331, 0.13559906, 0.07172004, 0.03665405, 0.01850046,
+                          0.00928768, 0.00465967, 0.00234445, 0.00119249]),
+    "b3spline": np.array([0.38234752, 0.24305799, 0.16012153, 0.10633541, 0.07083733, 0.04728659, 0.03163678,
+                          0.02122341, 0.01429102, 0.00952376]),
+}
+
+
+def default_backend() -> str:
+    return "cv2" if cv2 is not None else "numpy"
+
+
+def sigma_e(name: str, bilateral=None) -> np.ndarray:
+    """wavelets.py:199-219 (2-D branch): the bilateral table is selected whenever ``bilateral is not None``."""
+    return SIGMA_E_2D[name] if bilateral is None else SIGMA_E_2D_BILATERAL[name]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Border rule and per-scale smoothing  (watroo/wavelets.py:35-45 + :191-197)
+# ---------------------------------------------------------------------------------------------------------------
+def reflect_index(i, n):
+    """Half-sample symmetric reflection of integer index(es) ``i`` into [0, n): ``fedcba|abcdefgh|hgfedcb``.
+
+    Same rule as cv2.BORDER_REFLECT (wavelets.py:45) and np.pad(mode='symmetric') (wavelets.py:77), for any number
+    of reflections (period 2n)."""
+    m = np.mod(i, 2 * n)
+    return np.where(m < n, m, 2 * n - 1 - m)
+
+
+def _dense_kernel(taps: np.ndarray, s: int) -> np.ndarray:
+    """The dilated dense 2-D kernel of wavelets.py:191-197: outer(h,h) scattered with stride 2**s."""
+    k = len(taps)
+    side = (k - 1) * 2 ** s + 1
+    dense = np.zeros((side, side))
+    dense[:: 2 ** s, :: 2 ** s] = np.outer(taps, taps)
+    return dense
+
+
+def smooth(arr: np.ndarray, name: str, s: int = 0, backend: str | None = None) -> np.ndarray:
+    """c_{s+1} = S_s[c_s]   (wavelets.py:35-45, 2-D branch).
+
+    out(y,x) = sum_i sum_j h_i h_j arr(R(y+(i-c)2^s), R(x+(j-c)2^s)), R = reflect_index; output dtype = input dtype.
+    backend 'cv2'   : the reference's own call (dense dilated kernel, filter2D, BORDER_REFLECT).
+    backend 'numpy' : separable gather, float64 accumulation, one rounding to the image dtype.
+    """
+    if arr.ndim != 2:
+        raise ValueError("oracle covers the 2-D path only")
+    backend = backend or default_backend()
+    taps = TAPS[name]
+    if backend == "cv2":
+        out = np.empty_like(arr)
+        cv2.filter2D(arr, -1, _dense_kernel(taps, s).astype(arr.dtype), out, (-1, -1), 0, cv2.BORDER_REFLECT)
+        return out
+    h, w = arr.shape
+    c = len(taps) // 2
+    d = 2 ** s
+    a64 = arr.astype(np.float64)
+    rows = np.zeros((h, w), dtype=np.float64)
+    xs = np.arange(w)
+    for j, t in enumerate(taps):
+        rows += t * a64[:, reflect_index(xs + (j - c) * d, w)]
+    out = np.zeros((h, w), dtype=np.float64)
+    ys = np.arange(h)
+    for i, t in enumerate(taps):
+        out += t * rows[reflect_index(ys + (i - c) * d, h), :]
+    return out.astype(arr.dtype)
+
+
+def local_variance(arr: np.ndarray, name: str, s: int, backend: str | None = None) -> np.ndarray:
+    """sdev_loc(..., variance=True)  (wavelets.py:24-32): S_s[x^2] - (S_s[x])^2, non-positive -> 1e-20.
+
+    Squares and the subtraction are done in the image dtype exactly as the reference does (this cancels badly in
+    fp32 for bright pixels)."""
+    mean2 = smooth(arr, name, s, backend) ** 2
+    vari = smooth(arr ** 2, name, s, backend)
+    vari -= mean2
+    vari[vari <= 0] = 1e-20
+    return vari
+
+
+def bilateral_smooth(arr: np.ndarray, name: str, variance: np.ndarray, s: int) -> np.ndarray:
+    """atrous_convolution(image, kernel, bilateral_variance, s, 'symmetric')  (wavelets.py:74-105).
+
+    out = (k_c x + sum_t g_t x_t) / (k_c + sum_t g_t),  g_t = k_t exp(-(x - x_t)^2 / V / 2) over the K^2-1
+    off-centre taps, x_t read through the symmetric border, V taken at the output pixel.  All arithmetic in the
+    image dtype (the kernel is cast with .astype(arr.dtype), wavelets.py:438)."""
+    taps = TAPS[name]
+    k2d = np.outer(taps, taps).astype(arr.dtype)
+    n = len(taps)
+    c = n // 2
+    d = 2 ** s
+    h, w = arr.shape
+    padded = np.pad(arr, [(c * d, c * d), (c * d, c * d)], mode="symmetric")
+    out = k2d[c, c] * arr
+    norm = np.full_like(arr, k2d[c, c])
+    for i in range(n):
+        for j in range(n):
+            if i == c and j == c:
+                continue
+            shifted = padded[i * d:i * d + h, j * d:j * d + w]
+            k = k2d[i, j]
+            weight = k * np.exp(-((arr - shifted) ** 2) / variance / 2)
+            norm += weight
+            out += shifted * weight
+    out /= norm
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Cascade  (watroo/wavelets.py:307-328, :408-444)
+# ---------------------------------------------------------------------------------------------------------------
+_RECAST = [np.dtype(t) for t in (np.int16, np.uint16, np.int32, np.uint32, np.int64, ">f4", ">f8")]
+
+
+def _bilateral_list(bilateral, level):
+    """wavelets.py:421-424: scalar -> [b]*(level+1); list -> copy padded with 1 up to level+1 entries."""
+    sb = copy.copy(bilateral) if type(bilateral) is list else [bilateral, ] * (level + 1)
+    if len(sb) <= level:
+        sb.extend([1, ] * (level - len(sb) + 1))
+    return sb
+
+
+def atrous_transform(arr: np.ndarray, level: int, name: str = "b3spline", bilateral=None,
+                     bilateral_scaling: bool = False, backend: str | None = None) -> np.ndarray:
+    """AtrousTransform(sf, bilateral, bilateral_scaling)(arr, level).data  (wavelets.py:307-328, :408-444).
+
+    Planes [w_0 .. w_{L-1}, c_L] with c_0 = arr, c_{s+1} = S_s[c_s] (or its bilateral variant), w_s = c_s - c_{s+1}.
+    Integer and big-endian inputs are recast to float64 (wavelets.py:297,319-320); the input is never modified."""
+    if arr.ndim != 2:
+        raise ValueError("oracle covers the 2-D path only")
+    if arr.dtype in _RECAST:
+        arr = np.float64(arr)
+    sb = _bilateral_list(bilateral, level)
+    coeffs = np.empty((level + 1,) + arr.shape, dtype=arr.dtype)
+    coeffs[0] = arr
+    for s in range(level):
+        if bilateral is None:
+            coeffs[s + 1] = smooth(coeffs[s], name, s, backend)
+        else:
+            variance = local_variance(coeffs[s], name, s, backend) * sb[s] ** 2
+            if bilateral_scaling:
+                variance *= s + 1
+            coeffs[s + 1] = bilateral_smooth(coeffs[s], name, variance, s)
+        coeffs[s] -= coeffs[s + 1]
+    return coeffs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Noise, significance, denoise  (watroo/wavelets.py:126-149, watroo/utils.py:83-102)
+# ---------------------------------------------------------------------------------------------------------------
+def get_noise(planes: np.ndarray, name: str, bilateral=None):
+    """Coefficients.get_noise (wavelets.py:126-127): MAD estimate median(|w_0|)/0.6745/sigma_e[0].
+
+    dtype flow under NumPy>=2: median keeps the plane dtype, '/0.6745' keeps it (weak Python float), '/sigma_e[0]'
+    promotes to float64 (sigma_e is a float64 NumPy scalar)."""
+    return np.median(np.abs(planes[0])) / 0.6745 / sigma_e(name, bilateral)[0]
+
+
+def significance(planes: np.ndarray, name: str, sigma, scale: int, noise, bilateral=None,
+                 soft_threshold: bool = True) -> np.ndarray:
+    """Coefficients.significance (wavelets.py:129-143) for an already known ``noise`` (scalar or map).
+
+    sigma == 0 or scalar noise == 0 -> ones (plane dtype).  soft: erf(|w_s / (sigma*noise*sigma_e[s])|) -- a float64
+    array even for fp32 planes; hard: |w_s| > sigma*noise*sigma_e[s] compared in float64 (bool array)."""
+    if sigma != 0:
+        if type(noise) is not np.ndarray:
+            if noise == 0:
+                return np.ones_like(planes[0])
+        thr = sigma * noise * sigma_e(name, bilateral)[scale]
+        if soft_threshold:
+            return special.erf(np.abs(planes[scale] / thr))
+        return np.abs(planes[scale]) > thr
+    return np.ones_like(planes[0])
+
+
+def denoise_planes(planes: np.ndarray, name: str, sigma, weights=None, noise=None, bilateral=None,
+                   soft_threshold: bool = True):
+    """Coefficients.denoise (wavelets.py:145-149), in place on ``planes``; returns the noise that was used.
+
+    Only the first len(sigma) planes are touched; noise is estimated lazily from the *unmodified* plane 0 at the
+    first scale whose sigma is non-zero (wavelets.py:131-132)."""
+    if weights is None:
+        weights = (1,) * len(sigma)
+    for scl, (c, sig, wgt) in enumerate(zip(planes, sigma, weights)):
+        if sig != 0 and noise is None:
+            noise = get_noise(planes, name, bilateral)
+        c *= wgt * significance(planes, name, sig, scl, noise, bilateral, soft_threshold)
+    return noise
+
+
+def denoise(data: np.ndarray, weights, name: str = "b3spline", noise=None, bilateral=None,
+            soft_threshold: bool = True, backend: str | None = None) -> np.ndarray:
+    """utils.denoise (utils.py:83-102) without the Anscombe option: ``weights`` are the sigma thresholds and their
+    count is the number of scales; result = sum of the planes in plane order (np.sum(axis=0))."""
+    planes = atrous_transform(data, len(weights), name, bilateral=bilateral, backend=backend)
+    denoise_planes(planes, name, weights, noise=noise, bilateral=bilateral, soft_threshold=soft_threshold)
+    return np.sum(planes, axis=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# WOW  (watroo/utils.py:105-219; the h == 0, preserve_variance == False path plus `weights` / `whitening`)
+# ---------------------------------------------------------------------------------------------------------------
+def wow_default_scales(shape, name: str) -> int:
+    """utils.py:122: round(log2(min(shape)) - log2(len(taps)))."""
+    return int(np.round(np.log2(min(shape)) - np.log2(len(TAPS[name]))))
+
+
+def wow(data: np.ndarray, name: str = "b3spline", n_scales=None, weights=(), whitening: bool = True,
+        denoise_coefficients=(), noise=None, bilateral=None, bilateral_scaling: bool = False,
+        soft_threshold: bool = True, backend: str | None = None):
+    """utils.wow (utils.py:105-219) for an image input with h == 0 and preserve_variance == False.
+
+    Returns (recon, planes, noise): the synthesis, the whitened planes (what ``coefficients.data`` holds after the
+    call) and the noise value that was used (None if no significance was evaluated)."""
+    weights = list(weights)
+    denoise_coefficients = list(denoise_coefficients)
+    max_scales = wow_default_scales(data.shape, name)
+    if n_scales is None:
+        n_scales = max_scales
+    elif n_scales > max_scales:
+        n_scales = max_scales
+    table_len = len(sigma_e(name, bilateral))
+    if len(denoise_coefficients) >= table_len:  # utils.py:135-138
+        warnings.warn(f"Required number of scales lager then the maximum for scaling function. Using {table_len}.")
+        n_scales = table_len
+    sigma_bilateral = None if bilateral is None else _bilateral_list(bilateral, n_scales)  # utils.py:140-146
+
+    planes = atrous_transform(data, n_scales, name, bilateral=sigma_bilateral, bilateral_scaling=bilateral_scaling,
+                              backend=backend)
+
+    wts = copy.copy(weights)  # utils.py:160-163
+    if len(wts) <= n_scales:
+        wts.extend([1, ] * (n_scales - len(wts) + 1))
+    dns = copy.copy(denoise_coefficients)  # utils.py:165-170
+    if len(dns) < n_scales:
+        dns.extend([0, ] * (n_scales - len(dns)))
+    if len(dns) == n_scales:
+        dns.extend([1, ])
+
+    for s, (c, w, d) in enumerate(zip(planes, wts, dns)):  # utils.py:174-203
+        if s == n_scales:
+            if whitening:
+                local_power = np.std(c)
+                if local_power <= 0:
+                    local_power = 1e-15
+            else:
+                local_power = 1
+        else:
+            if whitening:
+                local_power = smooth(c ** 2, name, s, backend)  # plain smooth even if the transform was bilateral
+                local_power[local_power <= 0] = 1e-15
+                np.sqrt(local_power, out=local_power)
+            else:
+                local_power = 1
+            if d != 0 and noise is None:
+                noise = get_noise(planes, name, sigma_bilateral)
+            c *= significance(planes, name, d, s, noise, sigma_bilateral, soft_threshold)
+        c *= w * 1 / local_power
+    recon = np.sum(planes, axis=0)
+    return recon, planes, noise
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Monte-Carlo noise weights  (watroo/wavelets.py:221-229)
+# ---------------------------------------------------------------------------------------------------------------
+def compute_noise_weights(name: str, n_scales: int, n_trials: int = 100, bilateral=None, fields=None,
+                          backend: str | None = None) -> np.ndarray:
+    """Mean over trials of the per-plane population std of planes 0..n-1 of the transform of fp32 N(0,1) noise of
+    side len(sigma_e_1d)*2**n_scales.  ``fields`` (an iterable of ready-made fp32 noise images) replaces the global
+    NumPy RNG so that a test can feed identical fields to the GPU path."""
+    std = np.zeros(n_scales)
+    side = SIGMA_E_1D_LEN[name] * 2 ** n_scales
+    it = iter(fields) if fields is not None else None
+    for _ in range(n_trials):
+        field = next(it) if it is not None else np.random.normal(size=(side, side)).astype(np.float32)
+        planes = atrous_transform(field, n_scales, name, bilateral=bilateral, backend=backend)
+        std += planes[:-1].std(axis=(1, 2))
+    return std / n_trials
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Synthetic inputs and the parity metric shared by tests and bench  
+# ---------------------------------------------------------------------------------------------------------------
+def solar_like(n: int, seed: int = 2, flux: float = 1.0, dtype=np.float32, m: int | None = None) -> np.ndarray:
+    """Synthetic solar-like frame: limb-darkened disk + exponential off-limb corona + 30 Gaussian active regions
+    + background, Poisson noise.  Values are integers, hence identical in fp32 and fp64."""
+    m = n if m is None else m
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:n, 0:m].astype(np.float64)
+    scale = min(n, m)
+    r = np.hypot(x - m / 2, y - n / 2) / (0.4 * scale)
+    img = np.where(r < 1, 2000 * (0.4 + 0.6 * np.sqrt(np.clip(1 - r ** 2, 0, None))),
+                   800 * np.exp(-(np.clip(r, 1, None) - 1) / 0.15))
+    for _ in range(30):
+        cx, cy = rng.uniform(0.2 * m, 0.8 * m), rng.uniform(0.2 * n, 0.8 * n)
+        sg = rng.uniform(3, 30) * scale / 1024
+        amp = rng.uniform(500, 8000)
+        img += amp * np.exp(-((x - cx) ** 2 + (y - cy) ** 2) / (2 * sg ** 2))
+    img = (img + 20) * flux
+    return rng.poisson(img).astype(dtype)
+
+
+def emax(new: np.ndarray, ref: np.ndarray) -> float:
+    """Parity metric of SURVEY 8(d): max|new-ref| / max|ref| over one plane (never element-wise relative)."""
+    ref64 = np.asarray(ref, dtype=np.float64)
+    den = np.abs(ref64).max()
+    num = np.abs(np.asarray(new, dtype=np.float64) - ref64).max()
+    return float(num / den) if den > 0 else float(num)

@@ -1,0 +1,142 @@
+"""Generate tests/golden/*.npz by running the REAL reference (watroo 0.0.4 under /root/reference).
+
+Run here (the build container), never on the GPU box:   python tests/golden/make_golden.py
+Each .npz stores the exact inputs and the reference outputs, so the GPU tests need neither /root/reference nor a
+matching RNG.  numexpr is not installed in this image; its single call site is served by _numexpr_shim.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("WATROO_REFERENCE", "/root/reference")
+try:
+    import numexpr  # noqa: F401
+except ImportError:
+    sys.path.insert(0, os.path.join(HERE, "_numexpr_shim"))
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import watroo  # noqa: E402
+from watroo import AtrousTransform, B3spline, Triangle, denoise, wow  # noqa: E402
+from oracle.atrous_oracle import solar_like  # noqa: E402  (input generator only)
+
+SF = {"b3spline": B3spline, "triangle": Triangle}
+
+
+def gaussian(shape, seed, dtype):
+    return np.random.default_rng(seed).standard_normal(shape).astype(dtype)
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name:36s} {os.path.getsize(path) / 1024:8.1f} KiB")
+
+
+def main():
+    assert watroo.__version__ == "0.0.4", watroo.__version__
+    warnings.simplefilter("ignore")
+
+    # ---- plain transform: wavelets.py:408-444 via :307 ------------------------------------------------------
+    cases = [((64, 64), 4), ((37, 53), 4), ((6, 7), 3), ((96, 64), 6), ((24, 256), 5)]
+    for sf in SF:
+        for dt in ("float32", "float64"):
+            out = {}
+            for k, (shape, level) in enumerate(cases):
+                img = gaussian(shape, k, dt) * 3 + 10
+                out[f"in{k}"] = img
+                out[f"out{k}"] = AtrousTransform(SF[sf])(img, level).data
+                out[f"level{k}"] = np.int64(level)
+            save(f"transform_{sf}_{dt}", n=np.int64(len(cases)), **out)
+
+    # integer input is recast to float64 (wavelets.py:297,319-320)
+    img = (gaussian((32, 48), 7, "float64") * 100).astype(np.int16)
+    save("transform_int16", img=img, out=AtrousTransform(B3spline)(img, 3).data)
+
+    # known-answer test of the reference's own suite (tests/test_wavelets.py:8-13)
+    ones = np.ones((128, 128))
+    save("kat_ones", out=AtrousTransform()(ones, 4).data)
+
+    # ---- bilateral transform: wavelets.py:433-440, :24-32, :74-105 -------------------------------------------
+    for dt in ("float32", "float64"):
+        out = {}
+        img = solar_like(64, seed=3, flux=0.05, dtype=dt)
+        out["in_solar"] = img
+        out["solar_b1"] = AtrousTransform(B3spline, bilateral=1)(img, 4).data
+        out["solar_tri_b2"] = AtrousTransform(Triangle, bilateral=2.0)(img, 3).data
+        img = gaussian((48, 80), 5, dt)
+        out["in_gauss"] = img
+        out["gauss_list_scaling"] = AtrousTransform(B3spline, bilateral=[2, 1.5], bilateral_scaling=True)(img, 4).data
+        save(f"bilateral_{dt}", **out)
+
+    # ---- denoise / significance: wavelets.py:126-149, utils.py:83-102 ---------------------------------------
+    np.random.seed(0)
+    img = np.random.normal(size=(512, 512))  # README.md:37-51 (cfg1)
+    co = AtrousTransform(Triangle)(img, 2)
+    raw = co.data.copy()
+    hard = co.significance(3, 1, soft_threshold=False)
+    noise = np.float64(co.noise)
+    co.denoise([5, 3])
+    den = denoise(img, [5, 3], Triangle)
+    assert np.array_equal(den, co.data.sum(axis=0)) and np.array_equal(den, np.sum(co, axis=0))
+    save("cfg1_denoise_triangle_512", seed=np.int64(0), noise=noise, raw_sub=raw[:, ::4, ::4],
+         hard_sub=hard[::4, ::4], hard_count=np.int64(hard.sum()), out_sub=den[::4, ::4],
+         out_sum=np.float64(den.sum()), out_abs_sum=np.float64(np.abs(den).sum()))
+
+    for dt in ("float32", "float64"):
+        out = {}
+        img = gaussian((96, 128), 11, dt) + 0.02 * np.arange(128, dtype=dt)[None, :]
+        out["img"] = img
+        for sf in SF:
+            co = AtrousTransform(SF[sf])(img, 3)
+            out[f"{sf}_noise"] = np.float64(co.get_noise())
+            out[f"{sf}_soft2"] = co.significance(2.5, 2)
+            out[f"{sf}_hard0"] = co.significance(3, 0, soft_threshold=False)
+            out[f"{sf}_den_soft"] = denoise(img, [5, 3, 2], SF[sf])
+            out[f"{sf}_den_hard"] = denoise(img, [4, 3, 0], SF[sf], soft_threshold=False)
+            out[f"{sf}_den_noise"] = denoise(img, [3, 2], SF[sf], noise=0.8)
+            out[f"{sf}_den_bilateral"] = denoise(img, [3, 2], SF[sf], bilateral=1)
+        save(f"denoise_{dt}", **out)
+
+    # ---- wow: utils.py:105-219 ---------------------------------------------------------------------------------
+    for dt in ("float32", "float64"):
+        out = {}
+        for tag, img in (("gauss", gaussian((64, 64), 21, dt) * 5 + 50),
+                         ("solar", solar_like(64, seed=2, flux=0.01, dtype=dt)),
+                         ("rect", solar_like(48, seed=4, flux=0.05, dtype=dt, m=80))):
+            out[f"{tag}_in"] = img
+            for key, kw in (("default", {}),
+                            ("den", dict(denoise_coefficients=[5, 2])),
+                            ("den_hard", dict(denoise_coefficients=[5, 2], soft_threshold=False)),
+                            ("bil", dict(bilateral=1)),
+                            ("bil_den", dict(bilateral=1, denoise_coefficients=[5, 2])),
+                            ("weights", dict(weights=[0.5, 2.0, 1.5], n_scales=3)),
+                            ("nowhite", dict(whitening=False, denoise_coefficients=[3, 1], noise=1.3)),
+                            ("tri", dict(scaling_function=Triangle, denoise_coefficients=[0, 3]))):
+                if tag == "rect" and key not in ("default", "bil_den"):
+                    continue
+                recon, co = wow(img.copy(), **kw)
+                out[f"{tag}_{key}_recon"] = recon
+                if key in ("default", "den_hard", "bil_den", "tri"):
+                    out[f"{tag}_{key}_planes"] = co.data
+                out[f"{tag}_{key}_noise"] = np.float64(np.nan if co.noise is None else co.noise)
+        save(f"wow_{dt}", **out)
+
+    # ---- compute_noise_weights: wavelets.py:221-229 -------------------------------------------------------------
+    for sf in SF:
+        np.random.seed(5)
+        side = 11 * 2 ** 3
+        state = np.random.get_state()
+        fields = np.stack([np.random.normal(size=(side, side)).astype(np.float32) for _ in range(2)])
+        np.random.set_state(state)
+        import watroo.wavelets as ww
+        ww.tqdm = lambda it: it  # silence the progress bar
+        out = SF[sf](2).compute_noise_weights(3, n_trials=2)
+        save(f"noise_weights_{sf}", fields=fields, out=out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,216 @@
+"""Pins oracle/atrous_oracle.py against vectors produced by the real reference (tests/golden/make_golden.py),
+the reference's own known-answer test and the identities listed in SURVEY.md section 4.  CPU only."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import atrous_oracle as orc
+from tests.conftest import load_golden
+
+BACKENDS = ["numpy"] + (["cv2"] if orc.cv2 is not None else [])
+TOL = {"float32": 1e-5, "float64": 1e-13}  # north_star E_max tolerances; the cv2 backend must be bit-identical
+
+
+def check(new, ref, dt, backend, exact_with_cv2=True, scale=0.0):
+    """Per plane: max|new-ref| <= max(TOL*max|ref_p|, 4*eps*scale).  The second term is the rounding floor of the
+    fp32 data itself (w_s = c_s - c_{s+1} carries a few ulp of c_s, whatever the size of w_s)."""
+    assert new.dtype == ref.dtype and new.shape == ref.shape
+    if backend == "cv2" and exact_with_cv2:
+        assert np.array_equal(new, ref)
+    else:
+        floor = 4 * np.finfo(ref.dtype).eps * scale
+        for p in range(new.shape[0]) if new.ndim == 3 else [None]:
+            a, b = (new, ref) if p is None else (new[p], ref[p])
+            err = np.abs(a.astype(np.float64) - b).max()
+            assert err <= max(TOL[dt] * np.abs(b).max(), floor), (p, err, np.abs(b).max())
+
+
+def test_reflect_index_matches_np_pad_symmetric():
+    for n in (1, 2, 5, 8):
+        base = np.arange(n)
+        padded = np.pad(base, (3 * n + 1, 3 * n + 2), mode="symmetric")
+        idx = np.arange(-(3 * n + 1), n + 3 * n + 2)
+        assert np.array_equal(orc.reflect_index(idx, n), padded)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+@pytest.mark.parametrize("sf", ["b3spline", "triangle"])
+def test_transform_golden(sf, dt, backend):
+    g = load_golden(f"transform_{sf}_{dt}")
+    for k in range(int(g["n"])):
+        img = g[f"in{k}"]
+        keep = img.copy()
+        out = orc.atrous_transform(img, int(g[f"level{k}"]), sf, backend=backend)
+        assert np.array_equal(img, keep)  # input never modified (wavelets.py:427)
+        check(out, g[f"out{k}"], dt, backend, scale=np.abs(img).max())
+        # perfect reconstruction
+        assert orc.emax(out.sum(axis=0), img) < (1e-5 if dt == "float32" else 1e-13)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_integer_input_is_recast_to_float64(backend):
+    g = load_golden("transform_int16")
+    out = orc.atrous_transform(g["img"], 3, "b3spline", backend=backend)
+    assert out.dtype == np.float64
+    check(out, g["out"], "float64", backend)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_reference_kat_constant_image(backend):
+    """tests/test_wavelets.py:8-13 of the reference: ones -> zero detail planes, unit residual."""
+    out = orc.atrous_transform(np.ones((128, 128)), 4, "b3spline", backend=backend)
+    expected = np.zeros(out.shape)
+    expected[-1] = 1
+    assert np.isclose(out, expected).all()
+    assert np.isclose(load_golden("kat_ones")["out"], expected).all()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+def test_bilateral_golden(dt, backend):
+    g = load_golden(f"bilateral_{dt}")
+    tol = 5e-5 if dt == "float32" else 1e-11  # exp() ulp differences get amplified by the fp32 variance
+    cases = [("in_solar", "solar_b1", dict(level=4, name="b3spline", bilateral=1)),
+             ("in_solar", "solar_tri_b2", dict(level=3, name="triangle", bilateral=2.0)),
+             ("in_gauss", "gauss_list_scaling", dict(level=4, name="b3spline", bilateral=[2, 1.5],
+                                                     bilateral_scaling=True))]
+    for src, key, kw in cases:
+        out = orc.atrous_transform(g[src], backend=backend, **kw)
+        ref = g[key]
+        assert out.dtype == ref.dtype
+        for p in range(len(ref)):
+            assert orc.emax(out[p], ref[p]) <= tol, (key, p, orc.emax(out[p], ref[p]))
+
+
+def test_cfg1_readme_denoise():
+    """README.md:37-61 (BASELINE configs[0]): Triangle, 512x512 np.random.normal, denoise([5, 3])."""
+    g = load_golden("cfg1_denoise_triangle_512")
+    np.random.seed(int(g["seed"]))
+    img = np.random.normal(size=(512, 512))
+    for backend in BACKENDS:
+        planes = orc.atrous_transform(img, 2, "triangle", backend=backend)
+        assert orc.emax(planes[:, ::4, ::4], g["raw_sub"]) < 1e-13
+        noise = orc.get_noise(planes, "triangle")
+        assert abs(noise - float(g["noise"])) <= 1e-13 * float(g["noise"])
+        hard = orc.significance(planes, "triangle", 3, 1, noise, soft_threshold=False)
+        assert hard.dtype == np.bool_ and int(hard.sum()) == int(g["hard_count"])
+        assert np.array_equal(hard[::4, ::4], g["hard_sub"])
+        den = orc.denoise(img, [5, 3], "triangle", backend=backend)
+        assert orc.emax(den[::4, ::4], g["out_sub"]) < 1e-13
+        assert abs(den.sum() - float(g["out_sum"])) < 1e-8
+        # README equivalences: np.sum(coefficients, axis=0) == data.sum(axis=0) == denoise(...)
+        orc.denoise_planes(planes, "triangle", [5, 3])
+        assert np.array_equal(planes.sum(axis=0), den)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+def test_denoise_and_significance_golden(dt, backend):
+    g = load_golden(f"denoise_{dt}")
+    img = g["img"]
+    for sf in ("b3spline", "triangle"):
+        planes = orc.atrous_transform(img, 3, sf, backend=backend)
+        noise = orc.get_noise(planes, sf)
+        assert isinstance(noise, np.float64)  # NEP-50 promotion
+        assert abs(noise - float(g[f"{sf}_noise"])) <= (2e-6 if dt == "float32" else 1e-13) * noise
+        soft = orc.significance(planes, sf, 2.5, 2, noise)
+        assert soft.dtype == np.float64 == g[f"{sf}_soft2"].dtype
+        assert np.abs(soft - g[f"{sf}_soft2"]).max() < (1e-4 if dt == "float32" else 1e-11)
+        hard = orc.significance(planes, sf, 3, 0, noise, soft_threshold=False)
+        assert hard.dtype == np.bool_
+        if backend == "cv2":
+            assert np.array_equal(hard, g[f"{sf}_hard0"])
+        else:  # a 1-ulp difference in w_0 may flip a pixel sitting on the threshold
+            assert (hard != g[f"{sf}_hard0"]).mean() < 1e-3
+        for key, kw in (("den_soft", dict(weights=[5, 3, 2])),
+                        ("den_hard", dict(weights=[4, 3, 0], soft_threshold=False)),
+                        ("den_noise", dict(weights=[3, 2], noise=0.8)),
+                        ("den_bilateral", dict(weights=[3, 2], bilateral=1))):
+            out = orc.denoise(img, name=sf, backend=backend, **kw)
+            ref = g[f"{sf}_{key}"]
+            assert out.dtype == ref.dtype
+            if key == "den_hard" and backend != "cv2":
+                assert (np.abs(out - ref) > 1e-5 * np.abs(ref).max()).mean() < 1e-3
+            else:
+                tol = (5e-5 if key == "den_bilateral" else 2e-6) if dt == "float32" else 1e-11
+                assert orc.emax(out, ref) <= tol, (sf, key, orc.emax(out, ref))
+
+
+WOW_CASES = {
+    "default": {},
+    "den": dict(denoise_coefficients=[5, 2]),
+    "den_hard": dict(denoise_coefficients=[5, 2], soft_threshold=False),
+    "bil": dict(bilateral=1),
+    "bil_den": dict(bilateral=1, denoise_coefficients=[5, 2]),
+    "weights": dict(weights=[0.5, 2.0, 1.5], n_scales=3),
+    "nowhite": dict(whitening=False, denoise_coefficients=[3, 1], noise=1.3),
+    "tri": dict(name="triangle", denoise_coefficients=[0, 3]),
+}
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+def test_wow_golden(dt, backend):
+    g = load_golden(f"wow_{dt}")
+    for tag in ("gauss", "solar", "rect"):
+        img = g[f"{tag}_in"]
+        for key, kw in WOW_CASES.items():
+            if f"{tag}_{key}_recon" not in g:
+                continue
+            recon, planes, noise = orc.wow(img.copy(), backend=backend, **kw)
+            ref = g[f"{tag}_{key}_recon"]
+            assert recon.dtype == ref.dtype and recon.shape == ref.shape
+            bil = "bil" in key
+            if dt == "float64":
+                tol = 1e-9 if bil else 1e-11
+            else:
+                tol = 2e-3 if bil else 2e-5
+            if key == "den_hard" and backend != "cv2":
+                assert (np.abs(recon - ref) > tol * np.abs(ref).max()).mean() < 2e-3
+            else:
+                assert orc.emax(recon, ref) <= tol, (tag, key, orc.emax(recon, ref))
+            ref_noise = float(g[f"{tag}_{key}_noise"])
+            if np.isnan(ref_noise):
+                assert noise is None
+            else:
+                assert abs(noise - ref_noise) <= (1e-4 if dt == "float32" else 1e-11) * abs(ref_noise)
+            if f"{tag}_{key}_planes" in g and not (key == "den_hard" and backend != "cv2"):
+                rp = g[f"{tag}_{key}_planes"]
+                assert planes.shape == rp.shape
+                for p in range(len(rp)):
+                    assert orc.emax(planes[p], rp[p]) <= tol * 10, (tag, key, p, orc.emax(planes[p], rp[p]))
+
+
+def test_wow_scale_count_logic():
+    assert orc.wow_default_scales((4096, 4096), "b3spline") == 10  # utils.py:122 at BASELINE's size
+    assert orc.wow_default_scales((4096, 4096), "triangle") == 10
+    assert orc.wow_default_scales((512, 512), "b3spline") == 7
+    img = np.random.default_rng(0).standard_normal((64, 64))
+    _, planes, _ = orc.wow(img, n_scales=50, backend="numpy")  # clipped to the default (utils.py:125-126)
+    assert len(planes) == orc.wow_default_scales(img.shape, "b3spline") + 1
+    with warnings.catch_warnings(record=True) as rec:  # utils.py:135-138
+        warnings.simplefilter("always")
+        _, planes, _ = orc.wow(np.ones((16, 16)) + img[:16, :16], denoise_coefficients=[0] * 11, noise=1.0,
+                               backend="numpy")
+    assert len(planes) == 12 and any("lager" in str(w.message) for w in rec)
+
+
+@pytest.mark.parametrize("sf", ["b3spline", "triangle"])
+def test_noise_weights_golden_and_tables(sf):
+    g = load_golden(f"noise_weights_{sf}")
+    out = orc.compute_noise_weights(sf, 3, n_trials=2, fields=g["fields"])
+    assert np.abs(out / g["out"] - 1).max() < 1e-6
+    # statistical KAT: the recorded sigma_e_2d table (wavelets.py:245-247, :274-276), 2 trials of 88x88
+    assert np.abs(out / orc.SIGMA_E_2D[sf][:3] - 1).max() < 0.08
+
+
+def test_backends_agree_fp64():
+    if orc.cv2 is None:
+        pytest.skip("OpenCV not installed")
+    img = orc.solar_like(96, seed=1, flux=1.0, dtype=np.float64)
+    a = orc.atrous_transform(img, 5, "b3spline", backend="numpy")
+    b = orc.atrous_transform(img, 5, "b3spline", backend="cv2")
+    for p in range(6):
+        assert orc.emax(a[p], b[p]) < 1e-13
