@@ -1,0 +1,83 @@
+"""ctypes binding of libwavelets_b200.so (the C ABI of include/wavelets_b200.h).
+
+There is deliberately NO fallback: if the CUDA library cannot be loaded, or no CUDA device is present, every
+operation raises.  torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libwavelets_b200.so")
+
+WB_F32, WB_F64 = 0, 1
+WB_TRIANGLE, WB_B3SPLINE = 3, 5
+ABI_VERSION = 1
+
+_lock = threading.Lock()
+_lib = None
+
+_c_int, _c_ll, _c_vp, _c_dbl = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_double
+
+# name -> (restype, argtypes); must list every symbol declared in include/wavelets_b200.h
+SIGNATURES = {
+    "wb_abi_version": (_c_int, []),
+    "wb_error_string": (ctypes.c_char_p, [_c_int]),
+    "wb_atrous_scale_path": (_c_int, [_c_int, _c_int, _c_ll, _c_ll, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
+    "wb_atrous_scale": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll, _c_ll,
+                                 _c_ll, _c_int, _c_int, _c_int, _c_vp]),
+    "wb_atrous_transform": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_int, _c_int,
+                                     _c_int, _c_vp]),
+}
+# development hooks exported by the library but not part of the stable ABI
+_EXTRA = {
+    "wb_tune_k1": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int]),
+}
+
+
+def load(require_cuda: bool = False) -> ctypes.CDLL:
+    """Load the shared library (once).  Raises RuntimeError when it is missing -- there is no CPU path."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -m wavelets_b200.build` "
+                    "(wavelets_b200 has no CPU fallback)")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in {**SIGNATURES, **_EXTRA}.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            if lib.wb_abi_version() != ABI_VERSION:
+                raise RuntimeError("libwavelets_b200.so ABI version mismatch; rebuild it")
+            _lib = lib
+    if require_cuda and not torch.cuda.is_available():
+        raise RuntimeError("wavelets_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().wb_error_string(status).decode()
+        raise RuntimeError(f"wavelets_b200: {msg} (status {status})")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return WB_F32
+    if dtype == torch.float64:
+        return WB_F64
+    raise TypeError(f"wavelets_b200 computes in float32 or float64, got {dtype}")
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def np_to_torch_dtype(dt: np.dtype) -> torch.dtype:
+    return {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dt)]

@@ -1,0 +1,128 @@
+// Shared device/host helpers for the sm_100a à trous kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/wavelets_b200.h"
+
+namespace wb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// 16-byte vectors: 4 x fp32 or 2 x fp64.  Every thread of the row-pipeline kernels owns whole vectors of columns so
+// that shared-memory reads are LDS.128 and global stores are STG.128.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int V = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int V = 2; };
+
+template <typename T, int V> struct Pack { T v[V]; };
+
+__device__ __forceinline__ Pack<float, 4> ld_vec(const float *p) {
+    float4 t = *reinterpret_cast<const float4 *>(p);
+    Pack<float, 4> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+__device__ __forceinline__ Pack<double, 2> ld_vec(const double *p) {
+    double2 t = *reinterpret_cast<const double2 *>(p);
+    Pack<double, 2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
+}
+__device__ __forceinline__ void st_vec(float *p, const Pack<float, 4> &r) {
+    *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+}
+__device__ __forceinline__ void st_vec(double *p, const Pack<double, 2> &r) {
+    *reinterpret_cast<double2 *>(p) = make_double2(r.v[0], r.v[1]);
+}
+// Streaming (evict-first) 128-bit global store: planes that nobody re-reads soon (w_s) should not displace the
+// running smooth plane c_{s+1} from L2.
+__device__ __forceinline__ void st_vec_cs(float *p, const Pack<float, 4> &r) {
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+}
+__device__ __forceinline__ void st_vec_cs(double *p, const Pack<double, 2> &r) {
+    __stcs(reinterpret_cast<double2 *>(p), make_double2(r.v[0], r.v[1]));
+}
+
+// Half-sample symmetric reflection into [0, n), any number of reflections (cv2.BORDER_REFLECT, np.pad 'symmetric').
+__host__ __device__ __forceinline__ int reflect_any(long long i, int n) {
+    long long period = 2LL * n;
+    long long m = i % period;
+    if (m < 0) m += period;
+    return (int)(m < n ? m : period - 1 - m);
+}
+
+template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
+template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
+
+// Filter taps (watroo/wavelets.py:239 Triangle, :268 B3spline); dyadic rationals, exact in fp32.
+template <typename T, int TAPS> struct Taps;
+template <typename T> struct Taps<T, 3> {
+    __host__ __device__ static constexpr T h(int k) { return k == 1 ? T(0.5) : T(0.25); }
+};
+template <typename T> struct Taps<T, 5> {
+    __host__ __device__ static constexpr T h(int k) {
+        return k == 2 ? T(0.375) : ((k == 1 || k == 3) ? T(0.25) : T(0.0625));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier + TMA bulk-copy PTX (sm_90+; on sm_100a the copy shows up in SASS as UBLKCP)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WB_DONE_%=;\n"
+        "bra WB_WAIT_%=;\n"
+        "WB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk asynchronous copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, both 16B aligned).
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------------
+inline int dtype_size(int dtype) { return dtype == WB_F32 ? 4 : (dtype == WB_F64 ? 8 : 0); }
+
+inline int check_common(int batch, int H, int W, int taps, int dtype) {
+    if (dtype != WB_F32 && dtype != WB_F64) return WB_EINVAL_DTYPE;
+    if (taps != WB_TRIANGLE && taps != WB_B3SPLINE) return WB_EINVAL_TAPS;
+    if (batch < 1 || H < 1 || W < 1 || batch > 65535) return WB_EINVAL_SHAPE;
+    return WB_OK;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Launch-time error check that does not synchronise.
+inline int launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return (int)e;
+}
+
+}  // namespace wb
