@@ -23,6 +23,8 @@
 #ifndef WAVELETS_B200_H
 #define WAVELETS_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -76,6 +78,91 @@ int wb_atrous_scale(const void *in, void *out_c, void *out_w, int batch, int H, 
  */
 int wb_atrous_transform(const void *in, void *planes, void *scratch, int batch, int H, int W,
                         long long in_pitch, long long in_bstride, int levels, int taps, int dtype, void *stream);
+
+/*
+ * One scale of the BILATERAL cascade.  Replaces, per scale, watroo/wavelets.py:433-442: sdev_loc (:24-32), the
+ * variance scaling (:434-436), atrous_convolution(..., bilateral_variance) (:74-105) and the subtraction (:442):
+ *     var = S[in^2] - S[in]^2 (<= 0 -> 1e-20),  V = var * var_factor,  var_factor = sigma_b[s]^2 * (s+1 | 1)
+ *     out_c = (k_c x + sum_t k_t exp(-(x - x_t)^2 / V / 2) x_t) / (k_c + sum_t k_t exp(...)),   out_w = in - out_c
+ * Same pointer rules as wb_atrous_scale.
+ */
+int wb_atrous_scale_bilateral(const void *in, void *out_c, void *out_w, int batch, int H, int W,
+                              long long in_pitch, long long in_bstride,
+                              long long out_c_pitch, long long out_c_bstride,
+                              long long out_w_pitch, long long out_w_bstride,
+                              int scale, int taps, int dtype, double var_factor, void *stream);
+
+/*
+ * WOW whitening of one detail plane.  Replaces the body of the per-scale loop of watroo/utils.py:177,193-203:
+ *     P   = S_scale[w_raw^2] (plain smooth, never bilateral; <= 0 -> 1e-15),  lp = sqrt(P)
+ *     out = w_raw * significance(w_raw) * (weight / lp)
+ * significance (watroo/wavelets.py:129-143): sig_mode 0 -> 1; 1 -> erf(|w / thr|); 2 -> (|w| > thr), with
+ * thr = (sigma * noise) * sigma_e and noise read from `noise_dev[frame]` (device, e.g. written by wb_abs_median)
+ * when non-NULL, else `noise_host`; noise == 0 -> 1.  `out` must not alias `w_raw`.
+ */
+int wb_wow_whiten_scale(const void *w_raw, void *out, int batch, int H, int W,
+                        long long in_pitch, long long in_bstride, long long out_pitch, long long out_bstride,
+                        int scale, int taps, int dtype, int sig_mode, double sigma, double sigma_e,
+                        double noise_host, const double *noise_dev, double weight, void *stream);
+
+/*
+ * Exact median of |x| over n contiguous elements per frame, on the device and without host synchronisation.
+ * Replaces np.median(np.abs(data[0])) of Coefficients.get_noise (watroo/wavelets.py:126-127); bit-identical to
+ * np.median (mean of the two middle values, in the plane dtype).  `out_median` (dtype of x, one per frame) and/or
+ * `out_noise` (float64, one per frame: (median / 0.6745 in the plane dtype) / sigma_e0 in float64, i.e. get_noise
+ * under NumPy >= 2) are written.  `workspace`: wb_abs_median_workspace_bytes(dtype, batch) bytes of device memory.
+ */
+size_t wb_abs_median_workspace_bytes(int dtype, int batch);
+int wb_abs_median(const void *x, long long n, int batch, long long bstride, int dtype, void *out_median,
+                  double *out_noise, double sigma_e0, void *workspace, void *stream);
+
+/*
+ * Population moments of n contiguous elements per frame: out[frame] = {mean, variance, std} (float64).
+ * Replaces np.std(c) (watroo/utils.py:187) and data[:-1].std(axis=(1,2)) (watroo/wavelets.py:227).
+ * `workspace`: wb_plane_moments_workspace_bytes(batch) bytes.
+ */
+size_t wb_plane_moments_workspace_bytes(int batch);
+int wb_plane_moments(const void *x, long long n, int batch, long long bstride, int dtype, double *out,
+                     void *workspace, void *stream);
+
+/*
+ * Significance map of one plane (Coefficients.significance, watroo/wavelets.py:129-143).
+ * soft != 0: out is float64[n] = erf(|w / thr|); soft == 0: out is uint8[n] = (|w| > thr).
+ * thr = (sigma * noise) * sigma_e; noise = *noise_dev if non-NULL else noise_host, or a per-pixel `noise_map`
+ * (dtype of w) if non-NULL.  Scalar noise == 0 -> all ones.
+ */
+int wb_significance(const void *w, long long n, int dtype, double sigma, double sigma_e, double noise_host,
+                    const double *noise_dev, const void *noise_map, int soft, void *out, void *stream);
+
+/*
+ * In-place denoise of one plane per frame: w <- dtype(float64(w) * (weight * significance(w))), the statement
+ * `c *= wgt * self.significance(sig, scl)` of Coefficients.denoise (watroo/wavelets.py:145-149).
+ * sig_mode as in wb_wow_whiten_scale (0 multiplies by `weight` only).
+ */
+int wb_denoise_plane(void *w, long long n, int batch, long long bstride, int dtype, int sig_mode, double sigma,
+                     double sigma_e, double noise_host, const double *noise_dev, const void *noise_map,
+                     double weight, void *stream);
+
+/*
+ * Residual plane of WOW: c <- c * dtype(weight / std), std = moments[frame][2] rounded to the plane dtype,
+ * non-positive -> 1e-15 (watroo/utils.py:185-189, :203).
+ */
+int wb_residual_rescale(void *c, long long n, int batch, long long bstride, int dtype, const double *moments,
+                        double weight, void *stream);
+
+/*
+ * Synthesis: out = ((p_0 + p_1) + p_2) + ... over `nplanes` planes `plane_stride` elements apart, in the plane
+ * dtype and in plane order -- np.sum(coefficients, axis=0) (watroo/utils.py:98, :205).
+ */
+int wb_synthesis(const void *planes, int nplanes, long long plane_stride, long long n, int batch,
+                 long long in_bstride, void *out, long long out_bstride, int dtype, void *stream);
+
+/*
+ * n standard-normal float32 samples (Philox4x32-10 + Box-Muller), the device stand-in for
+ * np.random.normal(...).astype(np.float32) of compute_noise_weights (watroo/wavelets.py:225).
+ * `offset` advances the counter so that successive calls with one seed give independent fields.
+ */
+int wb_randn_f32(float *out, long long n, unsigned long long seed, unsigned long long offset, void *stream);
 
 #ifdef __cplusplus
 }

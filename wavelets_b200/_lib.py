@@ -23,6 +23,7 @@ _lock = threading.Lock()
 _lib = None
 
 _c_int, _c_ll, _c_vp, _c_dbl = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_double
+_c_ull, _c_sz = ctypes.c_ulonglong, ctypes.c_size_t
 
 # name -> (restype, argtypes); must list every symbol declared in include/wavelets_b200.h
 SIGNATURES = {
@@ -33,6 +34,20 @@ SIGNATURES = {
                                  _c_ll, _c_int, _c_int, _c_int, _c_vp]),
     "wb_atrous_transform": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_int, _c_int,
                                      _c_int, _c_vp]),
+    "wb_atrous_scale_bilateral": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll,
+                                           _c_ll, _c_ll, _c_int, _c_int, _c_int, _c_dbl, _c_vp]),
+    "wb_wow_whiten_scale": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll, _c_int, _c_int,
+                                     _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_vp, _c_dbl, _c_vp]),
+    "wb_abs_median_workspace_bytes": (_c_sz, [_c_int, _c_int]),
+    "wb_abs_median": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_int, _c_vp, _c_vp, _c_dbl, _c_vp, _c_vp]),
+    "wb_plane_moments_workspace_bytes": (_c_sz, [_c_int]),
+    "wb_plane_moments": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_int, _c_vp, _c_vp, _c_vp]),
+    "wb_significance": (_c_int, [_c_vp, _c_ll, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_vp, _c_vp, _c_int, _c_vp, _c_vp]),
+    "wb_denoise_plane": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_vp, _c_vp,
+                                  _c_dbl, _c_vp]),
+    "wb_residual_rescale": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_int, _c_vp, _c_dbl, _c_vp]),
+    "wb_synthesis": (_c_int, [_c_vp, _c_int, _c_ll, _c_ll, _c_int, _c_ll, _c_vp, _c_ll, _c_int, _c_vp]),
+    "wb_randn_f32": (_c_int, [_c_vp, _c_ll, _c_ull, _c_ull, _c_vp]),
 }
 # development hooks exported by the library but not part of the stable ABI
 _EXTRA = {

@@ -19,87 +19,50 @@
 //     coalesced stores (w_s with an evict-first hint so it does not push c_{s+1} out of L2 before scale s+1 reads it).
 //   * Anything the vector path cannot take (W % V != 0, unaligned pointers, 2^s*c > W so more than one reflection)
 //     goes to a generic gather kernel with the full modular reflection.
-#include "common.cuh"
+#include "pipeline.cuh"
 
 namespace wb {
 
-struct ScaleParams {
-    const void *in;
-    void *out_c;
-    void *out_w;
-    int H, W, d;
-    long long in_pitch, in_bstride, c_pitch, c_bstride, w_pitch, w_bstride;
-    int wt;          // strip width in elements (= consumer threads * V * NG)
-    int n_strips;    // column strips per row
-    int seg;         // chain rows produced per thread block
-    int n_seg;       // segments per chain
-    int slots;       // depth of the shared-memory row ring
-    int row_stride;  // elements per ring slot
-    int halo_al;     // x halo kept in shared memory on each side of a strip (multiple of V)
+// Whitening of one coefficient (watroo/utils.py:195-203 + watroo/wavelets.py:129-143), P = S_s[w^2] at that pixel.
+template <typename T> struct WhitenEpilogue {
+    int mode;
+    double thr;  // (sigma * noise) * sigma_e
+    T thr_t;
+    T weight;
+    __device__ __forceinline__ void init(const ScaleParams &p, int frame) {
+        mode = p.sig_mode;
+        thr = 0.0;
+        if (mode) {
+            const double noise = p.noise_dev ? p.noise_dev[frame] : p.noise_host;
+            if (noise == 0.0) mode = 0;  // scalar noise == 0 -> significance is all ones (wavelets.py:134-135)
+            thr = (p.sigma * noise) * p.sigma_e;
+        }
+        thr_t = (T)thr;
+        weight = (T)p.weight;
+    }
+    __device__ __forceinline__ T apply(T w, T power) const {
+        if (power <= T(0)) power = T(1e-15);
+        const T lp = sqrt(power);
+        if (mode == 1) {
+            if constexpr (sizeof(T) == 4) {
+                // the reference multiplies by erf() evaluated in float64 and rounds the product to fp32; erff on
+                // the fp32 ratio differs from that by a few fp32 ulp of the product
+                w = w * erff(fabsf(w / thr_t));
+            } else {
+                w = w * erf(fabs(w / thr));
+            }
+        } else if (mode == 2) {
+            w = (fabs((double)w) > thr) ? w : T(0);  // compared in float64 like NumPy >= 2 does
+        }
+        return w * (weight / lp);
+    }
 };
 
-// Load the V-wide aligned vector of columns starting at logical column p (p % V == 0, -W <= p < 2W) of the staged
-// row `srow` (which holds global columns [lo, hi)), through the symmetric border.
-template <typename T, int V>
-__device__ __forceinline__ Pack<T, V> load_tap(const T *srow, int p, int W, int lo) {
-    const bool left = p < 0, right = p >= W;
-    const int q = left ? (-V - p) : (right ? (2 * W - V - p) : p);
-    Pack<T, V> t = ld_vec(srow + (q - lo));
-    if (left || right) {
-#pragma unroll
-        for (int e = 0; e < V / 2; ++e) {
-            T a = t.v[e];
-            t.v[e] = t.v[V - 1 - e];
-            t.v[V - 1 - e] = a;
-        }
-    }
-    return t;
-}
-
-// Row pass for one vector of columns starting at x.  DMODE == 0: d % V == 0, taps are whole aligned vectors.
-// DMODE == d in {1, 2}: d < V, all taps lie in the previous/current/next vector.  SQUARE: filter the squares.
-template <typename T, int TAPS, int DMODE, bool SQUARE>
-__device__ __forceinline__ Pack<T, VecOf<T>::V> row_pass(const T *srow, int x, int d, int W, int lo) {
+template <typename T, int TAPS, int DMODE, int NG, int OP>
+__global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
     constexpr int V = VecOf<T>::V;
     constexpr int C = TAPS / 2;
-    Pack<T, V> acc;
-    if constexpr (DMODE == 0) {
-#pragma unroll
-        for (int k = 0; k < TAPS; ++k) {
-            Pack<T, V> t = load_tap<T, V>(srow, x + (k - C) * d, W, lo);
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-                T v = SQUARE ? t.v[e] * t.v[e] : t.v[e];
-                acc.v[e] = (k == 0) ? Taps<T, TAPS>::h(0) * v : fma_t<T>(Taps<T, TAPS>::h(k), v, acc.v[e]);
-            }
-        }
-    } else {
-        T win[3 * V];
-        Pack<T, V> a = load_tap<T, V>(srow, x - V, W, lo);
-        Pack<T, V> b = load_tap<T, V>(srow, x, W, lo);
-        Pack<T, V> c = load_tap<T, V>(srow, x + V, W, lo);
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-            win[e] = SQUARE ? a.v[e] * a.v[e] : a.v[e];
-            win[V + e] = SQUARE ? b.v[e] * b.v[e] : b.v[e];
-            win[2 * V + e] = SQUARE ? c.v[e] * c.v[e] : c.v[e];
-        }
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-#pragma unroll
-            for (int k = 0; k < TAPS; ++k) {
-                T v = win[V + e + (k - C) * DMODE];
-                acc.v[e] = (k == 0) ? Taps<T, TAPS>::h(0) * v : fma_t<T>(Taps<T, TAPS>::h(k), v, acc.v[e]);
-            }
-        }
-    }
-    return acc;
-}
-
-template <typename T, int TAPS, int DMODE, int NG>
-__global__ void __launch_bounds__(544, 1) atrous_rows_kernel(const ScaleParams p) {
-    constexpr int V = VecOf<T>::V;
-    constexpr int C = TAPS / 2;
+    constexpr int NV = PlanSize<TAPS, DMODE>::NV;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *rows = reinterpret_cast<T *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)p.slots * p.row_stride * sizeof(T));
@@ -163,12 +126,17 @@ __global__ void __launch_bounds__(544, 1) atrous_rows_kernel(const ScaleParams p
     if (out_c) out_c += (long long)frame * p.c_bstride;
     if (out_w) out_w += (long long)frame * p.w_bstride;
 
+    WhitenEpilogue<T> epi;
+    if constexpr (OP == OP_WHITEN) epi.init(p, frame);
+
     int xg[NG];
     bool act[NG];
+    TapPlan<NV> plan[NG];
 #pragma unroll
     for (int q = 0; q < NG; ++q) {
         xg[q] = x0 + (q * nt + tid) * V;
         act[q] = xg[q] < p.W;
+        plan[q] = make_tap_plan<V, NV>(act[q] ? xg[q] : x0, DMODE == 0 ? p.d : V, p.W, lo);
     }
 
     Pack<T, V> ring[TAPS][NG];
@@ -179,7 +147,9 @@ __global__ void __launch_bounds__(544, 1) atrous_rows_kernel(const ScaleParams p
 #pragma unroll
             for (int e = 0; e < V; ++e) ring[k][q].v[e] = T(0);
 
-    int slot = 0, cslot = 0, rslot = 0;  // slot of row j, of the centre row j-C, of the row being released
+    // first output row of this block and the per-row pointer increments
+    long long orow = (long long)r + (long long)i0 * p.d;
+    int slot = 0, cslot = 0;  // ring slot of row j and of the centre row j - C (the next one to be released)
     uint32_t parity = 0;
     for (int j = 0; j < n_load; ++j) {
         mbar_wait(&full[slot], parity);
@@ -191,11 +161,10 @@ __global__ void __launch_bounds__(544, 1) atrous_rows_kernel(const ScaleParams p
             for (int q = 0; q < NG; ++q) ring[k][q] = ring[k + 1][q];
 #pragma unroll
         for (int q = 0; q < NG; ++q)
-            if (act[q]) ring[TAPS - 1][q] = row_pass<T, TAPS, DMODE, false>(srow, xg[q], p.d, p.W, lo);
+            if (act[q]) ring[TAPS - 1][q] = row_pass<T, TAPS, DMODE, OP == OP_WHITEN>(srow, plan[q]);
 
         if (j >= 2 * C) {
-            const long long y = (long long)r + (long long)(i0 + j - 2 * C) * p.d;
-            const T *crow = rows + (size_t)cslot * p.row_stride;
+            const T *crow = rows + (size_t)cslot * p.row_stride - lo;
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
                 if (!act[q]) continue;
@@ -207,20 +176,27 @@ __global__ void __launch_bounds__(544, 1) atrous_rows_kernel(const ScaleParams p
                     for (int k = 1; k < TAPS; ++k) a = fma_t<T>(Taps<T, TAPS>::h(k), ring[k][q].v[e], a);
                     c.v[e] = a;
                 }
-                if (out_c) st_vec(out_c + y * p.c_pitch + xg[q], c);
-                if (out_w) {
-                    Pack<T, V> raw = ld_vec(crow + (xg[q] - lo));
+                if constexpr (OP == OP_TRANSFORM) {
+                    if (out_c) st_vec(out_c + orow * p.c_pitch + xg[q], c);
+                    if (out_w) {
+                        Pack<T, V> raw = ld_vec(crow + xg[q]);
 #pragma unroll
-                    for (int e = 0; e < V; ++e) raw.v[e] -= c.v[e];
-                    st_vec_cs(out_w + y * p.w_pitch + xg[q], raw);
+                        for (int e = 0; e < V; ++e) raw.v[e] -= c.v[e];
+                        st_vec_cs(out_w + orow * p.w_pitch + xg[q], raw);
+                    }
+                } else {
+                    Pack<T, V> raw = ld_vec(crow + xg[q]);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) raw.v[e] = epi.apply(raw.v[e], c.v[e]);
+                    st_vec_cs(out_w + orow * p.w_pitch + xg[q], raw);
                 }
             }
+            orow += p.d;
         }
         if (j >= C) {
             // the raw row j-C is not needed any more: hand its slot back to the producer
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[rslot]);
-            if (++rslot == p.slots) rslot = 0;
+            if (lane == 0) mbar_arrive(&empty[cslot]);
             if (++cslot == p.slots) cslot = 0;
         }
         if (++slot == p.slots) { slot = 0; parity ^= 1; }
@@ -228,7 +204,7 @@ __global__ void __launch_bounds__(544, 1) atrous_rows_kernel(const ScaleParams p
 }
 
 // Generic path: one thread per output pixel, full modular reflection, any shape / alignment.
-template <typename T, int TAPS>
+template <typename T, int TAPS, int OP>
 __global__ void __launch_bounds__(256) atrous_generic_kernel(const ScaleParams p) {
     constexpr int C = TAPS / 2;
     const long long n = (long long)p.H * p.W;
@@ -236,6 +212,8 @@ __global__ void __launch_bounds__(256) atrous_generic_kernel(const ScaleParams p
     const T *in = reinterpret_cast<const T *>(p.in) + (long long)frame * p.in_bstride;
     T *out_c = reinterpret_cast<T *>(p.out_c);
     T *out_w = reinterpret_cast<T *>(p.out_w);
+    WhitenEpilogue<T> epi;
+    if constexpr (OP == OP_WHITEN) epi.init(p, frame);
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (long long)gridDim.x * blockDim.x) {
         const int y = (int)(idx / p.W), x = (int)(idx % p.W);
@@ -246,103 +224,34 @@ __global__ void __launch_bounds__(256) atrous_generic_kernel(const ScaleParams p
 #pragma unroll
         for (int i = 0; i < TAPS; ++i) {
             const T *row = in + (long long)reflect_any((long long)y + (long long)(i - C) * p.d, p.H) * p.in_pitch;
-            T ra = Taps<T, TAPS>::h(0) * row[xs[0]];
+            T ra = T(0);
 #pragma unroll
-            for (int k = 1; k < TAPS; ++k) ra = fma_t<T>(Taps<T, TAPS>::h(k), row[xs[k]], ra);
+            for (int k = 0; k < TAPS; ++k) {
+                T v = row[xs[k]];
+                if (OP == OP_WHITEN) v = v * v;
+                ra = (k == 0) ? Taps<T, TAPS>::h(0) * v : fma_t<T>(Taps<T, TAPS>::h(k), v, ra);
+            }
             acc = (i == 0) ? Taps<T, TAPS>::h(0) * ra : fma_t<T>(Taps<T, TAPS>::h(i), ra, acc);
         }
-        if (out_c) out_c[(long long)frame * p.c_bstride + (long long)y * p.c_pitch + x] = acc;
-        if (out_w)
-            out_w[(long long)frame * p.w_bstride + (long long)y * p.w_pitch + x] = in[(long long)y * p.in_pitch + x] - acc;
+        const T raw = in[(long long)y * p.in_pitch + x];
+        if constexpr (OP == OP_TRANSFORM) {
+            if (out_c) out_c[(long long)frame * p.c_bstride + (long long)y * p.c_pitch + x] = acc;
+            if (out_w) out_w[(long long)frame * p.w_bstride + (long long)y * p.w_pitch + x] = raw - acc;
+        } else {
+            out_w[(long long)frame * p.w_bstride + (long long)y * p.w_pitch + x] = epi.apply(raw, acc);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Host: configuration and dispatch
+// Host: dispatch
 // ---------------------------------------------------------------------------------------------------------------
-struct K1Config { int nt, ng, slots, seg; };
+K1Config g_override[32];
+bool g_override_set[32];
 
-static K1Config g_override[32];
-static bool g_override_set[32];
-
-static constexpr int kMaxSmem = 227 * 1024;
-
-static int device_sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
-    return sms;
-}
-
-static int round_up(int a, int b) { return (a + b - 1) / b * b; }
-
-static bool fast_path_ok(const ScaleParams &p, int taps, int esize) {
-    const int V = 16 / esize;
-    const int c = taps / 2;
-    if (p.W % V || p.W < 8 * V) return false;
-    if ((long long)c * p.d > p.W) return false;  // more than one reflection in x
-    if (p.in_pitch % V || p.in_bstride % V || !aligned16(p.in)) return false;
-    if (p.out_c && (p.c_pitch % V || p.c_bstride % V || !aligned16(p.out_c))) return false;
-    if (p.out_w && (p.w_pitch % V || p.w_bstride % V || !aligned16(p.out_w))) return false;
-    return true;
-}
-
-// Fill in the strip/segment/ring geometry.  Returns false if no geometry fits in shared memory.
-static bool plan_fast(ScaleParams &p, int taps, int esize, int batch, int scale, K1Config *cfg_out) {
-    const int V = 16 / esize;
-    const int c = taps / 2;
-    K1Config cfg;
-    if (scale < 32 && g_override_set[scale]) {
-        cfg = g_override[scale];
-    } else {
-        cfg.ng = 2;
-        const int vecs = (p.W + V - 1) / V;
-        cfg.nt = round_up((vecs + cfg.ng - 1) / cfg.ng, 32);
-        // a strip is at most 16 KiB of row data (4096 fp32 / 2048 fp64 columns)
-        const int nt_cap = 16384 / (16 * cfg.ng);
-        if (cfg.nt > nt_cap) cfg.nt = nt_cap;
-        if (cfg.nt > 512) cfg.nt = 512;
-        cfg.slots = 8;
-        cfg.seg = 0;  // decided below
-    }
-    if (cfg.nt % 32 || cfg.nt < 32 || cfg.nt > 512 || (cfg.ng != 1 && cfg.ng != 2)) return false;
-    p.wt = cfg.nt * V * cfg.ng;
-    p.n_strips = (p.W + p.wt - 1) / p.wt;
-    p.halo_al = round_up(c * p.d, V);
-    long long rs = (long long)p.wt + 2LL * p.halo_al;
-    if (rs > p.W) rs = p.W;
-    p.row_stride = (int)rs;
-    const int min_slots = c + 2;
-    int slots = cfg.slots;
-    while (slots > min_slots && (long long)slots * p.row_stride * esize + 16LL * slots > kMaxSmem) --slots;
-    if ((long long)slots * p.row_stride * esize + 16LL * slots > kMaxSmem || slots < min_slots) return false;
-    p.slots = slots;
-    const int n_max = (p.H + p.d - 1) / p.d;  // longest chain
-    int seg = cfg.seg;
-    if (seg <= 0) {
-        // aim at ~2 blocks per SM in flight, but never let the (taps-1)-row halo exceed ~25 % of a segment
-        const long long chains = (long long)p.n_strips * (p.d < p.H ? p.d : p.H) * batch;
-        const long long target = 2LL * device_sm_count();
-        long long per_chain = (target + chains - 1) / chains;
-        if (per_chain < 1) per_chain = 1;
-        seg = (int)((n_max + per_chain - 1) / per_chain);
-        if (seg < 8 * c) seg = 8 * c;
-    }
-    if (seg > n_max) seg = n_max;
-    p.seg = seg;
-    p.n_seg = (n_max + seg - 1) / seg;
-    cfg.slots = slots;
-    cfg.seg = seg;
-    if (cfg_out) *cfg_out = cfg;
-    return true;
-}
-
-template <typename T, int TAPS, int DMODE, int NG>
+template <typename T, int TAPS, int DMODE, int NG, int OP>
 static int launch_rows(const ScaleParams &p, int batch, int nt, cudaStream_t st) {
-    auto kern = atrous_rows_kernel<T, TAPS, DMODE, NG>;
+    auto kern = atrous_rows_kernel<T, TAPS, DMODE, NG, OP>;
     const size_t smem = (size_t)p.slots * p.row_stride * sizeof(T) + 16 * (size_t)p.slots;
     static bool configured[64] = {};  // per instantiation, per device
     int dev = 0;
@@ -357,14 +266,15 @@ static int launch_rows(const ScaleParams &p, int batch, int nt, cudaStream_t st)
     return launch_status();
 }
 
-template <typename T, int TAPS>
+template <typename T, int TAPS, int OP>
 static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
     constexpr int V = VecOf<T>::V;
     K1Config cfg;
     if (fast_path_ok(p, TAPS, (int)sizeof(T)) && plan_fast(p, TAPS, (int)sizeof(T), batch, scale, &cfg)) {
         const int dmode = (p.d % V == 0) ? 0 : p.d;
-#define WB_LAUNCH(DM)                                                               \
-    (cfg.ng == 1 ? launch_rows<T, TAPS, DM, 1>(p, batch, cfg.nt, st) : launch_rows<T, TAPS, DM, 2>(p, batch, cfg.nt, st))
+#define WB_LAUNCH(DM)                                                                   \
+    (cfg.ng == 1 ? launch_rows<T, TAPS, DM, 1, OP>(p, batch, cfg.nt, st)                \
+                 : launch_rows<T, TAPS, DM, 2, OP>(p, batch, cfg.nt, st))
         if (dmode == 0) return WB_LAUNCH(0);
         if (dmode == 1) return WB_LAUNCH(1);
         if constexpr (V == 4) {
@@ -376,8 +286,15 @@ static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
     long long blocks = (n + 255) / 256;
     const long long cap = 32LL * device_sm_count();
     if (blocks > cap) blocks = cap;
-    atrous_generic_kernel<T, TAPS><<<dim3((unsigned)blocks, (unsigned)batch), 256, 0, st>>>(p);
+    atrous_generic_kernel<T, TAPS, OP><<<dim3((unsigned)blocks, (unsigned)batch), 256, 0, st>>>(p);
     return launch_status();
+}
+
+template <int OP>
+static int dispatch_typed(ScaleParams &p, int batch, int scale, int taps, int dtype, cudaStream_t st) {
+    if (dtype == WB_F32)
+        return taps == 3 ? dispatch<float, 3, OP>(p, batch, scale, st) : dispatch<float, 5, OP>(p, batch, scale, st);
+    return taps == 3 ? dispatch<double, 3, OP>(p, batch, scale, st) : dispatch<double, 5, OP>(p, batch, scale, st);
 }
 
 static int scale_impl(const void *in, void *out_c, void *out_w, int batch, int H, int W, long long in_pitch,
@@ -396,9 +313,7 @@ static int scale_impl(const void *in, void *out_c, void *out_w, int batch, int H
     p.in_pitch = in_pitch; p.in_bstride = in_bstride;
     p.c_pitch = c_pitch; p.c_bstride = c_bstride;
     p.w_pitch = w_pitch; p.w_bstride = w_bstride;
-    if (dtype == WB_F32)
-        return taps == 3 ? dispatch<float, 3>(p, batch, scale, st) : dispatch<float, 5>(p, batch, scale, st);
-    return taps == 3 ? dispatch<double, 3>(p, batch, scale, st) : dispatch<double, 5>(p, batch, scale, st);
+    return dispatch_typed<OP_TRANSFORM>(p, batch, scale, taps, dtype, st);
 }
 
 }  // namespace wb
@@ -431,6 +346,26 @@ int wb_atrous_scale(const void *in, void *out_c, void *out_w, int batch, int H, 
                     long long out_w_bstride, int scale, int taps, int dtype, void *stream) {
     return wb::scale_impl(in, out_c, out_w, batch, H, W, in_pitch, in_bstride, out_c_pitch, out_c_bstride,
                           out_w_pitch, out_w_bstride, scale, taps, dtype, (cudaStream_t)stream);
+}
+
+int wb_wow_whiten_scale(const void *w_raw, void *out, int batch, int H, int W, long long in_pitch,
+                        long long in_bstride, long long out_pitch, long long out_bstride, int scale, int taps,
+                        int dtype, int sig_mode, double sigma, double sigma_e, double noise_host,
+                        const double *noise_dev, double weight, void *stream) {
+    int rc = wb::check_common(batch, H, W, taps, dtype);
+    if (rc) return rc;
+    if (scale < 0 || scale > 30) return WB_EINVAL_SCALE;
+    if (!w_raw || !out || w_raw == out) return WB_EINVAL_POINTER;
+    if (in_pitch < W || out_pitch < W || sig_mode < 0 || sig_mode > 2) return WB_EINVAL_ARG;
+    wb::ScaleParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = w_raw; p.out_c = nullptr; p.out_w = out;
+    p.H = H; p.W = W; p.d = 1 << scale;
+    p.in_pitch = in_pitch; p.in_bstride = in_bstride;
+    p.w_pitch = out_pitch; p.w_bstride = out_bstride;
+    p.sig_mode = sig_mode; p.sigma = sigma; p.sigma_e = sigma_e;
+    p.noise_host = noise_host; p.noise_dev = noise_dev; p.weight = weight;
+    return wb::dispatch_typed<wb::OP_WHITEN>(p, batch, scale, taps, dtype, (cudaStream_t)stream);
 }
 
 int wb_atrous_transform(const void *in, void *planes, void *scratch, int batch, int H, int W, long long in_pitch,

@@ -1,0 +1,204 @@
+// Pieces shared by the row-pipeline kernels (K1 transform, K3 whitening, K2 bilateral): launch parameters, the
+// reflecting vector tap loader, the separable row pass and the host-side geometry planner.
+#pragma once
+
+#include "common.cuh"
+
+namespace wb {
+
+struct ScaleParams {
+    const void *in;
+    void *out_c;
+    void *out_w;
+    int H, W, d;
+    long long in_pitch, in_bstride, c_pitch, c_bstride, w_pitch, w_bstride;
+    int wt;          // strip width in elements (= consumer threads * V * NG)
+    int n_strips;    // column strips per row
+    int seg;         // chain rows produced per thread block
+    int n_seg;       // segments per chain
+    int slots;       // depth of the shared-memory row ring
+    int row_stride;  // elements per ring slot
+    int halo_al;     // x halo kept in shared memory on each side of a strip (multiple of V)
+    // --- whitening epilogue (OP_WHITEN): out_w = significance(raw) * raw * (weight / sqrt(max(S[raw^2], 1e-15)))
+    int sig_mode;              // 0: no thresholding, 1: soft (erf), 2: hard
+    double sigma, sigma_e;     // threshold = (sigma * noise) * sigma_e   (watroo/wavelets.py:137,141)
+    double noise_host;         // used when noise_dev == nullptr
+    const double *noise_dev;   // device scalar per frame (from wb_abs_median), or nullptr
+    double weight;             // recomposition weight of this plane
+};
+
+enum { OP_TRANSFORM = 0, OP_WHITEN = 1 };
+
+// Per-thread, per-column-group tap plan, computed ONCE per thread block: the shared-memory element offset of the
+// aligned vector that holds each tap (relative to the start of a staged row) and whether that vector has to be read
+// backwards (symmetric border).  Nothing here depends on the row, so the inner loop is LDS.128 + FMA only.
+//   DMODE == 0 (d % V == 0): NV = TAPS vectors at columns x + (k - C) d.
+//   DMODE == d in {1, 2} (d < V): NV = 3 vectors (previous, current, next); the taps are picked from that window.
+template <int NV> struct TapPlan {
+    int off[NV];
+    unsigned rev;  // bit k: vector k is mirrored
+};
+
+template <int V, int NV>
+__device__ __forceinline__ TapPlan<NV> make_tap_plan(int x, int step, int W, int lo) {
+    TapPlan<NV> tp;
+    tp.rev = 0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int p = x + (k - NV / 2) * step;  // p % V == 0, -W <= p < 2W (single reflection)
+        const bool left = p < 0, right = p >= W;
+        const int q = left ? (-V - p) : (right ? (2 * W - V - p) : p);
+        tp.off[k] = q - lo;
+        if (left || right) tp.rev |= 1u << k;
+    }
+    return tp;
+}
+
+template <typename T, int V> __device__ __forceinline__ void reverse_vec(Pack<T, V> &t) {
+#pragma unroll
+    for (int e = 0; e < V / 2; ++e) {
+        T a = t.v[e];
+        t.v[e] = t.v[V - 1 - e];
+        t.v[V - 1 - e] = a;
+    }
+}
+
+template <int TAPS, int DMODE> struct PlanSize { static constexpr int NV = (DMODE == 0) ? TAPS : 3; };
+
+// Row pass for one vector of columns.  SQUARE: filter the squares of the staged values (local power of WOW).
+template <typename T, int TAPS, int DMODE, bool SQUARE, bool MIRROR>
+__device__ __forceinline__ Pack<T, VecOf<T>::V> row_pass_impl(const T *srow, const TapPlan<PlanSize<TAPS, DMODE>::NV> &tp) {
+    constexpr int V = VecOf<T>::V;
+    constexpr int C = TAPS / 2;
+    Pack<T, V> acc;
+    if constexpr (DMODE == 0) {
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            Pack<T, V> t = ld_vec(srow + tp.off[k]);
+            if (MIRROR && ((tp.rev >> k) & 1u)) reverse_vec<T, V>(t);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const T v = SQUARE ? t.v[e] * t.v[e] : t.v[e];
+                acc.v[e] = (k == 0) ? Taps<T, TAPS>::h(0) * v : fma_t<T>(Taps<T, TAPS>::h(k), v, acc.v[e]);
+            }
+        }
+    } else {
+        T win[3 * V];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            Pack<T, V> t = ld_vec(srow + tp.off[k]);
+            if (MIRROR && ((tp.rev >> k) & 1u)) reverse_vec<T, V>(t);
+#pragma unroll
+            for (int e = 0; e < V; ++e) win[k * V + e] = SQUARE ? t.v[e] * t.v[e] : t.v[e];
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+#pragma unroll
+            for (int k = 0; k < TAPS; ++k) {
+                const T v = win[V + e + (k - C) * DMODE];
+                acc.v[e] = (k == 0) ? Taps<T, TAPS>::h(0) * v : fma_t<T>(Taps<T, TAPS>::h(k), v, acc.v[e]);
+            }
+        }
+    }
+    return acc;
+}
+
+template <typename T, int TAPS, int DMODE, bool SQUARE>
+__device__ __forceinline__ Pack<T, VecOf<T>::V> row_pass(const T *srow, const TapPlan<PlanSize<TAPS, DMODE>::NV> &tp) {
+    // interior threads (the vast majority) never mirror: keep their path free of the select chains
+    if (tp.rev == 0) return row_pass_impl<T, TAPS, DMODE, SQUARE, false>(srow, tp);
+    return row_pass_impl<T, TAPS, DMODE, SQUARE, true>(srow, tp);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host: geometry planning
+// ---------------------------------------------------------------------------------------------------------------
+struct K1Config { int nt, ng, slots, seg; };
+
+extern K1Config g_override[32];
+extern bool g_override_set[32];
+
+static constexpr int kMaxSmem = 227 * 1024;
+static constexpr int kRegsPerThread = 64;  // budget assumed by the occupancy estimate of the planner
+
+inline int device_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+inline bool fast_path_ok(const ScaleParams &p, int taps, int esize) {
+    const int V = 16 / esize;
+    const int c = taps / 2;
+    if (p.W % V || p.W < 8 * V) return false;
+    if ((long long)c * p.d > p.W) return false;  // more than one reflection in x
+    if (p.in_pitch % V || p.in_bstride % V || !aligned16(p.in)) return false;
+    if (p.out_c && (p.c_pitch % V || p.c_bstride % V || !aligned16(p.out_c))) return false;
+    if (p.out_w && (p.w_pitch % V || p.w_bstride % V || !aligned16(p.out_w))) return false;
+    return true;
+}
+
+// Fill in the strip/segment/ring geometry.  Returns false if no geometry fits in shared memory.
+inline bool plan_fast(ScaleParams &p, int taps, int esize, int batch, int scale, K1Config *cfg_out) {
+    const int V = 16 / esize;
+    const int c = taps / 2;
+    K1Config cfg;
+    if (scale < 32 && g_override_set[scale]) {
+        cfg = g_override[scale];
+    } else {
+        cfg.ng = 2;
+        const int vecs = (p.W + V - 1) / V;
+        cfg.nt = round_up((vecs + cfg.ng - 1) / cfg.ng, 32);
+        // a strip is at most 16 KiB of row data (4096 fp32 / 2048 fp64 columns)
+        const int nt_cap = 16384 / (16 * cfg.ng);
+        if (cfg.nt > nt_cap) cfg.nt = nt_cap;
+        if (cfg.nt > 512) cfg.nt = 512;
+        cfg.slots = 8;
+        cfg.seg = 0;  // decided below
+    }
+    if (cfg.nt % 32 || cfg.nt < 32 || cfg.nt > 512 || (cfg.ng != 1 && cfg.ng != 2)) return false;
+    p.wt = cfg.nt * V * cfg.ng;
+    p.n_strips = (p.W + p.wt - 1) / p.wt;
+    p.halo_al = round_up(c * p.d, V);
+    long long rs = (long long)p.wt + 2LL * p.halo_al;
+    if (rs > p.W) rs = p.W;
+    p.row_stride = (int)rs;
+    const int min_slots = c + 2;
+    int slots = cfg.slots;
+    while (slots > min_slots && (long long)slots * p.row_stride * esize + 16LL * slots > kMaxSmem) --slots;
+    if ((long long)slots * p.row_stride * esize + 16LL * slots > kMaxSmem || slots < min_slots) return false;
+    p.slots = slots;
+    const int n_max = (p.H + p.d - 1) / p.d;  // longest chain
+    int seg = cfg.seg;
+    if (seg <= 0) {
+        // One full wave: as many equal segments as there are block slots (SMs x resident blocks), so that no SM
+        // idles in a partial last wave, but never shorter than 4x the (taps-1)-row halo.
+        const long long chains = (long long)p.n_strips * (p.d < p.H ? p.d : p.H) * batch;
+        const size_t smem = (size_t)slots * p.row_stride * esize + 16 * (size_t)slots;
+        int occ = (int)(kMaxSmem / (smem + 1024));
+        const int occ_regs = 65536 / ((cfg.nt + 32) * kRegsPerThread);
+        if (occ > occ_regs) occ = occ_regs;
+        if (occ < 1) occ = 1;
+        const long long slots_total = (long long)device_sm_count() * occ;
+        long long per_chain = slots_total / chains;  // segments per chain that still fit in one wave
+        if (per_chain < 1) per_chain = 1;
+        seg = (int)((n_max + per_chain - 1) / per_chain);
+        if (seg < 8 * c) seg = 8 * c;
+    }
+    if (seg > n_max) seg = n_max;
+    p.seg = seg;
+    p.n_seg = (n_max + seg - 1) / seg;
+    cfg.slots = slots;
+    cfg.seg = seg;
+    if (cfg_out) *cfg_out = cfg;
+    return true;
+}
+
+
+}  // namespace wb

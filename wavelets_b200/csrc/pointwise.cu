@@ -1,0 +1,267 @@
+// K5 -- element-wise pieces of the hot path (all HBM-streaming, 128-bit accesses where alignment allows):
+//   * significance map            Coefficients.significance      watroo/wavelets.py:129-143
+//   * in-place denoise of a plane Coefficients.denoise           watroo/wavelets.py:145-149
+//   * residual-plane rescale      wow(), last plane              watroo/utils.py:185-189,203
+//   * synthesis sum               np.sum(coefficients, axis=0)   watroo/utils.py:98,205
+//   * N(0,1) fp32 noise fields    np.random.normal               watroo/wavelets.py:225 (device Philox4x32-10)
+#include "common.cuh"
+
+namespace wb {
+
+// threshold = (sigma * noise) * sigma_e evaluated like NumPy >= 2: with a scalar noise everything is float64; with a
+// per-pixel noise map of the plane dtype, `sigma * noise` stays in that dtype and only the product with the
+// float64 sigma_e is promoted (watroo/wavelets.py:137,141).
+template <typename T>
+__device__ __forceinline__ double threshold_at(const T *noise_map, long long i, double sigma, double scalar,
+                                               double sigma_e) {
+    if (noise_map) return (double)((T)sigma * noise_map[i]) * sigma_e;
+    return (sigma * scalar) * sigma_e;
+}
+
+// out: soft -> float64 erf(|w / thr|); hard -> uint8 (|w| > thr).  thr = (sigma * noise) * sigma_e, in float64
+// exactly as NumPy >= 2 evaluates it; noise is a host scalar, a device scalar or a per-pixel map.
+template <typename T>
+__global__ void __launch_bounds__(256) significance_kernel(const T *w, long long n, double sigma, double sigma_e,
+                                                           double noise_host, const double *noise_dev,
+                                                           const T *noise_map, int soft, double *out_soft,
+                                                           unsigned char *out_hard) {
+    const double nz = noise_dev ? *noise_dev : noise_host;
+    const bool ones = (!noise_map && nz == 0.0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (ones) {
+            if (soft) out_soft[i] = 1.0; else out_hard[i] = 1;
+            continue;
+        }
+        const double thr = threshold_at<T>(noise_map, i, sigma, nz, sigma_e);
+        const double v = (double)w[i];
+        if (soft) out_soft[i] = erf(fabs(v / thr));
+        else out_hard[i] = fabs(v) > thr ? 1 : 0;
+    }
+}
+
+// w <- T( double(w) * (weight * significance) ): the product is formed in float64 and rounded once, like
+// `c *= wgt * self.significance(...)` (wavelets.py:149).  sig_mode 0 multiplies by `weight` only.
+template <typename T>
+__global__ void __launch_bounds__(256) denoise_plane_kernel(T *w, long long n, int batch, long long bstride,
+                                                            int sig_mode, double sigma, double sigma_e,
+                                                            double noise_host, const double *noise_dev,
+                                                            const T *noise_map, double weight) {
+    const int frame = blockIdx.y;
+    T *wf = w + (long long)frame * bstride;
+    int mode = sig_mode;
+    const double nz = noise_dev ? noise_dev[frame] : noise_host;
+    if (mode && !noise_map && nz == 0.0) mode = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = (double)wf[i];
+        double f = weight;
+        if (mode) {
+            const double thr = threshold_at<T>(noise_map, i, sigma, nz, sigma_e);
+            if (mode == 1) f = weight * erf(fabs(v / thr));
+            else f = weight * (fabs(v) > thr ? 1.0 : 0.0);
+        }
+        wf[i] = (T)(v * f);
+    }
+}
+
+// c_L <- c_L * T(weight / std_T), std_T = population std rounded to the plane dtype, non-positive -> 1e-15
+// (utils.py:185-189, :203).  `moments` = [mean, var, std] per frame from wb_plane_moments.
+template <typename T>
+__global__ void __launch_bounds__(256) residual_rescale_kernel(T *c, long long n, int batch, long long bstride,
+                                                               const double *moments, double weight) {
+    const int frame = blockIdx.y;
+    T *cf = c + (long long)frame * bstride;
+    T sd = (T)moments[frame * 3 + 2];
+    if (sd <= T(0)) sd = T(1e-15);
+    const T ratio = (T)weight / sd;
+    constexpr int V = VecOf<T>::V;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(cf) & 15u) == 0) {
+        const long long nvec = n / V;
+        for (long long i = tid; i < nvec; i += nth) {
+            Pack<T, V> p = ld_vec(cf + i * V);
+#pragma unroll
+            for (int e = 0; e < V; ++e) p.v[e] *= ratio;
+            st_vec(cf + i * V, p);
+        }
+        for (long long i = nvec * V + tid; i < n; i += nth) cf[i] *= ratio;
+    } else {
+        for (long long i = tid; i < n; i += nth) cf[i] *= ratio;
+    }
+}
+
+// out = ((p_0 + p_1) + p_2) + ... in plane order and in the plane dtype, as np.sum(axis=0) does.
+template <typename T>
+__global__ void __launch_bounds__(256) synthesis_kernel(const T *planes, int nplanes, long long plane_stride,
+                                                        long long n, int batch, long long in_bstride, T *out,
+                                                        long long out_bstride) {
+    const int frame = blockIdx.y;
+    const T *pf = planes + (long long)frame * in_bstride;
+    T *of = out + (long long)frame * out_bstride;
+    constexpr int V = VecOf<T>::V;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(pf) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(of) & 15u) == 0) &&
+                        (plane_stride % V == 0);
+    if (vec_ok) {
+        const long long nvec = n / V;
+        for (long long i = tid; i < nvec; i += nth) {
+            Pack<T, V> acc = ld_vec(pf + i * V);
+            for (int k = 1; k < nplanes; ++k) {
+                Pack<T, V> p = ld_vec(pf + (long long)k * plane_stride + i * V);
+#pragma unroll
+                for (int e = 0; e < V; ++e) acc.v[e] += p.v[e];
+            }
+            st_vec(of + i * V, acc);
+        }
+        for (long long i = nvec * V + tid; i < n; i += nth) {
+            T acc = pf[i];
+            for (int k = 1; k < nplanes; ++k) acc += pf[(long long)k * plane_stride + i];
+            of[i] = acc;
+        }
+    } else {
+        for (long long i = tid; i < n; i += nth) {
+            T acc = pf[i];
+            for (int k = 1; k < nplanes; ++k) acc += pf[(long long)k * plane_stride + i];
+            of[i] = acc;
+        }
+    }
+}
+
+// Philox4x32-10 counter-based generator + Box-Muller: 4 standard normals per counter.
+__device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0,
+                                             uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+__global__ void __launch_bounds__(256) randn_kernel(float *out, long long n, unsigned long long seed,
+                                                    unsigned long long offset) {
+    const long long nquad = (n + 3) / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquad;
+         i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long ctr = (unsigned long long)i + offset;
+        uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x5EEDu, c3 = 0;
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            philox_round(c0, c1, c2, c3, k0, k1);
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        // uniforms in (0, 1]: (x + 1) * 2^-32
+        const float u0 = ((float)c0 + 1.0f) * 2.3283064365386963e-10f;
+        const float u1 = ((float)c1) * 2.3283064365386963e-10f;
+        const float u2 = ((float)c2 + 1.0f) * 2.3283064365386963e-10f;
+        const float u3 = ((float)c3) * 2.3283064365386963e-10f;
+        const float r0 = sqrtf(-2.0f * logf(fminf(u0, 1.0f))), r1 = sqrtf(-2.0f * logf(fminf(u2, 1.0f)));
+        float s0, co0, s1, co1;
+        sincospif(2.0f * u1, &s0, &co0);
+        sincospif(2.0f * u3, &s1, &co1);
+        const float v[4] = {r0 * co0, r0 * s0, r1 * co1, r1 * s1};
+        const long long base = i * 4;
+        if (base + 3 < n && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0)) {
+            *reinterpret_cast<float4 *>(out + base) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int e = 0; e < 4; ++e)
+                if (base + e < n) out[base + e] = v[e];
+        }
+    }
+}
+
+static unsigned grid_for(long long work_items) {
+    long long blocks = (work_items + 255) / 256;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+    const long long cap = 16LL * sms;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace wb
+
+extern "C" {
+
+int wb_significance(const void *w, long long n, int dtype, double sigma, double sigma_e, double noise_host,
+                    const double *noise_dev, const void *noise_map, int soft, void *out, void *stream) {
+    if (dtype != WB_F32 && dtype != WB_F64) return WB_EINVAL_DTYPE;
+    if (n < 1) return WB_EINVAL_SHAPE;
+    if (!w || !out) return WB_EINVAL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = wb::grid_for(n);
+    double *os = soft ? reinterpret_cast<double *>(out) : nullptr;
+    unsigned char *oh = soft ? nullptr : reinterpret_cast<unsigned char *>(out);
+    if (dtype == WB_F32)
+        wb::significance_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float *>(w), n, sigma, sigma_e,
+                                                             noise_host, noise_dev,
+                                                             reinterpret_cast<const float *>(noise_map), soft, os, oh);
+    else
+        wb::significance_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double *>(w), n, sigma, sigma_e,
+                                                              noise_host, noise_dev,
+                                                              reinterpret_cast<const double *>(noise_map), soft, os, oh);
+    return wb::launch_status();
+}
+
+int wb_denoise_plane(void *w, long long n, int batch, long long bstride, int dtype, int sig_mode, double sigma,
+                     double sigma_e, double noise_host, const double *noise_dev, const void *noise_map, double weight,
+                     void *stream) {
+    if (dtype != WB_F32 && dtype != WB_F64) return WB_EINVAL_DTYPE;
+    if (n < 1 || batch < 1 || batch > 65535) return WB_EINVAL_SHAPE;
+    if (!w) return WB_EINVAL_POINTER;
+    if (sig_mode < 0 || sig_mode > 2) return WB_EINVAL_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(wb::grid_for(n), (unsigned)batch);
+    if (dtype == WB_F32)
+        wb::denoise_plane_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<float *>(w), n, batch, bstride, sig_mode,
+                                                              sigma, sigma_e, noise_host, noise_dev,
+                                                              reinterpret_cast<const float *>(noise_map), weight);
+    else
+        wb::denoise_plane_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<double *>(w), n, batch, bstride,
+                                                               sig_mode, sigma, sigma_e, noise_host, noise_dev,
+                                                               reinterpret_cast<const double *>(noise_map), weight);
+    return wb::launch_status();
+}
+
+int wb_residual_rescale(void *c, long long n, int batch, long long bstride, int dtype, const double *moments,
+                        double weight, void *stream) {
+    if (dtype != WB_F32 && dtype != WB_F64) return WB_EINVAL_DTYPE;
+    if (n < 1 || batch < 1 || batch > 65535) return WB_EINVAL_SHAPE;
+    if (!c || !moments) return WB_EINVAL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(wb::grid_for(n / 4 + 1), (unsigned)batch);
+    if (dtype == WB_F32)
+        wb::residual_rescale_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<float *>(c), n, batch, bstride, moments, weight);
+    else
+        wb::residual_rescale_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<double *>(c), n, batch, bstride, moments, weight);
+    return wb::launch_status();
+}
+
+int wb_synthesis(const void *planes, int nplanes, long long plane_stride, long long n, int batch,
+                 long long in_bstride, void *out, long long out_bstride, int dtype, void *stream) {
+    if (dtype != WB_F32 && dtype != WB_F64) return WB_EINVAL_DTYPE;
+    if (n < 1 || nplanes < 1 || batch < 1 || batch > 65535) return WB_EINVAL_SHAPE;
+    if (!planes || !out) return WB_EINVAL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(wb::grid_for(n / 4 + 1), (unsigned)batch);
+    if (dtype == WB_F32)
+        wb::synthesis_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float *>(planes), nplanes, plane_stride,
+                                                          n, batch, in_bstride, reinterpret_cast<float *>(out), out_bstride);
+    else
+        wb::synthesis_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double *>(planes), nplanes, plane_stride,
+                                                           n, batch, in_bstride, reinterpret_cast<double *>(out), out_bstride);
+    return wb::launch_status();
+}
+
+int wb_randn_f32(float *out, long long n, unsigned long long seed, unsigned long long offset, void *stream) {
+    if (n < 1) return WB_EINVAL_SHAPE;
+    if (!out) return WB_EINVAL_POINTER;
+    wb::randn_kernel<<<wb::grid_for(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
+    return wb::launch_status();
+}
+
+}  // extern "C"

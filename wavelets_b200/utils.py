@@ -1,0 +1,259 @@
+"""Applications on top of the transform: ``denoise`` and ``wow`` (mirror of watroo/utils.py:83-102, :105-219).
+
+Both keep the reference's signatures and quirks (``denoise``'s ``weights`` are the sigma thresholds; ``wow`` returns
+``(recon, coefficients)`` with the planes overwritten by their whitened values).  NumPy in -> NumPy out for the image
+results; torch tensor in -> torch CUDA tensor out.  ``coefficients.data`` always stays on the device.
+"""
+from __future__ import annotations
+
+import copy
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from .scaling import B3spline
+from .wavelets import (AtrousTransform, Coefficients, _Noise, _frame_layout, abs_median_noise, atrous_scale,
+                       bilateral_list, plane_moments, synthesis, to_device_image)
+
+__all__ = ["denoise", "wow", "wow_batch", "generalized_anscombe"]
+
+
+def generalized_anscombe(signal, alpha=1, g=0, sigma=0, inverse=False):
+    """Variance-stabilising transform and its algebraic inverse (watroo/wavelets.py:14-21), element-wise on a torch
+    tensor (device or host)."""
+    if inverse:
+        return ((alpha * signal / 2) ** 2 + alpha * g - sigma ** 2 - 3 * alpha / 8) / alpha
+    dum = alpha * signal + 3 * alpha ** 2 / 8 + sigma ** 2 - alpha * g
+    return 2 * torch.sqrt(torch.clamp(dum, min=0)) / alpha
+
+
+def _result(t, as_numpy):
+    return t.cpu().numpy() if as_numpy else t
+
+
+def denoise(data, weights, scaling_function=B3spline, noise=None, bilateral=None, soft_threshold=True,
+            anscombe=False):
+    """Convenience denoiser (watroo/utils.py:83-102).  NB ``weights`` are the sigma thresholds of each scale and
+    their count sets the number of scales; the result is the sum of the thresholded planes."""
+    img, was_numpy = to_device_image(data)
+    if anscombe:
+        img = generalized_anscombe(img)
+    transform = AtrousTransform(scaling_function, bilateral=bilateral)
+    coefficients = transform(img, len(weights))
+    coefficients.noise = noise
+    coefficients.denoise(weights, soft_threshold=soft_threshold)
+    out = synthesis(coefficients.data)
+    if anscombe:
+        out = generalized_anscombe(out, inverse=True)
+    return _result(out, was_numpy)
+
+
+def _wow_plan(shape, scaling_function, n_scales, weights, denoise_coefficients, bilateral, from_coefficients=None):
+    """Scale-count and per-scale parameter lists of wow() (watroo/utils.py:121-146, :160-170)."""
+    n_taps = len(scaling_function.coefficients_1d)
+    if from_coefficients is None:
+        max_scales = int(np.round(np.log2(min(shape)) - np.log2(n_taps)))
+        if n_scales is None:
+            n_scales = max_scales
+        elif n_scales > max_scales:
+            n_scales = max_scales
+    else:
+        n_scales = len(from_coefficients) - 1
+    table_len = len(scaling_function(2).sigma_e(bilateral=bilateral))
+    if len(denoise_coefficients) >= table_len:
+        warnings.warn(f"Required number of scales lager then the maximum for scaling function. Using {table_len}.")
+        n_scales = table_len
+    sigma_bilateral = None if bilateral is None else bilateral_list(bilateral, n_scales)
+    wts = copy.copy(list(weights))
+    if len(wts) <= n_scales:
+        wts.extend([1, ] * (n_scales - len(wts) + 1))
+    dns = copy.copy(list(denoise_coefficients))
+    if len(dns) < n_scales:
+        dns.extend([0, ] * (n_scales - len(dns)))
+    if len(dns) == n_scales:
+        dns.extend([1, ])
+    return n_scales, sigma_bilateral, wts, dns
+
+
+def _whiten_scale(lib, w_raw, out, s, scaling_function, sig_mode, sigma, sigma_e, nz, weight):
+    b, h, w, pitch, bstride = _frame_layout(w_raw)
+    _, _, _, o_pitch, o_bstride = _frame_layout(out)
+    with torch.cuda.device(w_raw.device):
+        _lib.check(lib.wb_wow_whiten_scale(w_raw.data_ptr(), out.data_ptr(), b, h, w, pitch, bstride, o_pitch,
+                                           o_bstride, s, scaling_function.taps_code, _lib.dtype_code(w_raw.dtype),
+                                           sig_mode, float(sigma), float(sigma_e), nz.host, nz.dev_ptr, float(weight),
+                                           _lib.stream_ptr(w_raw.device)))
+
+
+def _scalar_noise(noise, device):
+    """None -> None; number / 0-d array / 1-element tensor -> _Noise with a host or device scalar."""
+    if noise is None:
+        return None
+    if isinstance(noise, torch.Tensor):
+        if noise.numel() == 1 and noise.ndim <= 1 and noise.is_cuda and noise.dtype == torch.float64:
+            return _Noise(dev=noise)
+        if noise.numel() == 1:
+            return _Noise(host=float(noise.item()))
+        return "map"
+    if isinstance(noise, np.ndarray) and noise.ndim > 0:
+        return "map"
+    return _Noise(host=float(noise))
+
+
+def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilateral, bilateral_scaling, whitening,
+               soft_threshold, noise):
+    """The fused WOW pipeline on a stack (B, H, W) of frames.  Returns (recon (B,H,W), planes (B,L+1,H,W), noise).
+
+    Per scale: K1/K2 writes c_{s+1} into a ping-pong scratch and the raw w_s into a one-plane scratch; K3 reads the
+    raw plane once, forms the local power S_s[w_s^2], applies significance and whitening and writes the final plane.
+    Raw detail planes never reach the output array, the MAD noise is estimated on the device from the raw w_0
+    (no host synchronisation anywhere), the residual plane is rescaled in place and K5 sums the planes."""
+    lib = _lib.load(require_cuda=True)
+    sf = scaling_function_class(2)
+    b, h, w = stack.shape
+    dev, dt = stack.device, stack.dtype
+    L = n_scales
+    planes = torch.empty((b, L + 1, h, w), dtype=dt, device=dev)
+    bilateral = sigma_bilateral
+    sigma_e = sf.sigma_e(bilateral=bilateral)
+    transform = AtrousTransform(scaling_function_class, bilateral=bilateral, bilateral_scaling=bilateral_scaling)
+    factors = transform.var_factors(L) if bilateral is not None else [None] * L
+    if L == 0:
+        planes[:, 0].copy_(stack)
+    scratch = torch.empty((3, b, h, w), dtype=dt, device=dev) if L > 0 else None
+    nz = noise  # _Noise or None
+    src = stack
+    for s in range(L):
+        dst_c = planes[:, L] if s == L - 1 else scratch[s & 1]
+        d, wt = dns[s], wts[s]
+        need_sig = d != 0
+        if whitening:
+            w_raw = scratch[2]
+            atrous_scale(src, s, sf, out_c=dst_c, out_w=w_raw, var_factor=factors[s])
+            if need_sig and nz is None:
+                # lazily, from the current state of plane 0 (raw w_0 when s == 0) -- watroo/wavelets.py:131-132
+                nz = _Noise(dev=abs_median_noise(w_raw if s == 0 else planes[:, 0], sigma_e[0]))
+            mode = (1 if soft_threshold else 2) if need_sig else 0
+            _whiten_scale(lib, w_raw, planes[:, s], s, sf, mode, d, sigma_e[s] if need_sig else 1.0,
+                          nz if need_sig else _Noise(), wt)
+        else:
+            atrous_scale(src, s, sf, out_c=dst_c, out_w=planes[:, s], var_factor=factors[s])
+            if need_sig and nz is None:
+                nz = _Noise(dev=abs_median_noise(planes[:, 0], sigma_e[0]))
+            mode = (1 if soft_threshold else 2) if need_sig else 0
+            if mode or wt != 1:
+                use = nz if need_sig else _Noise()
+                with torch.cuda.device(dev):
+                    _lib.check(lib.wb_denoise_plane(planes[:, s].data_ptr(), h * w, b, (L + 1) * h * w,
+                                                    _lib.dtype_code(dt), mode, float(d),
+                                                    float(sigma_e[s]) if need_sig else 1.0, use.host, use.dev_ptr, 0,
+                                                    float(wt), _lib.stream_ptr(dev)))
+        src = dst_c
+    # residual plane: c_L *= wt_L / std(c_L)  (watroo/utils.py:185-189, :203)
+    last = planes[:, L]
+    if whitening:
+        mom = plane_moments(last)
+        with torch.cuda.device(dev):
+            _lib.check(lib.wb_residual_rescale(last.data_ptr(), h * w, b, (L + 1) * h * w, _lib.dtype_code(dt),
+                                               mom.data_ptr(), float(wts[L]), _lib.stream_ptr(dev)))
+    elif wts[L] != 1:
+        last.mul_(wts[L])
+    recon = synthesis(planes)
+    return recon, planes, nz
+
+
+def wow(data, scaling_function=B3spline, n_scales=None, weights=[], whitening=True, denoise_coefficients=[],
+        noise=None, bilateral=None, bilateral_scaling=False, soft_threshold=True, preserve_variance=False, gamma=3.2,
+        gamma_min=None, gamma_max=None, h=0):
+    """Wavelets Optimized Whitening (watroo/utils.py:105-219): ``(recon, coefficients)``.
+
+    ``data`` is a 2-D image (ndarray or torch tensor) or a ``Coefficients`` object (which is then whitened in
+    place, as in the reference).  ``h > 0`` (gamma blending) and ``preserve_variance`` are not on the accelerated
+    path yet and raise NotImplementedError."""
+    if h != 0 or preserve_variance:
+        raise NotImplementedError("wow(h > 0) and wow(preserve_variance=True) are not implemented on the device path")
+    if isinstance(data, Coefficients):
+        return _wow_coefficients(data, weights, whitening, denoise_coefficients, bilateral, soft_threshold)
+    if not isinstance(data, (np.ndarray, torch.Tensor)):
+        raise ValueError("Unknown input type")  # watroo/utils.py:133
+    img, was_numpy = to_device_image(data)
+    n_scales, sigma_bilateral, wts, dns = _wow_plan(img.shape, scaling_function, n_scales, weights,
+                                                    denoise_coefficients, bilateral)
+    nz = _scalar_noise(noise, img.device)
+    if nz == "map":
+        # per-pixel noise maps take the unfused route: transform, then whiten plane by plane
+        transform = AtrousTransform(scaling_function, bilateral=sigma_bilateral, bilateral_scaling=bilateral_scaling)
+        co = transform(img, n_scales)
+        co.noise = noise
+        recon, co = _wow_coefficients(co, weights, whitening, denoise_coefficients, bilateral, soft_threshold,
+                                      plan=(n_scales, sigma_bilateral, wts, dns))
+        return _result(recon, was_numpy), co
+    recon, planes, nz = _wow_stack(img.unsqueeze(0), scaling_function, n_scales, wts, dns, sigma_bilateral,
+                                   bilateral_scaling, whitening, soft_threshold, nz)
+    co = Coefficients(planes[0], scaling_function(2), sigma_bilateral)
+    if nz is not None:
+        co.noise = nz.dev if nz.dev is not None else nz.host
+    else:
+        co.noise = None
+    return _result(recon[0], was_numpy), co
+
+
+def wow_batch(frames, scaling_function=B3spline, n_scales=None, weights=[], whitening=True, denoise_coefficients=[],
+              noise=None, bilateral=None, bilateral_scaling=False, soft_threshold=True):
+    """NEW entry point (no reference equivalent): WOW of a stack ``(B, H, W)`` of independent frames, every kernel
+    launched once for the whole stack.  Returns ``(recon (B,H,W), planes (B,L+1,H,W), noise (B,) or None)`` as device
+    tensors; per-frame results are identical to ``wow(frame, ...)``."""
+    stack, _ = to_device_image(frames, ndim_ok=(3,))
+    n_scales, sigma_bilateral, wts, dns = _wow_plan(stack.shape[1:], scaling_function, n_scales, weights,
+                                                    denoise_coefficients, bilateral)
+    nz = _scalar_noise(noise, stack.device)
+    if nz == "map":
+        raise NotImplementedError("wow_batch() takes a scalar noise or None")
+    recon, planes, nz = _wow_stack(stack, scaling_function, n_scales, wts, dns, sigma_bilateral, bilateral_scaling,
+                                   whitening, soft_threshold, nz)
+    noise_out = None if nz is None else (nz.dev if nz.dev is not None else nz.host)
+    return recon, planes, noise_out
+
+
+def _wow_coefficients(co, weights, whitening, denoise_coefficients, bilateral, soft_threshold, plan=None):
+    """wow() on already computed coefficients (watroo/utils.py:128-131, :152-153): planes are whitened in place,
+    in plane order, with the lazily estimated noise of the object."""
+    lib = _lib.load(require_cuda=True)
+    sf = co.scaling_function
+    if plan is None:
+        n_scales, _, wts, dns = _wow_plan(co.data.shape[1:], sf.__class__, None, weights, denoise_coefficients,
+                                          bilateral, from_coefficients=co)
+        if n_scales != len(co) - 1:
+            n_scales = len(co) - 1  # the warning branch cannot add planes to existing coefficients
+    else:
+        n_scales, _, wts, dns = plan
+    data = co.data
+    L = n_scales
+    tmp = torch.empty_like(data[0])
+    for s in range(L):
+        d, wt = dns[s], wts[s]
+        plane = data[s]
+        if whitening:
+            # local power from the raw plane, significance from the raw plane, then both factors (utils.py:194-203)
+            nz = co._noise_arg(d) if d != 0 else _Noise()
+            if nz.map is not None:
+                sig = co.significance(d, s, soft_threshold=soft_threshold)
+                _whiten_scale(lib, plane, tmp, s, sf, 0, 0.0, 1.0, _Noise(), wt)
+                plane.copy_((tmp.to(torch.float64) * sig.to(torch.float64)).to(plane.dtype))
+            else:
+                mode = (1 if soft_threshold else 2) if d != 0 else 0
+                _whiten_scale(lib, plane, tmp, s, sf, mode, d, co.sigma_e[s] if d != 0 else 1.0, nz, wt)
+                plane.copy_(tmp)
+        else:
+            co._denoise_plane(lib, s, d, wt, soft_threshold)
+    last = data[L]
+    if whitening:
+        mom = plane_moments(last)
+        with torch.cuda.device(last.device):
+            _lib.check(lib.wb_residual_rescale(last.data_ptr(), last.numel(), 1, 0, _lib.dtype_code(last.dtype),
+                                               mom.data_ptr(), float(wts[L]), _lib.stream_ptr(last.device)))
+    elif wts[L] != 1:
+        last.mul_(wts[L])
+    return synthesis(data), co

@@ -8,6 +8,7 @@ to the current CUDA device) or torch tensors.  All arithmetic runs in the sm_100
 from __future__ import annotations
 
 import copy
+import numbers
 
 import numpy as np
 import torch
@@ -15,7 +16,7 @@ import torch
 from . import _lib
 from .scaling import AbstractScalingFunction, B3spline, Triangle
 
-__all__ = ["AtrousTransform", "B3spline", "Triangle", "Coefficients", "atrous_scale"]
+__all__ = ["AtrousTransform", "B3spline", "Triangle", "Coefficients", "atrous_scale", "convolution"]
 
 # integer / big-endian inputs are recast to float64 (watroo/wavelets.py:297, :319-320)
 _RECAST_NUMPY = tuple(np.dtype(t) for t in (np.int16, np.uint16, np.int32, np.uint32, np.int64, ">f4", ">f8"))
@@ -52,7 +53,7 @@ def to_device_image(arr, ndim_ok=(2,)):
         if t.dtype not in (torch.float32, torch.float64):
             raise TypeError(f"unsupported image dtype {t.dtype}: expected float32/float64 or a recast integer type")
         if not t.is_cuda:
-            t = t.to(_device())
+            t = t.to(_device(), non_blocking=True)
         if t.stride(-1) != 1:
             t = t.contiguous()
     if t.ndim not in ndim_ok:
@@ -71,41 +72,158 @@ def _frame_layout(t):
     return t.shape[0], t.shape[1], t.shape[2], t.stride(1), t.stride(0)
 
 
-def atrous_scale(src, scale, scaling_function, out_c=None, out_w=None):
-    """One scale of the plain cascade on device tensors: ``out_c = S_scale[src]``, ``out_w = src - out_c``.
+def _out_args(t):
+    if t is None or t is False:
+        return 0, 0, 0
+    _, _, _, pitch, bstride = _frame_layout(t)
+    return t.data_ptr(), pitch, bstride
 
-    Thin wrapper over ``wb_atrous_scale`` (replaces ``convolution`` watroo/wavelets.py:35-45 plus the subtraction of
-    :442).  ``src`` is (H, W) or (B, H, W); outputs are allocated when not given (pass ``False`` to skip one)."""
+
+def atrous_scale(src, scale, scaling_function, out_c=None, out_w=None, var_factor=None):
+    """One scale of the cascade on device tensors: ``out_c = S_scale[src]`` (or its bilateral variant when
+    ``var_factor`` is given), ``out_w = src - out_c``.
+
+    Thin wrapper over ``wb_atrous_scale`` / ``wb_atrous_scale_bilateral``.  ``src`` is (H, W) or (B, H, W); outputs
+    are allocated when not given (pass ``False`` to skip one)."""
     lib = _lib.load(require_cuda=True)
     b, h, w, pitch, bstride = _frame_layout(src)
     if out_c is None:
         out_c = torch.empty(src.shape, dtype=src.dtype, device=src.device)
     if out_w is None:
         out_w = torch.empty(src.shape, dtype=src.dtype, device=src.device)
-    pc = pw = 0
-    lc = lw = (0, 0)
-    if out_c is not False:
-        pc, lc = out_c.data_ptr(), _frame_layout(out_c)[3:]
-    if out_w is not False:
-        pw, lw = out_w.data_ptr(), _frame_layout(out_w)[3:]
+    pc, c_pitch, c_bs = _out_args(out_c)
+    pw, w_pitch, w_bs = _out_args(out_w)
     with torch.cuda.device(src.device):
-        _lib.check(lib.wb_atrous_scale(src.data_ptr(), pc, pw, b, h, w, pitch, bstride, lc[0], lc[1], lw[0], lw[1],
-                                       int(scale), scaling_function.taps_code, _lib.dtype_code(src.dtype),
-                                       _lib.stream_ptr(src.device)))
+        if var_factor is None:
+            _lib.check(lib.wb_atrous_scale(src.data_ptr(), pc, pw, b, h, w, pitch, bstride, c_pitch, c_bs, w_pitch,
+                                           w_bs, int(scale), scaling_function.taps_code, _lib.dtype_code(src.dtype),
+                                           _lib.stream_ptr(src.device)))
+        else:
+            _lib.check(lib.wb_atrous_scale_bilateral(src.data_ptr(), pc, pw, b, h, w, pitch, bstride, c_pitch, c_bs,
+                                                     w_pitch, w_bs, int(scale), scaling_function.taps_code,
+                                                     _lib.dtype_code(src.dtype), float(var_factor),
+                                                     _lib.stream_ptr(src.device)))
     return (None if out_c is False else out_c), (None if out_w is False else out_w)
+
+
+def convolution(arr, scaling_function, s=0, output=None):
+    """Device counterpart of the reference's exported ``convolution`` (watroo/wavelets.py:35-45, 2-D branch):
+    the dilated smooth ``S_s[arr]`` with the symmetric border.  Returns a device tensor."""
+    img, _ = to_device_image(arr)
+    out, _ = atrous_scale(img, s, scaling_function, out_c=output, out_w=False)
+    return out
+
+
+def bilateral_list(bilateral, level):
+    """watroo/wavelets.py:421-424: a scalar is broadcast to level+1 entries, a list is copied and padded with 1."""
+    sb = copy.copy(bilateral) if type(bilateral) is list else [bilateral, ] * (level + 1)
+    if len(sb) <= level:
+        sb.extend([1, ] * (level - len(sb) + 1))
+    return sb
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Device reductions
+# ---------------------------------------------------------------------------------------------------------------
+def abs_median_noise(plane, sigma_e0, out_noise=None):
+    """MAD noise of one plane per frame, on the device: ``(median(|plane|) / 0.6745) / sigma_e0`` -> float64 tensor of
+    shape (batch,).  ``plane`` is (H, W) or (B, H, W) with contiguous frames.  No host synchronisation."""
+    lib = _lib.load(require_cuda=True)
+    b, h, w, pitch, bstride = _frame_layout(plane)
+    if pitch != w:
+        plane = plane.contiguous()
+        b, h, w, pitch, bstride = _frame_layout(plane)
+    code = _lib.dtype_code(plane.dtype)
+    ws = torch.empty(lib.wb_abs_median_workspace_bytes(code, b), dtype=torch.uint8, device=plane.device)
+    if out_noise is None:
+        out_noise = torch.empty(b, dtype=torch.float64, device=plane.device)
+    with torch.cuda.device(plane.device):
+        _lib.check(lib.wb_abs_median(plane.data_ptr(), h * w, b, bstride, code, 0, out_noise.data_ptr(),
+                                     float(sigma_e0), ws.data_ptr(), _lib.stream_ptr(plane.device)))
+    return out_noise
+
+
+def abs_median(plane):
+    """Exact ``np.median(np.abs(plane))`` per frame as a tensor of the plane dtype, shape (batch,)."""
+    lib = _lib.load(require_cuda=True)
+    b, h, w, pitch, bstride = _frame_layout(plane)
+    if pitch != w:
+        plane = plane.contiguous()
+        b, h, w, pitch, bstride = _frame_layout(plane)
+    code = _lib.dtype_code(plane.dtype)
+    ws = torch.empty(lib.wb_abs_median_workspace_bytes(code, b), dtype=torch.uint8, device=plane.device)
+    out = torch.empty(b, dtype=plane.dtype, device=plane.device)
+    with torch.cuda.device(plane.device):
+        _lib.check(lib.wb_abs_median(plane.data_ptr(), h * w, b, bstride, code, out.data_ptr(), 0, 1.0,
+                                     ws.data_ptr(), _lib.stream_ptr(plane.device)))
+    return out
+
+
+def plane_moments(planes):
+    """Population [mean, variance, std] (float64) of each contiguous 2-D plane of ``planes`` ((H,W) or (N,H,W))."""
+    lib = _lib.load(require_cuda=True)
+    b, h, w, pitch, bstride = _frame_layout(planes)
+    if pitch != w:
+        planes = planes.contiguous()
+        b, h, w, pitch, bstride = _frame_layout(planes)
+    ws = torch.empty(lib.wb_plane_moments_workspace_bytes(b), dtype=torch.uint8, device=planes.device)
+    out = torch.empty((b, 3), dtype=torch.float64, device=planes.device)
+    with torch.cuda.device(planes.device):
+        _lib.check(lib.wb_plane_moments(planes.data_ptr(), h * w, b, bstride, _lib.dtype_code(planes.dtype),
+                                        out.data_ptr(), ws.data_ptr(), _lib.stream_ptr(planes.device)))
+    return out
+
+
+def synthesis(planes):
+    """``np.sum(planes, axis=0)`` in plane order and plane dtype, on the device.  (N,H,W) -> (H,W); (B,N,H,W) ->
+    (B,H,W)."""
+    lib = _lib.load(require_cuda=True)
+    if not planes.is_contiguous():
+        planes = planes.contiguous()
+    if planes.ndim == 3:
+        n, h, w = planes.shape
+        b, in_bs = 1, 0
+        out = torch.empty((h, w), dtype=planes.dtype, device=planes.device)
+    else:
+        b, n, h, w = planes.shape
+        in_bs = n * h * w
+        out = torch.empty((b, h, w), dtype=planes.dtype, device=planes.device)
+    with torch.cuda.device(planes.device):
+        _lib.check(lib.wb_synthesis(planes.data_ptr(), n, h * w, h * w, b, in_bs, out.data_ptr(), h * w,
+                                    _lib.dtype_code(planes.dtype), _lib.stream_ptr(planes.device)))
+    return out
+
+
+class _Noise:
+    """How a threshold kernel receives the noise: host scalar, device scalar (float64) or per-pixel map."""
+
+    __slots__ = ("host", "dev", "map")
+
+    def __init__(self, host=0.0, dev=None, map_=None):
+        self.host, self.dev, self.map = host, dev, map_
+
+    @property
+    def dev_ptr(self):
+        return 0 if self.dev is None else self.dev.data_ptr()
+
+    @property
+    def map_ptr(self):
+        return 0 if self.map is None else self.map.data_ptr()
 
 
 class Coefficients:
     """Wavelet planes plus the metadata needed to threshold them (mirror of watroo/wavelets.py:108-149).
 
     ``data``: torch CUDA tensor ``(L+1, H, W)``; ``scaling_function``: instance; ``bilateral``: what the transform
-    was run with (selects the sigma_e table); ``noise``: scalar / map, estimated lazily when first needed."""
+    was run with (selects the sigma_e table); ``noise``: None until needed, then the MAD estimate (kept on the
+    device; reading the attribute synchronises and returns a float), or whatever the caller assigned: a number or
+    a per-pixel map (ndarray / tensor)."""
 
     def __init__(self, data, scaling_function, bilateral=None):
         self.data = data
         self.scaling_function = scaling_function
         self.bilateral = bilateral
-        self.noise = None
+        self._noise = None
 
     def __len__(self):
         return len(self.data)
@@ -118,6 +236,98 @@ class Coefficients:
     @property
     def sigma_e(self):
         return self.scaling_function.sigma_e(bilateral=self.bilateral)
+
+    # -- noise ------------------------------------------------------------------------------------------------
+    @property
+    def noise(self):
+        n = self._noise
+        if isinstance(n, torch.Tensor) and n.numel() == 1 and n.dtype == torch.float64 and n.ndim <= 1:
+            return np.float64(n.item())
+        return n
+
+    @noise.setter
+    def noise(self, value):
+        self._noise = value
+
+    def get_noise(self):
+        """MAD estimate ``median(|w_0|) / 0.6745 / sigma_e[0]`` (watroo/wavelets.py:126-127) as a float64 scalar.
+        Computed on the device (exact median); this accessor synchronises to hand back a number."""
+        return np.float64(self._estimate_noise().item())
+
+    def _estimate_noise(self):
+        return abs_median_noise(self.data[0], self.sigma_e[0])
+
+    def _noise_arg(self, sigma):
+        """Resolve ``self.noise`` for a threshold kernel, estimating it lazily like the reference
+        (watroo/wavelets.py:131-132).  Returns a _Noise."""
+        if self._noise is None:
+            self._noise = self._estimate_noise()
+        n = self._noise
+        if isinstance(n, torch.Tensor):
+            if n.numel() == 1 and n.ndim <= 1:
+                if n.is_cuda and n.dtype == torch.float64:
+                    return _Noise(dev=n)
+                return _Noise(host=float(n.item()))
+            m = n.to(device=self.data.device, dtype=self.data.dtype).contiguous()
+            return _Noise(map_=m)
+        if isinstance(n, np.ndarray):
+            if n.ndim == 0:
+                return _Noise(host=float(n))
+            m = torch.from_numpy(np.ascontiguousarray(n)).to(device=self.data.device, dtype=self.data.dtype)
+            self._noise = m  # keep the device copy for the next scale
+            return _Noise(map_=m)
+        if isinstance(n, numbers.Number):
+            return _Noise(host=float(n))
+        raise TypeError(f"unsupported noise type {type(n)}")
+
+    # -- thresholding -------------------------------------------------------------------------------------------
+    def significance(self, sigma, scale, soft_threshold=True):
+        """watroo/wavelets.py:129-143.  ``sigma == 0`` or scalar ``noise == 0`` -> ones (plane dtype); soft ->
+        float64 tensor ``erf(|w_s / (sigma noise sigma_e[s])|)``; hard -> bool tensor ``|w_s| > sigma noise sigma_e[s]``
+        compared in float64."""
+        plane = self.data[scale]
+        if sigma == 0:
+            return torch.ones_like(self.data[0])
+        nz = self._noise_arg(sigma)
+        if nz.map is None and nz.dev is None and nz.host == 0:
+            return torch.ones_like(self.data[0])
+        lib = _lib.load(require_cuda=True)
+        if not plane.is_contiguous():
+            plane = plane.contiguous()
+        out = torch.empty(plane.shape, dtype=torch.float64 if soft_threshold else torch.uint8, device=plane.device)
+        with torch.cuda.device(plane.device):
+            _lib.check(lib.wb_significance(plane.data_ptr(), plane.numel(), _lib.dtype_code(plane.dtype), float(sigma),
+                                           float(self.sigma_e[scale]), nz.host, nz.dev_ptr, nz.map_ptr,
+                                           1 if soft_threshold else 0, out.data_ptr(), _lib.stream_ptr(plane.device)))
+        return out if soft_threshold else out.view(torch.bool)
+
+    def denoise(self, sigma, weights=None, soft_threshold=True):
+        """watroo/wavelets.py:145-149: ``c *= wgt * significance(sig, scl)`` in place for the first ``len(sigma)``
+        planes (the residual plane is never touched unless ``sigma`` is that long).  Returns None."""
+        if weights is None:
+            weights = (1,) * len(sigma)
+        lib = _lib.load(require_cuda=True)
+        for scl, (sig, wgt) in enumerate(zip(sigma, weights)):
+            if scl >= len(self.data):
+                break
+            self._denoise_plane(lib, scl, sig, wgt, soft_threshold)
+
+    def _denoise_plane(self, lib, scl, sig, wgt, soft_threshold):
+        plane = self.data[scl]
+        mode = 0
+        nz = _Noise()
+        if sig != 0:
+            nz = self._noise_arg(sig)
+            mode = 1 if soft_threshold else 2
+            if nz.map is None and nz.dev is None and nz.host == 0:
+                mode = 0
+        if mode == 0 and wgt == 1:
+            return
+        assert plane.is_contiguous()
+        with torch.cuda.device(plane.device):
+            _lib.check(lib.wb_denoise_plane(plane.data_ptr(), plane.numel(), 1, 0, _lib.dtype_code(plane.dtype), mode,
+                                            float(sig), float(self.sigma_e[scl]), nz.host, nz.dev_ptr, nz.map_ptr,
+                                            float(wgt), _lib.stream_ptr(plane.device)))
 
 
 class AtrousTransform:
@@ -140,20 +350,24 @@ class AtrousTransform:
         return Coefficients(planes, scaling_function, self.bilateral)
 
     def batch(self, frames, level):
-        """NEW entry point (no reference equivalent): transform a stack ``(B, H, W)`` of independent frames in one
-        launch per scale.  Returns a ``(B, level + 1, H, W)`` tensor.  Plain (non-bilateral) cascade only."""
+        """NEW entry point (no reference equivalent): transform a stack ``(B, H, W)`` of independent frames with one
+        launch per scale.  Returns a ``(B, level + 1, H, W)`` tensor."""
         stack, _ = to_device_image(frames, ndim_ok=(3,))
-        if self.bilateral is not None:
-            raise NotImplementedError("batch() supports the plain cascade only")
         return self._run(stack, int(level), self.scaling_function_class(2))
 
     # -- internals ----------------------------------------------------------------------------------------------
+    def var_factors(self, level):
+        """sigma_b[s]**2 * (s + 1 if bilateral_scaling) for s < level (watroo/wavelets.py:421-424, :434-436)."""
+        sb = bilateral_list(self.bilateral, level)
+        return [float(sb[s]) ** 2 * ((s + 1) if self.bilateral_scaling else 1) for s in range(level)]
+
     def _run(self, img, level, scaling_function):
         if level < 0:
             raise ValueError("level must be >= 0")
         lib = _lib.load(require_cuda=True)
         b, h, w, pitch, bstride = _frame_layout(img)
-        shape = (level + 1, h, w) if img.ndim == 2 else (b, level + 1, h, w)
+        batched = img.ndim == 3
+        shape = (b, level + 1, h, w) if batched else (level + 1, h, w)
         planes = torch.empty(shape, dtype=img.dtype, device=img.device)
         if self.bilateral is None:
             scratch = torch.empty((2, b, h, w), dtype=img.dtype, device=img.device) if level > 1 else None
@@ -163,8 +377,47 @@ class AtrousTransform:
                     bstride, level, scaling_function.taps_code, _lib.dtype_code(img.dtype),
                     _lib.stream_ptr(img.device)))
             return planes
-        raise NotImplementedError("bilateral cascade: kernel K2 not built yet")
+        # bilateral cascade: one fused K2 launch per scale, c_s ping-pong in scratch
+        view = planes if batched else planes.unsqueeze(0)  # (B, L+1, H, W)
+        if level == 0:
+            view[:, 0].copy_(img if batched else img.unsqueeze(0))
+            return planes
+        factors = self.var_factors(level)
+        scratch = torch.empty((2, b, h, w), dtype=img.dtype, device=img.device)
+        src = img if batched else img.unsqueeze(0)
+        for s in range(level):
+            dst_c = view[:, level] if s == level - 1 else scratch[s & 1]
+            atrous_scale(src, s, scaling_function, out_c=dst_c, out_w=view[:, s], var_factor=factors[s])
+            src = dst_c
+        return planes
+
+
+def randn_field(shape, seed, offset=0, device=None):
+    """fp32 N(0,1) field from the library's Philox generator (device stand-in for np.random.normal)."""
+    lib = _lib.load(require_cuda=True)
+    device = device or _device()
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(lib.wb_randn_f32(out.data_ptr(), out.numel(), int(seed), int(offset), _lib.stream_ptr(device)))
+    return out
 
 
 def noise_weights(scaling_function, n_scales, n_trials=100, bilateral=None, fields=None, seed=None):
-    raise NotImplementedError("compute_noise_weights: reduction kernels not built yet")
+    """compute_noise_weights (watroo/wavelets.py:221-229) on the device; see AbstractScalingFunction."""
+    if scaling_function.n_dim != 2:
+        raise NotImplementedError("wavelets_b200 covers the 2-D path only")
+    transform = AtrousTransform(scaling_function.__class__, bilateral=bilateral)
+    side = len(scaling_function.sigma_e_1d) * 2 ** n_scales
+    if seed is None:
+        seed = int(np.random.SeedSequence().entropy % (2 ** 63))
+    total = torch.zeros(n_scales, dtype=torch.float64, device=_device())
+    it = iter(fields) if fields is not None else None
+    quads = (side * side + 3) // 4
+    for trial in range(n_trials):
+        if it is not None:
+            field, _ = to_device_image(next(it))
+        else:
+            field = randn_field((side, side), seed, offset=trial * quads)
+        planes = transform._run(field, n_scales, scaling_function)
+        total += plane_moments(planes[:-1])[:, 2]
+    return (total / n_trials).cpu().numpy()
