@@ -80,6 +80,22 @@ int wb_atrous_transform(const void *in, void *planes, void *scratch, int batch, 
                         long long in_pitch, long long in_bstride, int levels, int taps, int dtype, void *stream);
 
 /*
+ * One scale of the plain cascade on ONE ROW BAND of a taller image (multi-GPU row-band sharding, no reference
+ * equivalent: the reference is single-process).  The band owns global rows [band_y0, band_y0 + band_rows) of an image
+ * of height global_H.  `in` is a buffer whose row `in_row_offset + i` holds global row band_y0 + i, for every i in
+ * [-c*2^scale, band_rows + c*2^scale) that falls inside the image (c = taps/2): the halo rows just outside the band
+ * must have been filled by the caller (neighbour exchange); rows beyond the global top/bottom are taken by symmetric
+ * reflection about global_H and must then lie inside the same window.  Output row i goes to row
+ * out_*_row_offset + i of out_c / out_w.  The arithmetic is the same as wb_atrous_scale's, so a banded cascade is
+ * bit-identical to the single-device one.
+ */
+int wb_atrous_scale_band(const void *in, void *out_c, void *out_w, int band_rows, int W, int global_H,
+                         long long band_y0, long long in_row_offset, long long in_pitch,
+                         long long out_c_row_offset, long long out_c_pitch,
+                         long long out_w_row_offset, long long out_w_pitch,
+                         int scale, int taps, int dtype, void *stream);
+
+/*
  * One scale of the BILATERAL cascade.  Replaces, per scale, watroo/wavelets.py:433-442: sdev_loc (:24-32), the
  * variance scaling (:434-436), atrous_convolution(..., bilateral_variance) (:74-105) and the subtraction (:442):
  *     var = S[in^2] - S[in]^2 (<= 0 -> 1e-20),  V = var * var_factor,  var_factor = sigma_b[s]^2 * (s+1 | 1)

@@ -1,0 +1,103 @@
+"""Host-side logic of the multi-GPU modes, on CPU: frame sharding, band geometry, and the per-scale halo exchange
+run for real over the gloo backend with world sizes 2 and 3 (the per-band arithmetic is done by the oracle here; on
+GPUs it is wb_atrous_scale_band -- see tests/test_sharded_gpu.py and tools/check_banded.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import atrous_oracle as orc
+from wavelets_b200.sharded import BandedTransform, band_range, exchange_plan, frame_shard, halo_rows
+
+
+def test_frame_shard_partitions_all_frames():
+    for n, world in ((2048, 8), (7, 3), (2, 4), (0, 2)):
+        seen = sorted(i for r in range(world) for i in frame_shard(n, r, world))
+        assert seen == list(range(n))
+    assert list(frame_shard(2048, 3, 8))[:3] == [3, 11, 19] and len(frame_shard(2048, 3, 8)) == 256
+
+
+def test_band_range_and_halo():
+    for h, world in ((32768, 8), (100, 3), (5, 4)):
+        bands = [band_range(h, r, world) for r in range(world)]
+        assert bands[0][0] == 0 and bands[-1][1] == h
+        assert all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+        sizes = [b - a for a, b in bands]
+        assert max(sizes) - min(sizes) <= 1
+    assert band_range(32768, 3, 8) == (12288, 16384)
+    assert halo_rows(11, 5) == 4096 and halo_rows(0, 3) == 1   # cfg5: s = 11 needs one whole neighbour band
+
+
+def test_exchange_plan_is_symmetric_and_complete():
+    for h, world, halo in ((64, 2, 4), (60, 3, 8), (60, 3, 32), (32, 4, 16)):
+        plans = [exchange_plan(h, world, r, halo) for r in range(world)]
+        for r in range(world):
+            recv, send = plans[r]
+            for peer, g0, g1 in recv:          # whatever I receive, the owner sends
+                assert (r, g0, g1) in plans[peer][1]
+            y0, y1 = band_range(h, r, world)
+            need = set(range(max(0, y0 - halo), y0)) | set(range(y1, min(h, y1 + halo)))
+            got = set()
+            for _, g0, g1 in recv:
+                got |= set(range(g0, g1))
+            assert got == need
+
+
+def _oracle_band_scale(ext_in, pad, out_c, out_pad, w_out, rows, width, height, y0, scale, taps_code):
+    """One scale of one band with the oracle's arithmetic (float64), reading only rows the band is entitled to."""
+    name = "b3spline" if taps_code == 5 else "triangle"
+    taps = orc.TAPS[name]
+    c, d = len(taps) // 2, 2 ** scale
+    a = ext_in.numpy()
+    xs = np.arange(width)
+    gy = np.arange(y0, y0 + rows)
+    out = np.zeros((rows, width))
+    for i, ti in enumerate(taps):
+        src = a[orc.reflect_index(gy + (i - c) * d, height) - y0 + pad]
+        rowf = np.zeros((rows, width))
+        for j, tj in enumerate(taps):
+            rowf += tj * src[:, orc.reflect_index(xs + (j - c) * d, width)]
+        out += ti * rowf
+    assert np.isfinite(out).all(), "a halo row that was never exchanged has been read"
+    out_c[out_pad:out_pad + rows] = torch.from_numpy(out)
+    w_out[:] = torch.from_numpy(a[pad:pad + rows] - out)
+
+
+def _worker(rank, world, port, height, width, level, sf_name, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import wavelets_b200 as wb
+        img = np.random.default_rng(42).standard_normal((height, width))
+        y0, y1 = band_range(height, rank, world)
+        sf = {"b3spline": wb.B3spline, "triangle": wb.Triangle}[sf_name]
+        planes = BandedTransform(sf, scale_fn=_oracle_band_scale, poison=True)(torch.from_numpy(img[y0:y1].copy()),
+                                                                              level, height)
+        np.save(os.path.join(result_dir, f"band{rank}.npy"), planes.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,height,width,level,sf", [(2, 64, 48, 4, "b3spline"), (3, 50, 40, 4, "triangle"),
+                                                         (3, 36, 32, 4, "b3spline")])
+def test_banded_cascade_over_gloo(tmp_path, world, height, width, level, sf):
+    """world_size-2/3 gloo run: bands + per-scale halo exchange reproduce the unsharded oracle cascade.  The third
+    case has halos taller than a band (multi-hop exchange) and reflections reaching into neighbour bands."""
+    mp.spawn(_worker, args=(world, _free_port(), height, width, level, sf, str(tmp_path)), nprocs=world, join=True)
+    img = np.random.default_rng(42).standard_normal((height, width))
+    want = orc.atrous_transform(img, level, sf, backend="numpy")
+    got = np.concatenate([np.load(tmp_path / f"band{r}.npy") for r in range(world)], axis=1)
+    assert got.shape == want.shape
+    for p in range(level + 1):
+        assert orc.emax(got[p], want[p]) < 1e-13, (p, orc.emax(got[p], want[p]))

@@ -110,9 +110,9 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
             uint32_t round = 0;
             for (int j = 0; j < n_load; ++j) {
                 if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
-                const int y = reflect_any((long long)r + (long long)(i0 - C + j) * p.d, p.H);
+                const long long y = reflect_any(p.gwy0 + r + (long long)(i0 - C + j) * p.d, p.Hg) - p.gwy0 + p.row_off_in;
                 mbar_arrive_expect_tx(&full[slot], row_bytes);
-                tma_load_1d(rows + (size_t)slot * p.row_stride, src + (long long)y * p.in_pitch, row_bytes,
+                tma_load_1d(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes,
                             &full[slot]);
                 if (++slot == p.slots) { slot = 0; ++round; }
             }
@@ -177,18 +177,18 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
                     c.v[e] = a;
                 }
                 if constexpr (OP == OP_TRANSFORM) {
-                    if (out_c) st_vec(out_c + orow * p.c_pitch + xg[q], c);
+                    if (out_c) st_vec(out_c + (orow + p.row_off_c) * p.c_pitch + xg[q], c);
                     if (out_w) {
                         Pack<T, V> raw = ld_vec(crow + xg[q]);
 #pragma unroll
                         for (int e = 0; e < V; ++e) raw.v[e] -= c.v[e];
-                        st_vec_cs(out_w + orow * p.w_pitch + xg[q], raw);
+                        st_vec_cs(out_w + (orow + p.row_off_w) * p.w_pitch + xg[q], raw);
                     }
                 } else {
                     Pack<T, V> raw = ld_vec(crow + xg[q]);
 #pragma unroll
                     for (int e = 0; e < V; ++e) raw.v[e] = epi.apply(raw.v[e], c.v[e]);
-                    st_vec_cs(out_w + orow * p.w_pitch + xg[q], raw);
+                    st_vec_cs(out_w + (orow + p.row_off_w) * p.w_pitch + xg[q], raw);
                 }
             }
             orow += p.d;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) atrous_generic_kernel(const ScaleParams p
         T acc = T(0);
 #pragma unroll
         for (int i = 0; i < TAPS; ++i) {
-            const T *row = in + (long long)reflect_any((long long)y + (long long)(i - C) * p.d, p.H) * p.in_pitch;
+            const T *row = in + (reflect_any(p.gwy0 + y + (long long)(i - C) * p.d, p.Hg) - p.gwy0 + p.row_off_in) * p.in_pitch;
             T ra = T(0);
 #pragma unroll
             for (int k = 0; k < TAPS; ++k) {
@@ -233,12 +233,12 @@ __global__ void __launch_bounds__(256) atrous_generic_kernel(const ScaleParams p
             }
             acc = (i == 0) ? Taps<T, TAPS>::h(0) * ra : fma_t<T>(Taps<T, TAPS>::h(i), ra, acc);
         }
-        const T raw = in[(long long)y * p.in_pitch + x];
+        const T raw = in[((long long)y + p.row_off_in) * p.in_pitch + x];
         if constexpr (OP == OP_TRANSFORM) {
-            if (out_c) out_c[(long long)frame * p.c_bstride + (long long)y * p.c_pitch + x] = acc;
-            if (out_w) out_w[(long long)frame * p.w_bstride + (long long)y * p.w_pitch + x] = raw - acc;
+            if (out_c) out_c[(long long)frame * p.c_bstride + ((long long)y + p.row_off_c) * p.c_pitch + x] = acc;
+            if (out_w) out_w[(long long)frame * p.w_bstride + ((long long)y + p.row_off_w) * p.w_pitch + x] = raw - acc;
         } else {
-            out_w[(long long)frame * p.w_bstride + (long long)y * p.w_pitch + x] = epi.apply(raw, acc);
+            out_w[(long long)frame * p.w_bstride + ((long long)y + p.row_off_w) * p.w_pitch + x] = epi.apply(raw, acc);
         }
     }
 }
@@ -309,7 +309,7 @@ static int scale_impl(const void *in, void *out_c, void *out_w, int batch, int H
     ScaleParams p;
     memset(&p, 0, sizeof(p));
     p.in = in; p.out_c = out_c; p.out_w = out_w;
-    p.H = H; p.W = W; p.d = 1 << scale;
+    p.H = H; p.W = W; p.d = 1 << scale; p.Hg = H;
     p.in_pitch = in_pitch; p.in_bstride = in_bstride;
     p.c_pitch = c_pitch; p.c_bstride = c_bstride;
     p.w_pitch = w_pitch; p.w_bstride = w_bstride;
@@ -326,7 +326,7 @@ int wb_atrous_scale_path(int H, int W, long long in_pitch, long long out_pitch, 
     wb::ScaleParams p;
     memset(&p, 0, sizeof(p));
     p.in = in; p.out_c = const_cast<void *>(out_c); p.out_w = const_cast<void *>(out_w);
-    p.H = H; p.W = W; p.d = 1 << scale;
+    p.H = H; p.W = W; p.d = 1 << scale; p.Hg = H;
     p.in_pitch = in_pitch; p.c_pitch = out_pitch; p.w_pitch = out_pitch;
     const int esize = wb::dtype_size(dtype);
     return (wb::fast_path_ok(p, taps, esize) && wb::plan_fast(p, taps, esize, 1, scale, nullptr)) ? 1 : 0;
@@ -348,6 +348,26 @@ int wb_atrous_scale(const void *in, void *out_c, void *out_w, int batch, int H, 
                           out_w_pitch, out_w_bstride, scale, taps, dtype, (cudaStream_t)stream);
 }
 
+int wb_atrous_scale_band(const void *in, void *out_c, void *out_w, int band_rows, int W, int global_H,
+                         long long band_y0, long long in_row_offset, long long in_pitch, long long out_c_row_offset,
+                         long long out_c_pitch, long long out_w_row_offset, long long out_w_pitch, int scale, int taps,
+                         int dtype, void *stream) {
+    int rc = wb::check_common(1, band_rows, W, taps, dtype);
+    if (rc) return rc;
+    if (scale < 0 || scale > 30) return WB_EINVAL_SCALE;
+    if (!in || (!out_c && !out_w) || in == out_c || in == out_w) return WB_EINVAL_POINTER;
+    if (global_H < band_rows || band_y0 < 0 || band_y0 + band_rows > global_H || in_pitch < W ||
+        (out_c && out_c_pitch < W) || (out_w && out_w_pitch < W))
+        return WB_EINVAL_ARG;
+    wb::ScaleParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = in; p.out_c = out_c; p.out_w = out_w;
+    p.H = band_rows; p.W = W; p.d = 1 << scale; p.Hg = global_H;
+    p.gwy0 = band_y0; p.row_off_in = in_row_offset; p.row_off_c = out_c_row_offset; p.row_off_w = out_w_row_offset;
+    p.in_pitch = in_pitch; p.c_pitch = out_c_pitch; p.w_pitch = out_w_pitch;
+    return wb::dispatch_typed<wb::OP_TRANSFORM>(p, 1, scale, taps, dtype, (cudaStream_t)stream);
+}
+
 int wb_wow_whiten_scale(const void *w_raw, void *out, int batch, int H, int W, long long in_pitch,
                         long long in_bstride, long long out_pitch, long long out_bstride, int scale, int taps,
                         int dtype, int sig_mode, double sigma, double sigma_e, double noise_host,
@@ -360,7 +380,7 @@ int wb_wow_whiten_scale(const void *w_raw, void *out, int batch, int H, int W, l
     wb::ScaleParams p;
     memset(&p, 0, sizeof(p));
     p.in = w_raw; p.out_c = nullptr; p.out_w = out;
-    p.H = H; p.W = W; p.d = 1 << scale;
+    p.H = H; p.W = W; p.d = 1 << scale; p.Hg = H;
     p.in_pitch = in_pitch; p.in_bstride = in_bstride;
     p.w_pitch = out_pitch; p.w_bstride = out_bstride;
     p.sig_mode = sig_mode; p.sigma = sigma; p.sigma_e = sigma_e;

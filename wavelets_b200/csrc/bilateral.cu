@@ -114,9 +114,9 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
             uint32_t round = 0;
             for (int j = 0; j < n_load; ++j) {
                 if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
-                const int y = reflect_any((long long)r + (long long)(i0 - C + j) * p.d, p.H);
+                const long long y = reflect_any(p.gwy0 + r + (long long)(i0 - C + j) * p.d, p.Hg) - p.gwy0 + p.row_off_in;
                 mbar_arrive_expect_tx(&full[slot], row_bytes);
-                tma_load_1d(rows + (size_t)slot * p.row_stride, src + (long long)y * p.in_pitch, row_bytes,
+                tma_load_1d(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes,
                             &full[slot]);
                 if (++slot == p.slots) { slot = 0; ++round; }
             }
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) bilateral_generic_kernel(const BilateralP
         T s1 = T(0), s2 = T(0);
 #pragma unroll
         for (int i = 0; i < TAPS; ++i) {
-            const T *row = in + (long long)reflect_any((long long)y + (long long)(i - C) * p.d, p.H) * p.in_pitch;
+            const T *row = in + (long long)reflect_any((long long)y + (long long)(i - C) * p.d, p.Hg) * p.in_pitch;
 #pragma unroll
             for (int k = 0; k < TAPS; ++k) {
                 const T dd = xc - row[reflect_any((long long)x + (long long)(k - C) * p.d, p.W)];
@@ -334,7 +334,7 @@ int wb_atrous_scale_bilateral(const void *in, void *out_c, void *out_w, int batc
     memset(&bp, 0, sizeof(bp));
     wb::ScaleParams &p = bp.sp;
     p.in = in; p.out_c = out_c; p.out_w = out_w;
-    p.H = H; p.W = W; p.d = 1 << scale;
+    p.H = H; p.W = W; p.d = 1 << scale; p.Hg = H;
     p.in_pitch = in_pitch; p.in_bstride = in_bstride;
     p.c_pitch = out_c_pitch; p.c_bstride = out_c_bstride;
     p.w_pitch = out_w_pitch; p.w_bstride = out_w_bstride;

@@ -10,7 +10,14 @@ struct ScaleParams {
     const void *in;
     void *out_c;
     void *out_w;
-    int H, W, d;
+    int H, W, d;     // H = number of OUTPUT rows (the whole image, or one row band of it)
+    // Row-band mode (multi-GPU, wb_atrous_scale_band): the buffers hold a window of a taller global image.
+    // Output row i of this launch is global row gwy0 + i; taps reflect about the GLOBAL height Hg; a global row g is
+    // found at buffer row g - gwy0 + row_off_in of `in` (halo rows materialised by the caller), and output row i is
+    // written to buffer row i + row_off_c / row_off_w of out_c / out_w.  Single image: Hg = H, everything else 0.
+    int Hg;
+    long long gwy0;
+    long long row_off_in, row_off_c, row_off_w;
     long long in_pitch, in_bstride, c_pitch, c_bstride, w_pitch, w_bstride;
     int wt;          // strip width in elements (= consumer threads * V * NG)
     int n_strips;    // column strips per row
