@@ -41,7 +41,8 @@ enum {
     WB_EINVAL_SHAPE = -3,
     WB_EINVAL_SCALE = -4,
     WB_EINVAL_POINTER = -5,
-    WB_EINVAL_ARG = -6
+    WB_EINVAL_ARG = -6,
+    WB_ENOT_FUSABLE = -7 /* wb_wow_scale only: shape/alignment outside the fused kernel; use the two-pass route */
 };
 
 /* ABI version of the loaded library (== WB_ABI_VERSION of the header it was built from). */
@@ -120,6 +121,27 @@ int wb_wow_whiten_scale(const void *w_raw, void *out, int batch, int H, int W,
                         long long in_pitch, long long in_bstride, long long out_pitch, long long out_bstride,
                         int scale, int taps, int dtype, int sig_mode, double sigma, double sigma_e,
                         double noise_host, const double *noise_dev, double weight, void *stream);
+
+/*
+ * One WOW scale fused in a single pass: the smooth + subtraction of wb_atrous_scale (watroo/wavelets.py:35-45, :442)
+ * AND the whitening of wb_wow_whiten_scale (watroo/utils.py:177,193-203) without ever writing the raw detail plane:
+ *     out_c = S_scale[in]                                 (c_{s+1}, needed by the next scale)
+ *     w     = in - out_c;  P = S_scale[w^2] (<= 0 -> 1e-15)
+ *     out_w = w * significance(w) * (weight / sqrt(P))    (the final, whitened plane s)
+ * 3 elements of HBM traffic per pixel instead of 5; results are bit-identical to wb_atrous_scale followed by
+ * wb_wow_whiten_scale.  The fused kernel stages whole rows on chip: it takes 16-byte aligned, vector-multiple widths
+ * up to 4096 (float32) / 2048 (float64) columns; anything else returns WB_ENOT_FUSABLE before launching anything
+ * (wb_wow_scale_path() == 0 tells beforehand) and the caller takes the two-pass route.  Significance arguments as in
+ * wb_wow_whiten_scale.  `out_c`, `out_w` and `in` must be three distinct buffers.
+ */
+int wb_wow_scale_path(int batch, int H, int W, long long in_pitch, long long out_c_pitch, long long out_w_pitch,
+                      int scale, int taps, int dtype, const void *in, const void *out_c, const void *out_w);
+int wb_wow_scale(const void *in, void *out_c, void *out_w, int batch, int H, int W,
+                 long long in_pitch, long long in_bstride,
+                 long long out_c_pitch, long long out_c_bstride,
+                 long long out_w_pitch, long long out_w_bstride,
+                 int scale, int taps, int dtype, int sig_mode, double sigma, double sigma_e,
+                 double noise_host, const double *noise_dev, double weight, void *stream);
 
 /*
  * Exact median of |x| over n contiguous elements per frame, on the device and without host synchronisation.

@@ -285,3 +285,71 @@ def test_wow_full_size_cfg3(dt, bilateral):
         want = (w / torch.sqrt(torch.clamp(power, min=1e-15)))[1000:1016]
         got = co.data[s][1000:1016].to(torch.float64)
         assert ((got - want).abs().max() / want.abs().max()).item() < (2e-6 if dt == np.float32 else 1e-13)
+
+
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+@pytest.mark.parametrize("sf", ["b3spline", "triangle"])
+def test_wow_fused_scale_equals_two_pass(dt, sf):
+    """wb_wow_scale (K1+K3 in one pass, raw w_s kept on chip) equals wb_atrous_scale followed by
+    wb_wow_whiten_scale (bit for bit away from the top/bottom border), for every scale / significance mode / shape the fused kernel takes, and declines the rest."""
+    import wavelets_b200 as wb
+    from wavelets_b200 import _lib, utils
+    from wavelets_b200.wavelets import atrous_scale
+    lib = _lib.load(require_cuda=True)
+    tdt = getattr(torch, dt)
+    scf = _sf(sf)(2)
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    for (b, h, w) in ((1, 96, 128), (2, 67, 264), (1, 300, 1024), (1, 40, 2048), (3, 33, 32)):
+        src = torch.randn((b, h, w), generator=gen, device="cuda", dtype=tdt) * 3 + 1
+        noise_dev = torch.tensor([0.7, 1.1, 0.9][:b], dtype=torch.float64, device="cuda")
+        for s in range(0, 8):
+            if (scf.taps_code // 2) * 2 ** s > w:
+                break
+            for mode, nz in ((0, utils._Noise()), (1, utils._Noise(dev=noise_dev)), (2, utils._Noise(host=0.8))):
+                c_ref, w_raw = atrous_scale(src, s, scf)
+                w_ref = torch.empty_like(src)
+                utils._whiten_scale(lib, w_raw, w_ref, s, scf, mode, 2.5, 0.3, nz, 1.25)
+                c_f, w_f = torch.full_like(src, float("nan")), torch.full_like(src, float("nan"))
+                ok = utils._wow_scale_fused(lib, src, c_f, w_f, s, scf, mode, 2.5, 0.3, nz, 1.25)
+                assert ok == bool(lib.wb_wow_scale_path(b, h, w, w, w, w, s, scf.taps_code, _lib.dtype_code(tdt),
+                                                        src.data_ptr(), c_f.data_ptr(), w_f.data_ptr()))
+                assert ok, (b, h, w, s)
+                assert torch.equal(c_f, c_ref), (b, h, w, s, mode)
+                # rows whose power window reaches beyond the top/bottom border see c_{s+1} of a virtual (reflected)
+                # row, summed in the mirrored order: equal up to rounding there, bit-identical everywhere else
+                edge = (scf.taps_code // 2) * 2 ** s
+                if h > 2 * edge:
+                    assert torch.equal(w_f[:, edge:h - edge], w_ref[:, edge:h - edge]), (b, h, w, s, mode)
+                rel = (w_f - w_ref).abs() / w_ref.abs().max()
+                tol = 1e-5 if dt == "float32" else 1e-13
+                if mode == 2:  # an ulp in w_s may flip a coefficient that sits on the hard threshold
+                    assert (rel > tol).float().mean().item() < 1e-3, (b, h, w, s, mode)
+                else:
+                    assert rel.max().item() < tol, (b, h, w, s, mode, rel.max().item())
+    # shapes outside the fused kernel are declined before anything is launched
+    wide = torch.randn((1, 16, 8192), device="cuda", dtype=tdt)
+    out1, out2 = torch.zeros_like(wide), torch.zeros_like(wide)
+    assert not utils._wow_scale_fused(lib, wide, out1, out2, 0, scf, 0, 0.0, 1.0, utils._Noise(), 1.0)
+    odd = torch.randn((1, 16, 131), device="cuda", dtype=tdt)
+    o1, o2 = torch.zeros_like(odd), torch.zeros_like(odd)
+    assert not utils._wow_scale_fused(lib, odd, o1, o2, 0, scf, 0, 0.0, 1.0, utils._Noise(), 1.0)
+    assert not out1.any() and not o1.any()
+    # whole pipeline: fused and two-pass wow() agree bit for bit
+    img = torch.from_numpy(orc.solar_like(512, seed=3, flux=0.05, dtype=np.dtype(dt).type)).cuda()
+    for kw in ({}, dict(denoise_coefficients=[5, 2]), dict(denoise_coefficients=[0, 3], soft_threshold=False, noise=2.0),
+               dict(weights=[0.5, 2.0], noise=1.5, denoise_coefficients=[4])):
+        utils.FUSED_WOW = True
+        r1, c1 = wb.wow(img, scaling_function=_sf(sf), **kw)
+        utils.FUSED_WOW = False
+        try:
+            r2, c2 = wb.wow(img, scaling_function=_sf(sf), **kw)
+        finally:
+            utils.FUSED_WOW = True
+        if kw.get("soft_threshold", True):
+            assert orc.emax(r1.cpu().numpy(), r2.cpu().numpy()) < (1e-5 if dt == "float32" else 1e-12), kw
+            assert orc.emax(c1.data.cpu().numpy(), c2.data.cpu().numpy()) < (1e-5 if dt == "float32" else 1e-12), kw
+        else:
+            rel = (c1.data - c2.data).abs() / c2.data.abs().amax(dim=(1, 2), keepdim=True)
+            assert (rel > 1e-5).float().mean().item() < 1e-3, kw
+        interior = slice(64, 512 - 64)  # scales 0-4 of the 512^2 frame: no virtual rows involved
+        assert torch.equal(c1.data[:5, interior], c2.data[:5, interior]), kw

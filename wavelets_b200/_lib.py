@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_PKG, "libwavelets_b200.so")
 
 WB_F32, WB_F64 = 0, 1
 WB_TRIANGLE, WB_B3SPLINE = 3, 5
+WB_ENOT_FUSABLE = -7
 ABI_VERSION = 1
 
 _lock = threading.Lock()
@@ -40,6 +41,10 @@ SIGNATURES = {
                                            _c_ll, _c_ll, _c_int, _c_int, _c_int, _c_dbl, _c_vp]),
     "wb_wow_whiten_scale": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll, _c_int, _c_int,
                                      _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_vp, _c_dbl, _c_vp]),
+    "wb_wow_scale_path": (_c_int, [_c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_int, _c_int, _c_int, _c_vp, _c_vp,
+                                   _c_vp]),
+    "wb_wow_scale": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll, _c_ll, _c_ll,
+                              _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_vp, _c_dbl, _c_vp]),
     "wb_abs_median_workspace_bytes": (_c_sz, [_c_int, _c_int]),
     "wb_abs_median": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_int, _c_vp, _c_vp, _c_dbl, _c_vp, _c_vp]),
     "wb_plane_moments_workspace_bytes": (_c_sz, [_c_int]),

@@ -14,6 +14,7 @@ const char *wb_error_string(int status) {
         case WB_EINVAL_SCALE: return "invalid scale / number of levels";
         case WB_EINVAL_POINTER: return "null or aliasing device pointer";
         case WB_EINVAL_ARG: return "invalid argument (pitch smaller than width, bad count, ...)";
+        case WB_ENOT_FUSABLE: return "shape or alignment outside the fused WOW kernel (use the two-pass route)";
         default: break;
     }
     if (status > 0) return cudaGetErrorString((cudaError_t)status);

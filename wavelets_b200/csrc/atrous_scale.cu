@@ -20,43 +20,9 @@
 //   * Anything the vector path cannot take (W % V != 0, unaligned pointers, 2^s*c > W so more than one reflection)
 //     goes to a generic gather kernel with the full modular reflection.
 #include "pipeline.cuh"
+#include "whiten.cuh"
 
 namespace wb {
-
-// Whitening of one coefficient (watroo/utils.py:195-203 + watroo/wavelets.py:129-143), P = S_s[w^2] at that pixel.
-template <typename T> struct WhitenEpilogue {
-    int mode;
-    double thr;  // (sigma * noise) * sigma_e
-    T thr_t;
-    T weight;
-    __device__ __forceinline__ void init(const ScaleParams &p, int frame) {
-        mode = p.sig_mode;
-        thr = 0.0;
-        if (mode) {
-            const double noise = p.noise_dev ? p.noise_dev[frame] : p.noise_host;
-            if (noise == 0.0) mode = 0;  // scalar noise == 0 -> significance is all ones (wavelets.py:134-135)
-            thr = (p.sigma * noise) * p.sigma_e;
-        }
-        thr_t = (T)thr;
-        weight = (T)p.weight;
-    }
-    __device__ __forceinline__ T apply(T w, T power) const {
-        if (power <= T(0)) power = T(1e-15);
-        const T lp = sqrt(power);
-        if (mode == 1) {
-            if constexpr (sizeof(T) == 4) {
-                // the reference multiplies by erf() evaluated in float64 and rounds the product to fp32; erff on
-                // the fp32 ratio differs from that by a few fp32 ulp of the product
-                w = w * erff(fabsf(w / thr_t));
-            } else {
-                w = w * erf(fabs(w / thr));
-            }
-        } else if (mode == 2) {
-            w = (fabs((double)w) > thr) ? w : T(0);  // compared in float64 like NumPy >= 2 does
-        }
-        return w * (weight / lp);
-    }
-};
 
 template <typename T, int TAPS, int DMODE, int NG, int OP>
 __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
@@ -170,12 +136,7 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
                 if (!act[q]) continue;
                 Pack<T, V> c;
 #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    T a = Taps<T, TAPS>::h(0) * ring[0][q].v[e];
-#pragma unroll
-                    for (int k = 1; k < TAPS; ++k) a = fma_t<T>(Taps<T, TAPS>::h(k), ring[k][q].v[e], a);
-                    c.v[e] = a;
-                }
+                for (int e = 0; e < V; ++e) c.v[e] = col_pass<T, TAPS, NG>(ring, q, e);
                 if constexpr (OP == OP_TRANSFORM) {
                     if (out_c) st_vec(out_c + (orow + p.row_off_c) * p.c_pitch + xg[q], c);
                     if (out_w) {

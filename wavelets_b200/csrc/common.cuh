@@ -84,17 +84,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// The suspend-time hint lets the hardware park a waiting warp instead of having it spin through try_wait / branch
+// pairs that steal issue slots from the warps doing arithmetic.
+static constexpr uint32_t kMbarSuspendHintNs = 2000;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WB_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra WB_DONE_%=;\n"
         "bra WB_WAIT_%=;\n"
         "WB_DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(kMbarSuspendHintNs)
         : "memory");
 }
 // 1-D bulk asynchronous copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, both 16B aligned).

@@ -117,6 +117,17 @@ __device__ __forceinline__ Pack<T, VecOf<T>::V> row_pass(const T *srow, const Ta
     return row_pass_impl<T, TAPS, DMODE, SQUARE, true>(srow, tp);
 }
 
+// Column pass over the register ring of the last TAPS row-filtered rows, oldest row first:
+// ((((h_0 r_0) + h_1 r_1) + h_2 r_2) + ...).  The fused WOW kernel (wow_scale.cu, col_feed) accumulates in the same
+// order, so that its planes equal K1 followed by K3 bit for bit wherever no virtual (reflected) row is involved.
+template <typename T, int TAPS, int NG>
+__device__ __forceinline__ T col_pass(const Pack<T, VecOf<T>::V> (&ring)[TAPS][NG], int q, int e) {
+    T a = Taps<T, TAPS>::h(0) * ring[0][q].v[e];
+#pragma unroll
+    for (int k = 1; k < TAPS; ++k) a = fma_t<T>(Taps<T, TAPS>::h(k), ring[k][q].v[e], a);
+    return a;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Host: geometry planning
 // ---------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,63 @@
+// Whitening epilogue shared by K3 (wb_wow_whiten_scale) and the fused K1+K3 kernel (wb_wow_scale).
+#pragma once
+
+#include "pipeline.cuh"
+
+namespace wb {
+
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Whitening of one coefficient (watroo/utils.py:195-203 + watroo/wavelets.py:129-143), P = S_s[w^2] at that pixel:
+//     w' = w * significance(w) * (weight / sqrt(P > 0 ? P : 1e-15))
+// fp32: weight / sqrt(P) is evaluated as weight * rsqrt.approx(P) (MUFU.RSQ, <= 2 ulp) instead of the reference's
+// sqrt -> divide -> multiply chain (three roundings): a few 1e-7 relative, far inside the 1e-5 parity budget, and
+// 5 instructions per pixel instead of ~30 (the fused kernel is issue-bound, not HBM-bound, otherwise).
+// fp64 keeps the exact sqrt and divide.  Soft threshold: erf(|w / thr|) with the reciprocal of thr hoisted (fp32);
+// hard threshold: NumPy >= 2 compares |w| (fp32) with the float64 threshold; |w| > thr in float64 is equivalent to
+// |w| > RD(thr) in fp32 (RD = round towards -inf), so the mask stays bit-exact without float64 instructions.
+template <typename T> struct WhitenEpilogue {
+    int mode;
+    T thr_cmp;  // hard threshold in the plane dtype, rounded down
+    T thr;      // fp64: the threshold itself (soft); fp32: unused
+    T inv_thr;  // fp32 soft: 1 / thr
+    T weight;
+    __device__ __forceinline__ void init(const ScaleParams &p, int frame) {
+        mode = p.sig_mode;
+        double t = 0.0;
+        if (mode) {
+            const double noise = p.noise_dev ? p.noise_dev[frame] : p.noise_host;
+            if (noise == 0.0) mode = 0;  // scalar noise == 0 -> significance is all ones (wavelets.py:134-135)
+            t = (p.sigma * noise) * p.sigma_e;  // (sigma * noise) * sigma_e, float64 as in the reference
+        }
+        if constexpr (sizeof(T) == 4) {
+            thr_cmp = __double2float_rd(t);
+            thr = (T)t;
+            inv_thr = (T)(1.0 / t);
+        } else {
+            thr_cmp = t;
+            thr = t;
+            inv_thr = T(0);
+        }
+        weight = (T)p.weight;
+    }
+    __device__ __forceinline__ T apply(T w, T power) const {
+        power = (power <= T(0)) ? T(1e-15) : power;
+        T g;
+        if constexpr (sizeof(T) == 4) g = weight * rsqrt_fast(power);
+        else g = weight / sqrt(power);
+        if (mode == 1) {
+            // the reference multiplies by erf() evaluated in float64 and rounds the product to the plane dtype
+            if constexpr (sizeof(T) == 4) w = w * erff(fabsf(w * inv_thr));
+            else w = w * erf(fabs(w / thr));
+        } else if (mode == 2) {
+            w = (fabs(w) > thr_cmp) ? w : T(0);
+        }
+        return w * g;
+    }
+};
+
+}  // namespace wb

@@ -19,6 +19,9 @@ from .wavelets import (AtrousTransform, Coefficients, _Noise, _frame_layout, abs
 
 __all__ = ["denoise", "wow", "wow_batch", "generalized_anscombe"]
 
+# Development switch (tests compare the fused one-pass WOW scales against the two-pass route bit for bit).
+FUSED_WOW = True
+
 
 def generalized_anscombe(signal, alpha=1, g=0, sigma=0, inverse=False):
     """Variance-stabilising transform and its algebraic inverse (watroo/wavelets.py:14-21), element-wise on a torch
@@ -87,6 +90,23 @@ def _whiten_scale(lib, w_raw, out, s, scaling_function, sig_mode, sigma, sigma_e
                                            _lib.stream_ptr(w_raw.device)))
 
 
+def _wow_scale_fused(lib, src, dst_c, out_w, s, scaling_function, sig_mode, sigma, sigma_e, nz, weight):
+    """One fused WOW scale (wb_wow_scale).  Returns False without launching anything when the problem is outside the
+    fused kernel (the caller then takes the two-pass route)."""
+    b, h, w, pitch, bstride = _frame_layout(src)
+    _, _, _, c_pitch, c_bstride = _frame_layout(dst_c)
+    _, _, _, w_pitch, w_bstride = _frame_layout(out_w)
+    with torch.cuda.device(src.device):
+        rc = lib.wb_wow_scale(src.data_ptr(), dst_c.data_ptr(), out_w.data_ptr(), b, h, w, pitch, bstride, c_pitch,
+                              c_bstride, w_pitch, w_bstride, s, scaling_function.taps_code, _lib.dtype_code(src.dtype),
+                              sig_mode, float(sigma), float(sigma_e), nz.host, nz.dev_ptr, float(weight),
+                              _lib.stream_ptr(src.device))
+    if rc == _lib.WB_ENOT_FUSABLE:
+        return False
+    _lib.check(rc)
+    return True
+
+
 def _scalar_noise(noise, device):
     """None -> None; number / 0-d array / 1-element tensor -> _Noise with a host or device scalar."""
     if noise is None:
@@ -106,10 +126,11 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
                soft_threshold, noise):
     """The fused WOW pipeline on a stack (B, H, W) of frames.  Returns (recon (B,H,W), planes (B,L+1,H,W), noise).
 
-    Per scale: K1/K2 writes c_{s+1} into a ping-pong scratch and the raw w_s into a one-plane scratch; K3 reads the
-    raw plane once, forms the local power S_s[w_s^2], applies significance and whitening and writes the final plane.
-    Raw detail planes never reach the output array, the MAD noise is estimated on the device from the raw w_0
-    (no host synchronisation anywhere), the residual plane is rescaled in place and K5 sums the planes."""
+    Per plain scale ONE fused launch (wb_wow_scale: smooth, detail, local power, significance, whitening; the raw
+    detail plane never exists in HBM).  Bilateral scales, and scale 0 when the MAD noise must first be estimated from
+    the raw w_0, take two passes: K1/K2 writes c_{s+1} into a ping-pong scratch and the raw w_s into a one-plane
+    scratch, K3 whitens it into the output.  The noise is estimated on the device (no host synchronisation anywhere),
+    the residual plane is rescaled in place and K5 sums the planes."""
     lib = _lib.load(require_cuda=True)
     sf = scaling_function_class(2)
     b, h, w = stack.shape
@@ -122,27 +143,36 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
     factors = transform.var_factors(L) if bilateral is not None else [None] * L
     if L == 0:
         planes[:, 0].copy_(stack)
-    scratch = torch.empty((3, b, h, w), dtype=dt, device=dev) if L > 0 else None
+    scratch = torch.empty((2, b, h, w), dtype=dt, device=dev) if L > 1 else None
+    raw_plane = None  # one-plane scratch for the raw w_s of the two-pass route, allocated on first use
     nz = noise  # _Noise or None
     src = stack
     for s in range(L):
         dst_c = planes[:, L] if s == L - 1 else scratch[s & 1]
         d, wt = dns[s], wts[s]
         need_sig = d != 0
+        mode = (1 if soft_threshold else 2) if need_sig else 0
         if whitening:
-            w_raw = scratch[2]
-            atrous_scale(src, s, sf, out_c=dst_c, out_w=w_raw, var_factor=factors[s])
-            if need_sig and nz is None:
-                # lazily, from the current state of plane 0 (raw w_0 when s == 0) -- watroo/wavelets.py:131-132
-                nz = _Noise(dev=abs_median_noise(w_raw if s == 0 else planes[:, 0], sigma_e[0]))
-            mode = (1 if soft_threshold else 2) if need_sig else 0
-            _whiten_scale(lib, w_raw, planes[:, s], s, sf, mode, d, sigma_e[s] if need_sig else 1.0,
-                          nz if need_sig else _Noise(), wt)
+            if need_sig and nz is None and s > 0:
+                # lazily, from the current state of plane 0 (already whitened here) -- watroo/wavelets.py:131-132
+                nz = _Noise(dev=abs_median_noise(planes[:, 0], sigma_e[0]))
+            # One pass (K1+K3 fused, raw w_s stays on chip) unless the scale is bilateral, the MAD noise has to be
+            # estimated from the raw w_0 first (grid-wide dependency), or the shape is outside the fused kernel.
+            fused = FUSED_WOW and factors[s] is None and not (need_sig and nz is None) and \
+                _wow_scale_fused(lib, src, dst_c, planes[:, s], s, sf, mode, d, sigma_e[s] if need_sig else 1.0,
+                                 nz if need_sig else _Noise(), wt)
+            if not fused:
+                if raw_plane is None:
+                    raw_plane = torch.empty((b, h, w), dtype=dt, device=dev)
+                atrous_scale(src, s, sf, out_c=dst_c, out_w=raw_plane, var_factor=factors[s])
+                if need_sig and nz is None:
+                    nz = _Noise(dev=abs_median_noise(raw_plane, sigma_e[0]))  # s == 0: from the raw w_0
+                _whiten_scale(lib, raw_plane, planes[:, s], s, sf, mode, d, sigma_e[s] if need_sig else 1.0,
+                              nz if need_sig else _Noise(), wt)
         else:
             atrous_scale(src, s, sf, out_c=dst_c, out_w=planes[:, s], var_factor=factors[s])
             if need_sig and nz is None:
                 nz = _Noise(dev=abs_median_noise(planes[:, 0], sigma_e[0]))
-            mode = (1 if soft_threshold else 2) if need_sig else 0
             if mode or wt != 1:
                 use = nz if need_sig else _Noise()
                 with torch.cuda.device(dev):
