@@ -158,6 +158,45 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def solar_like_device(n, dtype, device, seed=2, flux=0.05):
+    """Synthetic solar-like frame generated on the device (SURVEY.md 8(d) 'S': limb-darkened disk + exponential corona
+    + 30 Gaussian active regions + background, photon noise, integer counts)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    ax = torch.arange(n, device=device, dtype=torch.float64)
+    y, x = torch.meshgrid(ax, ax, indexing="ij")
+    r = torch.hypot(x - n / 2, y - n / 2) / (0.4 * n)
+    img = torch.where(r < 1, 2000 * (0.4 + 0.6 * torch.sqrt(torch.clamp(1 - r ** 2, min=0))),
+                      800 * torch.exp(-(torch.clamp(r, min=1) - 1) / 0.15))
+    for _ in range(30):
+        cx, cy = ((torch.rand(2, generator=g, device=device) * 0.6 + 0.2) * n).tolist()
+        sg = float(torch.rand(1, generator=g, device=device) * 27 + 3) * n / 1024
+        amp = float(torch.rand(1, generator=g, device=device) * 7500 + 500)
+        img += amp * torch.exp(-((x - cx) ** 2 + (y - cy) ** 2) / (2 * sg ** 2))
+    img = (img + 20) * flux
+    img = img + torch.sqrt(img) * torch.randn(img.shape, generator=g, device=device, dtype=torch.float64)
+    return torch.round(torch.clamp(img, min=0)).to(dtype)
+
+
+def time_wow(wb, img, reps, peak, **kw):
+    """Device-resident wow(): frames/s and the algorithmic-byte roofline of SURVEY.md 8(d), (5L+3)*sizeof(T) B/pixel."""
+    import torch
+    for _ in range(3):
+        _, co = wb.wow(img, **kw)
+    levels = len(co) - 1
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        wb.wow(img, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    algo = (5 * levels + 3) * img.element_size() * img.numel()
+    return {"frames_per_s": 1e3 / ms, "ms_per_frame": ms, "scales": levels, "algorithmic_bytes_per_frame": algo,
+            "achieved_gbs": algo / ms / 1e6, "frac_of_hbm_peak": algo / ms / 1e6 / peak}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -247,6 +286,19 @@ def run_ours(args):
     value = units_per_step * args.steps * world / (elapsed_ms / 1e3)
     e2e_value = units_per_step * e2e_steps * world / (e2e_ms / 1e3)
 
+    # ---- WOW frames/s (BASELINE.json configs[2]), device-resident, rank 0 reports its own GPU ---------------------
+    wow_keys = {}
+    if rank == 0 and not args.no_wow:
+        peak_w, _ = measured_peaks()
+        solar = solar_like_device(N_SIDE, torch.float32, dev)
+        wow_keys["wow"] = time_wow(wb, solar, 30, peak_w)
+        wow_keys["wow_bilateral"] = time_wow(wb, solar, 15, peak_w, bilateral=1, denoise_coefficients=[5, 2])
+        wow_keys["wow"]["call"] = "wow(4096x4096 fp32 solar-like)"
+        wow_keys["wow_bilateral"]["call"] = "wow(4096x4096 fp32 solar-like, bilateral=1, denoise_coefficients=[5, 2])"
+        wow_keys["wow_bilateral"]["bound"] = "FMA/MUFU pipes (24 exp + ~190 fp32 ops per pixel per scale), not HBM"
+    if world > 1:
+        dist.barrier()
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         launch_ms = elapsed_ms / (args.steps * LEVELS)
@@ -271,6 +323,7 @@ def run_ours(args):
             "gpu_launches": args.steps * LEVELS,
             "clocks": clocks,
         }
+        line.update(wow_keys)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -282,6 +335,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-wow", action="store_true", help="skip the extra WOW frames/s measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

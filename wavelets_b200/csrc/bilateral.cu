@@ -201,6 +201,254 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 fast path: packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2), one PAIR of adjacent pixels per thread.
+//
+// The kernel is bound by the FMA and MUFU pipes, not by HBM (24 exponentials and ~190 fp32 operations per pixel), and
+// with scalar code it is bound by instruction ISSUE before either pipe saturates (ncu: 350 instructions per pixel, 64 %
+// issue-active, FMA pipe 44 %, XU pipe 41 %).  sm_100a's packed fp32 instructions do two fp32 operations per lane per
+// issue slot (tools/fma2bench.cu: 8 FFMA2 + 2 MUFU sustain 117 fma/clk/SM with the MUFU pipe at 92 %, 16 FFMA + 2 MUFU
+// only 98), so the pixel pair is carried as one 64-bit register pair end to end: LDS.64 delivers it, every D, k*D,
+// D^2, exponent argument and accumulation is one packed instruction, only the two ex2.approx are scalar.
+// Reflected taps are the mirrored pair read backwards (halves swapped), a path only border threads take.
+// Differences to the scalar formulation (all far below the fp32 parity budget): the tap weight enters through the
+// exponent (2^(a + log2 k) instead of k 2^a), 1/(2V) and the final num/den use rcp.approx.
+// ---------------------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void up2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 lds64(uint32_t a) {
+    u64 r;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ u64 swap2(u64 v) { float lo, hi; up2(v, lo, hi); return pk2(hi, lo); }
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// log2 of the taps (dyadic rationals except 3/8): log2(h_i h_k) = l_i + l_k
+template <int TAPS> struct TapLog2;
+template <> struct TapLog2<3> { __host__ __device__ static constexpr float l(int k) { return k == 1 ? -1.0f : -2.0f; } };
+template <> struct TapLog2<5> {
+    __host__ __device__ static constexpr float l(int k) { return k == 2 ? -1.4150374992788437f : ((k == 1 || k == 3) ? -2.0f : -4.0f); }
+};
+
+// DMODE 0: dilation even (>= 2): tap pair k is one aligned LDS.64 at column x + (k - C) d.
+// DMODE 1: dilation 1: three aligned LDS.64 at x-2, x, x+2 form a 6-pixel window the taps are picked from.
+template <int TAPS, int DMODE> struct PairPlan { static constexpr int NL = (DMODE == 0) ? TAPS : 3; };
+
+template <int TAPS, int DMODE, bool MIRROR>
+__device__ __forceinline__ void pair_taps(uint32_t rowb, const uint32_t (&colb)[PairPlan<TAPS, DMODE>::NL], unsigned rev,
+                                          u64 (&out)[TAPS]) {
+    constexpr int C = TAPS / 2;
+    if constexpr (DMODE == 0) {
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            u64 t = lds64(rowb + colb[k]);
+            if (MIRROR && ((rev >> k) & 1u)) t = swap2(t);
+            out[k] = t;
+        }
+    } else {
+        float win[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            u64 t = lds64(rowb + colb[k]);
+            if (MIRROR && ((rev >> k) & 1u)) t = swap2(t);
+            up2(t, win[2 * k], win[2 * k + 1]);
+        }
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) out[k] = pk2(win[2 + (k - C)], win[3 + (k - C)]);
+    }
+}
+
+// One step of the software pipeline (see the kernel): range weights + output of the OLD row from the differences in
+// D, differences + variance sums of the NEW row into D.  OLD / NEW are compile-time so the prologue (NEW only) and
+// the drain (OLD only) cost no selects in the steady state.
+template <int TAPS, int DMODE, bool OLD, bool NEW>
+__device__ __forceinline__ void pair_step(u64 (&D)[TAPS][TAPS], u64 &xc_old, u64 &nhi, const uint32_t (&rowb)[TAPS],
+                                          uint32_t cb, const uint32_t (&colb)[PairPlan<TAPS, DMODE>::NL], unsigned rev,
+                                          float var_factor, float *c_dst, float *w_dst, bool act) {
+    constexpr int C = TAPS / 2;
+    const float kc = Taps<float, TAPS>::h(C) * Taps<float, TAPS>::h(C);
+    u64 xc = 0ull;
+    if (NEW) xc = lds64(rowb[C] + cb);
+    u64 s1 = 0ull, s2 = 0ull;  // packed +0.0f
+    u64 num = 0ull, den = pk2(kc, kc);
+#pragma unroll
+    for (int i = 0; i < TAPS; ++i) {
+        u64 tv[TAPS];
+        if (NEW) {
+            if (rev == 0) pair_taps<TAPS, DMODE, false>(rowb[i], colb, rev, tv);
+            else pair_taps<TAPS, DMODE, true>(rowb[i], colb, rev, tv);
+        }
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            if (OLD && !(i == C && k == C)) {
+                const float lk = TapLog2<TAPS>::l(i) + TapLog2<TAPS>::l(k);
+                const u64 dd = D[i][k];
+                float a0, a1;
+                up2(fma2(mul2(dd, dd), nhi, pk2(lk, lk)), a0, a1);
+                const u64 gw = pk2(exp2_fast(a0), exp2_fast(a1));
+                den = add2(den, gw);
+                num = fma2(gw, dd, num);
+            }
+            if (NEW) {
+                const float kk = Taps<float, TAPS>::h(i) * Taps<float, TAPS>::h(k);
+                const u64 dn = sub2(xc, tv[k]);
+                D[i][k] = dn;
+                const u64 kd = mul2(pk2(kk, kk), dn);
+                s1 = add2(s1, kd);
+                s2 = fma2(kd, dn, s2);
+            }
+        }
+    }
+    if (OLD) {
+        float n0, n1, d0, d1, x0v, x1v;
+        up2(num, n0, n1);
+        up2(den, d0, d1);
+        up2(xc_old, x0v, x1v);
+        const float c0 = x0v - n0 * rcp_fast(d0), c1 = x1v - n1 * rcp_fast(d1);
+        if (act) {
+            if (c_dst) *reinterpret_cast<float2 *>(c_dst) = make_float2(c0, c1);
+            if (w_dst) __stcs(reinterpret_cast<float2 *>(w_dst), make_float2(x0v - c0, x1v - c1));
+        }
+    }
+    if (NEW) {
+        // var = S[x^2] - S[x]^2 in centred form; V = max(var, 1e-20) * var_factor; exponent scale -log2(e) / (2 V)
+        float v0, v1;
+        up2(sub2(s2, mul2(s1, s1)), v0, v1);
+        v0 = (v0 <= 0.0f) ? 1e-20f : v0;
+        v1 = (v1 <= 0.0f) ? 1e-20f : v1;
+        nhi = pk2(-0.72134752044448170f * rcp_fast(v0 * var_factor), -0.72134752044448170f * rcp_fast(v1 * var_factor));
+        xc_old = xc;
+    }
+}
+
+template <int TAPS, int DMODE>
+__global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const BilateralParams bp) {
+    const ScaleParams &p = bp.sp;
+    constexpr int C = TAPS / 2;
+    constexpr int NL = PairPlan<TAPS, DMODE>::NL;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *rows = reinterpret_cast<float *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)p.slots * p.row_stride * sizeof(float));
+    uint64_t *empty = full + p.slots;
+
+    const int nt = blockDim.x - 32;  // 8 consumer warps; the last warp is the TMA producer
+    const int nwc = nt >> 5;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    int bx = blockIdx.x;
+    const int strip = bx % p.n_strips;
+    bx /= p.n_strips;
+    const int r = bx % p.d;
+    const int g = bx / p.d;
+    const int frame = blockIdx.y;
+
+    const int n_chain = (r < p.H) ? (p.H - r + p.d - 1) / p.d : 0;
+    const int i0 = g * p.seg;
+    const int n_out = min(p.seg, n_chain - i0);
+    if (n_out <= 0) return;
+    const int n_load = n_out + 2 * C;
+
+    const int x0 = strip * p.wt;
+    const int lo = max(0, x0 - p.halo_al);
+    const int hi = min(p.W, x0 + p.wt + p.halo_al);
+    const uint32_t row_bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(float);
+    const uint32_t RB = (uint32_t)p.row_stride * (uint32_t)sizeof(float);
+
+    if (tid == 0) {
+        for (int s = 0; s < p.slots; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nwc);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == nwc) {
+        if (lane == 0) {
+            const float *src = reinterpret_cast<const float *>(p.in) + (long long)frame * p.in_bstride + lo;
+            int slot = 0;
+            uint32_t round = 0;
+            for (int j = 0; j < n_load; ++j) {
+                if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
+                const long long y = reflect_any(p.gwy0 + r + (long long)(i0 - C + j) * p.d, p.Hg) - p.gwy0 + p.row_off_in;
+                mbar_arrive_expect_tx(&full[slot], row_bytes);
+                tma_load_1d(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[slot]);
+                if (++slot == p.slots) { slot = 0; ++round; }
+            }
+        }
+        return;
+    }
+
+    float *out_c = reinterpret_cast<float *>(p.out_c);
+    float *out_w = reinterpret_cast<float *>(p.out_w);
+    if (out_c) out_c += (long long)frame * p.c_bstride;
+    if (out_w) out_w += (long long)frame * p.w_bstride;
+
+    int xg = x0 + tid * 2;
+    const bool act = xg < p.W && xg < x0 + p.wt;
+    if (!act) xg = x0;  // idle threads shadow the first pair of the strip; their stores are masked
+    uint32_t colb[NL];
+    unsigned rev = 0;
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+        const int pcol = xg + (k - NL / 2) * (DMODE == 0 ? p.d : 2);  // even; one reflection at most
+        const bool left = pcol < 0, right = pcol >= p.W;
+        const int q = left ? (-2 - pcol) : (right ? (2 * p.W - 2 - pcol) : pcol);
+        colb[k] = (uint32_t)(q - lo) * 4u;
+        if (left || right) rev |= 1u << k;
+    }
+    const uint32_t cb = (uint32_t)(xg - lo) * 4u;
+    const uint32_t smem_base = smem_u32(rows);
+    const float var_factor = (float)bp.var_factor;
+
+    // Per output row: pass 1 (differences + variance sums from the window rows in shared memory, FMA pipe only), then
+    // pass 2 (range weights from the differences kept in registers: 2 MUFU per packed tap).  Warps drift freely (no
+    // block barrier), so the passes of different warps overlap on the FMA and MUFU pipes.  [A variant that interleaves
+    // pass 2 of row n-1 with pass 1 of row n inside each thread (pair_step<.., true, true>) measured 20 % slower.]
+    long long orow = (long long)r + (long long)i0 * p.d;
+    int slot = 0, fslot = 0;  // slot of chain row j, slot of row j - 2C (first row of the window, next to be released)
+    uint32_t parity = 0;
+    u64 D[TAPS][TAPS];
+    u64 xc_old = 0ull, nhi = 0ull;
+    for (int j = 0; j < n_load; ++j) {
+        mbar_wait(&full[slot], parity);
+        if (j >= 2 * C) {
+            uint32_t rowb[TAPS];
+            int ws = fslot;
+#pragma unroll
+            for (int i = 0; i < TAPS; ++i) {
+                rowb[i] = smem_base + (uint32_t)ws * RB;
+                if (++ws == p.slots) ws = 0;
+            }
+            float *c_dst = out_c ? out_c + orow * p.c_pitch + xg : nullptr;
+            float *w_dst = out_w ? out_w + orow * p.w_pitch + xg : nullptr;
+            pair_step<TAPS, DMODE, false, true>(D, xc_old, nhi, rowb, cb, colb, rev, var_factor, c_dst, w_dst, act);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[fslot]);  // the window rows are only read in pass 1
+            if (++fslot == p.slots) fslot = 0;
+            pair_step<TAPS, DMODE, true, false>(D, xc_old, nhi, rowb, cb, colb, rev, var_factor, c_dst, w_dst, act);
+            orow += p.d;
+        }
+        if (++slot == p.slots) { slot = 0; parity ^= 1; }
+    }
+}
+
 template <typename T, int TAPS>
 __global__ void __launch_bounds__(256) bilateral_generic_kernel(const BilateralParams bp) {
     const ScaleParams &p = bp.sp;
@@ -296,10 +544,62 @@ static bool plan_bilateral(ScaleParams &p, int taps, int esize, int batch) {
     return true;
 }
 
+template <int TAPS, int DMODE>
+static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStream_t st) {
+    auto kern = bilateral_pairs_kernel<TAPS, DMODE>;
+    const ScaleParams &p = bp.sp;
+    const size_t smem = (size_t)p.slots * p.row_stride * sizeof(float) + 16 * (size_t)p.slots;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
+    kern<<<grid, 256 + 32, smem, st>>>(bp);
+    return launch_status();
+}
+
+// Geometry for the fp32 pair kernel: 256 consumer threads x 2 pixels = 512-column strips.
+static bool plan_bilateral_pairs(ScaleParams &p, int taps, int batch) {
+    const int c = taps / 2;
+    p.wt = 512;
+    p.n_strips = (p.W + p.wt - 1) / p.wt;
+    p.halo_al = round_up(c * p.d, 4);
+    long long rs = (long long)p.wt + 2LL * p.halo_al;
+    if (rs > p.W) rs = p.W;
+    p.row_stride = (int)rs;
+    int slots = taps + 3;
+    const int min_slots = taps + 1;
+    // two resident blocks per SM (register-limited anyway): keep a block under half of the shared memory if possible
+    while (slots > min_slots && (long long)slots * p.row_stride * 4 + 16LL * slots > kMaxSmem / 2 - 1024) --slots;
+    if ((long long)slots * p.row_stride * 4 + 16LL * slots > kMaxSmem) return false;
+    p.slots = slots;
+    const int n_max = (p.H + p.d - 1) / p.d;
+    // Compute-bound kernel: about 4 waves of 2 resident blocks per SM; halo rows only cost L2 reads.
+    const long long chains = (long long)p.n_strips * (p.d < p.H ? p.d : p.H) * batch;
+    const long long target = 4LL * 2LL * device_sm_count();
+    long long per_chain = (target + chains - 1) / chains;
+    if (per_chain < 1) per_chain = 1;
+    int seg = (int)((n_max + per_chain - 1) / per_chain);
+    if (seg < 8 * c) seg = 8 * c;
+    if (seg > n_max) seg = n_max;
+    p.seg = seg;
+    p.n_seg = (n_max + seg - 1) / seg;
+    return true;
+}
+
 template <typename T, int TAPS>
 static int dispatch_bilateral(BilateralParams &bp, int batch, cudaStream_t st) {
     constexpr int V = VecOf<T>::V;
     ScaleParams &p = bp.sp;
+    if constexpr (sizeof(T) == 4) {
+        // packed fp32x2 pair kernel: dilation 1 or even (every scale of a dyadic cascade)
+        if (fast_path_ok(p, TAPS, 4) && (p.d == 1 || p.d % 2 == 0) && plan_bilateral_pairs(p, TAPS, batch))
+            return p.d == 1 ? launch_bilateral_pairs<TAPS, 1>(bp, batch, st) : launch_bilateral_pairs<TAPS, 0>(bp, batch, st);
+    }
     if (fast_path_ok(p, TAPS, (int)sizeof(T)) && plan_bilateral(p, TAPS, (int)sizeof(T), batch)) {
         const int dmode = (p.d % V == 0) ? 0 : p.d;
         if (dmode == 0) return launch_bilateral<T, TAPS, 0>(bp, batch, 256, st);
