@@ -268,16 +268,18 @@ def wow_default_scales(shape, name: str) -> int:
 
 def wow(data: np.ndarray, name: str = "b3spline", n_scales=None, weights=(), whitening: bool = True,
         denoise_coefficients=(), noise=None, bilateral=None, bilateral_scaling: bool = False,
-        soft_threshold: bool = True, backend: str | None = None):
-    """utils.wow (utils.py:105-219) for an image input with h == 0 and preserve_variance == False.
+        soft_threshold: bool = True, preserve_variance: bool = False, gamma: float = 3.2, gamma_min=None,
+        gamma_max=None, h: float = 0, backend: str | None = None):
+    """utils.wow (utils.py:105-219) for an image input.
 
-    Returns (recon, planes, noise): the synthesis, the whitened planes (what ``coefficients.data`` holds after the
-    call) and the noise value that was used (None if no significance was evaluated)."""
+    Returns (recon, planes, noise): the synthesis (blended with the gamma-scaled image when h > 0, utils.py:207-217),
+    the whitened planes (what ``coefficients.data`` holds after the call) and the noise value that was used (None if
+    no significance was evaluated)."""
     weights = list(weights)
     denoise_coefficients = list(denoise_coefficients)
     max_scales = wow_default_scales(data.shape, name)
     if n_scales is None:
-        n_scales = max_scales
+        n_scales = max_scales if h < 1 else len(denoise_coefficients)  # utils.py:123-124
     elif n_scales > max_scales:
         n_scales = max_scales
     table_len = len(sigma_e(name, bilateral))
@@ -288,6 +290,7 @@ def wow(data: np.ndarray, name: str = "b3spline", n_scales=None, weights=(), whi
 
     planes = atrous_transform(data, n_scales, name, bilateral=sigma_bilateral, bilateral_scaling=bilateral_scaling,
                               backend=backend)
+    gamma_scaled = np.zeros_like(planes[0]) if h > 0 else None  # utils.py:157-158
 
     wts = copy.copy(weights)  # utils.py:160-163
     if len(wts) <= n_scales:
@@ -299,16 +302,21 @@ def wow(data: np.ndarray, name: str = "b3spline", n_scales=None, weights=(), whi
         dns.extend([1, ])
 
     for s, (c, w, d) in enumerate(zip(planes, wts, dns)):  # utils.py:174-203
+        power = c ** 2
+        if preserve_variance:  # utils.py:178-184
+            power_norm = np.std(c) if s == n_scales else np.sqrt(np.mean(power))
+        else:
+            power_norm = 1
         if s == n_scales:
-            if whitening:
+            if whitening and h < 1:
                 local_power = np.std(c)
                 if local_power <= 0:
                     local_power = 1e-15
             else:
                 local_power = 1
         else:
-            if whitening:
-                local_power = smooth(c ** 2, name, s, backend)  # plain smooth even if the transform was bilateral
+            if whitening and h < 1:
+                local_power = smooth(power, name, s, backend)  # plain smooth even if the transform was bilateral
                 local_power[local_power <= 0] = 1e-15
                 np.sqrt(local_power, out=local_power)
             else:
@@ -316,8 +324,21 @@ def wow(data: np.ndarray, name: str = "b3spline", n_scales=None, weights=(), whi
             if d != 0 and noise is None:
                 noise = get_noise(planes, name, sigma_bilateral)
             c *= significance(planes, name, d, s, noise, sigma_bilateral, soft_threshold)
-        c *= w * 1 / local_power
+        if h > 0:
+            gamma_scaled += c
+        c *= w * power_norm / local_power
     recon = np.sum(planes, axis=0)
+    if h > 0:  # utils.py:207-217
+        if gamma_min is None:
+            gamma_min = gamma_scaled.min()
+        if gamma_max is None:
+            gamma_max = gamma_scaled.max()
+        gamma_scaled -= gamma_min
+        gamma_scaled /= gamma_max - gamma_min
+        gamma_scaled[gamma_scaled < 0] = 0
+        gamma_scaled[gamma_scaled > 1] = 1
+        gamma_scaled **= 1 / gamma
+        recon = (1 - h) * recon + h * gamma_scaled
     return recon, planes, noise
 
 

@@ -125,6 +125,23 @@ def main():
                 out[f"{tag}_{key}_noise"] = np.float64(np.nan if co.noise is None else co.noise)
         save(f"wow_{dt}", **out)
 
+    # ---- wow options of SURVEY 8(f) rank 1: gamma blend (h > 0) and preserve_variance, utils.py:157-158,178-184,207-217
+    for dt in ("float32", "float64"):
+        out = {}
+        for tag, img in (("gauss", gaussian((64, 64), 23, dt) * 5 + 50),
+                         ("solar", solar_like(64, seed=6, flux=0.01, dtype=dt))):
+            out[f"{tag}_in"] = img
+            for key, kw in (("gamma", dict(h=0.4, denoise_coefficients=[5, 2], gamma=2.5)),
+                            ("gamma_one", dict(h=1, denoise_coefficients=[3, 2, 1])),
+                            ("gamma_range", dict(h=0.3, gamma_min=10.0, gamma_max=60.0, n_scales=3)),
+                            ("pv", dict(preserve_variance=True)),
+                            ("pv_den_gamma", dict(preserve_variance=True, h=0.25, denoise_coefficients=[4, 2],
+                                                  weights=[1.5, 0.5]))):
+                recon, co = wow(img.copy(), **kw)
+                out[f"{tag}_{key}_recon"] = recon
+                out[f"{tag}_{key}_planes"] = co.data
+        save(f"wow_options_{dt}", **out)
+
     # ---- compute_noise_weights: wavelets.py:221-229 -------------------------------------------------------------
     for sf in SF:
         np.random.seed(5)

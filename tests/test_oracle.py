@@ -183,6 +183,32 @@ def test_wow_golden(dt, backend):
                     assert orc.emax(planes[p], rp[p]) <= tol * 10, (tag, key, p, orc.emax(planes[p], rp[p]))
 
 
+WOW_OPTION_CASES = {
+    "gamma": dict(h=0.4, denoise_coefficients=[5, 2], gamma=2.5),
+    "gamma_one": dict(h=1, denoise_coefficients=[3, 2, 1]),
+    "gamma_range": dict(h=0.3, gamma_min=10.0, gamma_max=60.0, n_scales=3),
+    "pv": dict(preserve_variance=True),
+    "pv_den_gamma": dict(preserve_variance=True, h=0.25, denoise_coefficients=[4, 2], weights=[1.5, 0.5]),
+}
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+def test_wow_options_golden(dt, backend):
+    """gamma blend (h > 0) and preserve_variance (utils.py:157-158, :178-184, :207-217) against the real reference."""
+    g = load_golden(f"wow_options_{dt}")
+    for tag in ("gauss", "solar"):
+        img = g[f"{tag}_in"]
+        for key, kw in WOW_OPTION_CASES.items():
+            recon, planes, _ = orc.wow(img.copy(), backend=backend, **kw)
+            ref, rp = g[f"{tag}_{key}_recon"], g[f"{tag}_{key}_planes"]
+            assert recon.dtype == ref.dtype and recon.shape == ref.shape and planes.shape == rp.shape
+            tol = 1e-11 if dt == "float64" else 2e-5
+            assert orc.emax(recon, ref) <= tol, (tag, key, orc.emax(recon, ref))
+            for p in range(len(rp)):
+                assert orc.emax(planes[p], rp[p]) <= tol * 10, (tag, key, p, orc.emax(planes[p], rp[p]))
+
+
 def test_wow_scale_count_logic():
     assert orc.wow_default_scales((4096, 4096), "b3spline") == 10  # utils.py:122 at BASELINE's size
     assert orc.wow_default_scales((4096, 4096), "triangle") == 10

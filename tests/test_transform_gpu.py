@@ -179,3 +179,23 @@ def test_full_size_properties(dt):
         floor = 4 * np.finfo(dt).eps * np.abs(host).max()
         assert np.abs(got - w[ys]).max() <= max(tol * np.abs(w).max(), floor), (s, np.abs(got - w[ys]).max())
         c = nxt
+
+
+def test_stream_of_host_frames_matches_per_frame_calls():
+    """AtrousTransform.stream (H2D / transform / D2H overlapped on three streams) == the plain call per frame."""
+    import wavelets_b200 as wb
+    rng = np.random.default_rng(11)
+    frames = rng.standard_normal((5, 96, 160)).astype(np.float32)
+    tr = wb.AtrousTransform(wb.B3spline)
+    out = tr.stream(frames, 4)
+    assert isinstance(out, np.ndarray) and out.shape == (5, 5, 96, 160) and out.dtype == np.float32
+    for i in range(5):
+        assert np.array_equal(out[i], tr(frames[i], 4).data.cpu().numpy())
+    pinned = torch.from_numpy(frames.astype(np.float64)).pin_memory()
+    res = torch.empty((5, 3, 96, 160), dtype=torch.float64).pin_memory()
+    got = wb.AtrousTransform(wb.Triangle).stream(pinned, 2, out=res, depth=3)
+    assert got is res
+    for i in range(5):
+        assert torch.equal(res[i], wb.AtrousTransform(wb.Triangle)(pinned[i], 2).data.cpu())
+    with pytest.raises(NotImplementedError):
+        wb.AtrousTransform(wb.B3spline, bilateral=1).stream(frames, 2)

@@ -200,8 +200,6 @@ def test_wow_api_behaviour():
     assert wowed.shape == (128, 128) and len(co) == wb.utils._wow_plan((128, 128), wb.B3spline, None, [], [], True)[0] + 1
     with pytest.raises(ValueError, match="Unknown input type"):
         wb.wow([[1.0, 2.0]])
-    with pytest.raises(NotImplementedError):
-        wb.wow(ones, h=0.5)
     img = orc.solar_like(256, seed=5, flux=0.05, dtype=np.float32)
     # torch in -> torch out, coefficients whitened in place when passed back in
     t = torch.from_numpy(img).cuda()
@@ -353,3 +351,41 @@ def test_wow_fused_scale_equals_two_pass(dt, sf):
             assert (rel > 1e-5).float().mean().item() < 1e-3, kw
         interior = slice(64, 512 - 64)  # scales 0-4 of the 512^2 frame: no virtual rows involved
         assert torch.equal(c1.data[:5, interior], c2.data[:5, interior]), kw
+
+
+WOW_OPTION_CASES = {
+    "gamma": dict(h=0.4, denoise_coefficients=[5, 2], gamma=2.5),
+    "gamma_one": dict(h=1, denoise_coefficients=[3, 2, 1]),
+    "gamma_range": dict(h=0.3, gamma_min=10.0, gamma_max=60.0, n_scales=3),
+    "pv": dict(preserve_variance=True),
+    "pv_den_gamma": dict(preserve_variance=True, h=0.25, denoise_coefficients=[4, 2], weights=[1.5, 0.5]),
+}
+
+
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+def test_wow_options_golden(dt):
+    """wow(h > 0) gamma blend and preserve_variance against the real reference's outputs and the
+    float64 oracle (dual-oracle tolerance)."""
+    import wavelets_b200 as wb
+    g = load_golden(f"wow_options_{dt}")
+    for tag in ("gauss", "solar"):
+        img = g[f"{tag}_in"]
+        img64 = img.astype(np.float64)
+        for key, kw in WOW_OPTION_CASES.items():
+            recon, co = wb.wow(img, **kw)
+            ref, rp = g[f"{tag}_{key}_recon"], g[f"{tag}_{key}_planes"]
+            assert isinstance(recon, np.ndarray) and recon.dtype == ref.dtype and recon.shape == ref.shape
+            got = co.data.cpu().numpy()
+            assert got.shape == rp.shape and got.dtype == rp.dtype
+            ref64, planes64, _ = orc.wow(img64, backend="numpy", **kw)
+            tol = dual_tol(ref, ref64, dt, fp64_tol=1e-11)
+            assert orc.emax(recon, ref64) <= tol, (tag, key, orc.emax(recon, ref64), tol)
+            for p in range(len(rp)):
+                tp = dual_tol(rp[p], planes64[p], dt, fp64_tol=1e-10, base=2e-5)
+                assert orc.emax(got[p], planes64[p]) <= tp, (tag, key, p, orc.emax(got[p], planes64[p]), tp)
+    # Coefficients in -> whitened in place, same result as the image call
+    img = g["solar_in"]
+    r1, _ = wb.wow(img, h=0.4, denoise_coefficients=[5, 2], gamma=2.5)
+    co = wb.AtrousTransform(wb.B3spline)(img, wb.utils._wow_plan(img.shape, wb.B3spline, None, [], [5, 2], None)[0])
+    r2, co2 = wb.wow(co, h=0.4, denoise_coefficients=[5, 2], gamma=2.5)
+    assert co2 is co and orc.emax(r2.cpu().numpy(), r1) < (1e-6 if dt == "float32" else 1e-13)

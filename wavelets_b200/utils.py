@@ -53,13 +53,14 @@ def denoise(data, weights, scaling_function=B3spline, noise=None, bilateral=None
     return _result(out, was_numpy)
 
 
-def _wow_plan(shape, scaling_function, n_scales, weights, denoise_coefficients, bilateral, from_coefficients=None):
+def _wow_plan(shape, scaling_function, n_scales, weights, denoise_coefficients, bilateral, from_coefficients=None,
+              h=0):
     """Scale-count and per-scale parameter lists of wow() (watroo/utils.py:121-146, :160-170)."""
     n_taps = len(scaling_function.coefficients_1d)
     if from_coefficients is None:
         max_scales = int(np.round(np.log2(min(shape)) - np.log2(n_taps)))
         if n_scales is None:
-            n_scales = max_scales
+            n_scales = max_scales if h < 1 else len(denoise_coefficients)  # utils.py:123-124
         elif n_scales > max_scales:
             n_scales = max_scales
     else:
@@ -200,17 +201,27 @@ def wow(data, scaling_function=B3spline, n_scales=None, weights=[], whitening=Tr
     """Wavelets Optimized Whitening (watroo/utils.py:105-219): ``(recon, coefficients)``.
 
     ``data`` is a 2-D image (ndarray or torch tensor) or a ``Coefficients`` object (which is then whitened in
-    place, as in the reference).  ``h > 0`` (gamma blending) and ``preserve_variance`` are not on the accelerated
-    path yet and raise NotImplementedError."""
-    if h != 0 or preserve_variance:
-        raise NotImplementedError("wow(h > 0) and wow(preserve_variance=True) are not implemented on the device path")
+    place, as in the reference).  The default call and the ``bilateral`` / ``denoise_coefficients`` / ``weights`` /
+    ``whitening`` options run on the fused kernels; ``h > 0`` (gamma blending, utils.py:157-158, :207-217) and
+    ``preserve_variance`` (utils.py:178-184) take a plane-by-plane route over the same kernels."""
+    general = h != 0 or preserve_variance
     if isinstance(data, Coefficients):
+        if general:
+            return _wow_general(data, weights, whitening, denoise_coefficients, bilateral, soft_threshold,
+                                preserve_variance, gamma, gamma_min, gamma_max, h)
         return _wow_coefficients(data, weights, whitening, denoise_coefficients, bilateral, soft_threshold)
     if not isinstance(data, (np.ndarray, torch.Tensor)):
         raise ValueError("Unknown input type")  # watroo/utils.py:133
     img, was_numpy = to_device_image(data)
     n_scales, sigma_bilateral, wts, dns = _wow_plan(img.shape, scaling_function, n_scales, weights,
-                                                    denoise_coefficients, bilateral)
+                                                    denoise_coefficients, bilateral, h=h)
+    if general:
+        transform = AtrousTransform(scaling_function, bilateral=sigma_bilateral, bilateral_scaling=bilateral_scaling)
+        co = transform(img, n_scales)
+        co.noise = noise
+        recon, co = _wow_general(co, weights, whitening, denoise_coefficients, bilateral, soft_threshold,
+                                 preserve_variance, gamma, gamma_min, gamma_max, h, plan=(n_scales, wts, dns))
+        return _result(recon, was_numpy), co
     nz = _scalar_noise(noise, img.device)
     if nz == "map":
         # per-pixel noise maps take the unfused route: transform, then whiten plane by plane
@@ -287,3 +298,72 @@ def _wow_coefficients(co, weights, whitening, denoise_coefficients, bilateral, s
     elif wts[L] != 1:
         last.mul_(wts[L])
     return synthesis(data), co
+
+
+def _wow_general(co, weights, whitening, denoise_coefficients, bilateral, soft_threshold, preserve_variance, gamma,
+                 gamma_min, gamma_max, h, plan=None):
+    """wow() with the gamma blend (h > 0) and / or preserve_variance (watroo/utils.py:157-158, :174-217), plane by
+    plane on raw coefficients: the same kernels as the fused route (K3 whitening, significance, moments, synthesis)
+    plus a few device-scalar multiplications; nothing synchronises with the host."""
+    lib = _lib.load(require_cuda=True)
+    sf = co.scaling_function
+    if plan is None:
+        n_scales, _, wts, dns = _wow_plan(co.data.shape[1:], sf.__class__, None, weights, denoise_coefficients,
+                                          bilateral, from_coefficients=co, h=h)
+        n_scales = len(co) - 1
+    else:
+        n_scales, wts, dns = plan
+    data = co.data
+    dt = data.dtype
+    L = n_scales
+    white = whitening and h < 1  # utils.py:186, :193
+    gamma_scaled = torch.zeros_like(data[0]) if h > 0 else None
+    tmp = torch.empty_like(data[0]) if white else None
+    for s in range(L):
+        d, wt = dns[s], wts[s]
+        plane = data[s]
+        power_norm = None
+        if preserve_variance:
+            mom = plane_moments(plane)[0]                       # [mean, var, std] of the raw plane, float64
+            power_norm = torch.sqrt(mom[1] + mom[0] * mom[0]).to(dt)  # sqrt(mean(c**2)), utils.py:182
+        nz = co._noise_arg(d) if d != 0 else _Noise()           # lazily, from the current plane 0 (wavelets.py:131)
+        if nz.map is not None:
+            sig = co.significance(d, s, soft_threshold=soft_threshold).to(torch.float64)
+            if white:
+                _whiten_scale(lib, plane, tmp, s, sf, 0, 0.0, 1.0, _Noise(), wt)
+                tmp.copy_((tmp.to(torch.float64) * sig).to(dt))
+            plane.copy_((plane.to(torch.float64) * sig).to(dt))
+        else:
+            mode = (1 if soft_threshold else 2) if d != 0 else 0
+            if white:
+                _whiten_scale(lib, plane, tmp, s, sf, mode, d, co.sigma_e[s] if d != 0 else 1.0, nz, wt)
+            co._denoise_plane(lib, s, d, 1, soft_threshold)     # plane <- raw * significance
+        if gamma_scaled is not None:
+            gamma_scaled += plane                               # utils.py:200-201: after significance, before weighting
+        if white:
+            plane.copy_(tmp if power_norm is None else tmp * power_norm)
+        else:
+            factor = wt if power_norm is None else power_norm * wt
+            if power_norm is not None or wt != 1:
+                plane.mul_(factor)
+    last = data[L]
+    mom = plane_moments(last)[0] if (preserve_variance or white) else None
+    if gamma_scaled is not None:
+        gamma_scaled += last
+    factor = torch.ones((), dtype=torch.float64, device=last.device) * wts[L]
+    if preserve_variance:
+        factor = factor * mom[2].to(dt).to(torch.float64)       # power_norm = np.std(c), utils.py:180
+    if white:
+        std = mom[2].to(dt).to(torch.float64)
+        factor = factor / torch.where(std <= 0, torch.full_like(std, 1e-15), std)  # utils.py:187-189
+    last.mul_(factor.to(dt))
+    recon = synthesis(data)
+    if gamma_scaled is not None:  # utils.py:207-217
+        lo = gamma_scaled.min() if gamma_min is None else gamma_min
+        hi = gamma_scaled.max() if gamma_max is None else gamma_max
+        gamma_scaled -= lo
+        gamma_scaled /= (hi - lo)
+        gamma_scaled.clamp_(0, 1)
+        gamma_scaled.pow_(1 / gamma)
+        recon = (1 - h) * recon + h * gamma_scaled
+    return recon, co

@@ -355,6 +355,80 @@ class AtrousTransform:
         stack, _ = to_device_image(frames, ndim_ok=(3,))
         return self._run(stack, int(level), self.scaling_function_class(2))
 
+    def stream(self, frames, level, out=None, depth=2):
+        """NEW entry point (no reference equivalent): transform a sequence of HOST frames ``(N, H, W)`` into a host
+        array ``(N, level + 1, H, W)``, overlapping the host->device copy of frame n+1, the transform of frame n and
+        the device->host copy of the planes of frame n-1 on three CUDA streams (``depth`` device buffers in flight).
+
+        The per-frame cost of the plain call is dominated by PCIe (H*W in, (level+1)*H*W out); pipelining hides the
+        upload and the kernels behind the download.  ``frames`` / ``out``: torch CPU tensors (pinned memory is used as
+        is, pageable memory is staged through a pinned copy) or NumPy arrays; returns ``out`` (allocated pinned when
+        None; a NumPy view of it for NumPy input).  Plain (non-bilateral) transforms only."""
+        if self.bilateral is not None:
+            raise NotImplementedError("stream() covers the plain cascade")
+        was_numpy = not isinstance(frames, torch.Tensor)
+        host = torch.from_numpy(np.ascontiguousarray(frames)) if was_numpy else frames
+        if host.ndim != 3:
+            raise ValueError("stream() takes a stack of frames (N, H, W)")
+        if host.dtype not in (torch.float32, torch.float64):
+            host = host.to(torch.float64)  # the reference's recast rule for integer inputs
+        if host.is_cuda:
+            raise ValueError("stream() takes host frames; use batch() for device-resident stacks")
+        if not host.is_pinned():
+            host = host.contiguous().pin_memory()
+        level = int(level)
+        n, h, w = host.shape
+        if out is None:
+            out = torch.empty((n, level + 1, h, w), dtype=host.dtype).pin_memory()
+        out_t = torch.from_numpy(out) if isinstance(out, np.ndarray) else out
+        if tuple(out_t.shape) != (n, level + 1, h, w) or out_t.dtype != host.dtype:
+            raise ValueError("out must be (N, level + 1, H, W) of the frame dtype")
+        staged = None
+        if not out_t.is_pinned():
+            staged = torch.empty(out_t.shape, dtype=out_t.dtype).pin_memory()
+        dst = out_t if staged is None else staged
+        lib = _lib.load(require_cuda=True)
+        dev = _device()
+        sf = self.scaling_function_class(2)
+        code = _lib.dtype_code(host.dtype)
+        depth = max(1, min(int(depth), n))
+        s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        caller = torch.cuda.current_stream(dev)
+        for st in (s_in, s_cmp, s_out):
+            st.wait_stream(caller)
+        d_in = [torch.empty((h, w), dtype=host.dtype, device=dev) for _ in range(depth)]
+        d_pl = [torch.empty((level + 1, h, w), dtype=host.dtype, device=dev) for _ in range(depth)]
+        scratch = torch.empty((2, h, w), dtype=host.dtype, device=dev) if level > 1 else None
+        ev_in = [torch.cuda.Event() for _ in range(depth)]
+        ev_cmp = [torch.cuda.Event() for _ in range(depth)]
+        ev_out = [torch.cuda.Event() for _ in range(depth)]
+        with torch.cuda.device(dev):
+            for i in range(n):
+                b = i % depth
+                with torch.cuda.stream(s_in):
+                    if i >= depth:
+                        s_in.wait_event(ev_cmp[b])       # the transform that read d_in[b] is done
+                    d_in[b].copy_(host[i], non_blocking=True)
+                    ev_in[b].record(s_in)
+                with torch.cuda.stream(s_cmp):
+                    s_cmp.wait_event(ev_in[b])
+                    if i >= depth:
+                        s_cmp.wait_event(ev_out[b])      # the download of d_pl[b] is done
+                    _lib.check(lib.wb_atrous_transform(
+                        d_in[b].data_ptr(), d_pl[b].data_ptr(), 0 if scratch is None else scratch.data_ptr(), 1, h, w,
+                        w, 0, level, sf.taps_code, code, s_cmp.cuda_stream))
+                    ev_cmp[b].record(s_cmp)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_cmp[b])
+                    dst[i].copy_(d_pl[b], non_blocking=True)
+                    ev_out[b].record(s_out)
+        for st in (s_in, s_cmp, s_out):
+            caller.wait_stream(st)
+        s_out.synchronize()  # the result lives in host memory: hand it back complete
+        if staged is not None:
+            out_t.copy_(staged)
+        return out if (isinstance(out, np.ndarray) or not was_numpy) else out_t.numpy()
+
     # -- internals ----------------------------------------------------------------------------------------------
     def var_factors(self, level):
         """sigma_b[s]**2 * (s + 1 if bilateral_scaling) for s < level (watroo/wavelets.py:421-424, :434-436)."""
