@@ -72,14 +72,17 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
         // ---------------- producer warp: one lane streams the chain rows into the ring ----------------
         if (lane == 0) {
             const T *src = reinterpret_cast<const T *>(p.in) + (long long)frame * p.in_bstride + lo;
+            const uint64_t pol_in = policy_evict_first();  // c_s is dead once this launch has read it
             int slot = 0;
             uint32_t round = 0;
             for (int j = 0; j < n_load; ++j) {
                 if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
                 const long long y = reflect_any(p.gwy0 + r + (long long)(i0 - C + j) * p.d, p.Hg) - p.gwy0 + p.row_off_in;
                 mbar_arrive_expect_tx(&full[slot], row_bytes);
-                tma_load_1d(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes,
-                            &full[slot]);
+                if (p.l2_hints)
+                    tma_load_1d_hint(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[slot], pol_in);
+                else
+                    tma_load_1d(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[slot]);
                 if (++slot == p.slots) { slot = 0; ++round; }
             }
         }
@@ -87,81 +90,93 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
     }
 
     // ---------------- consumer warps ----------------
-    T *out_c = reinterpret_cast<T *>(p.out_c);
-    T *out_w = reinterpret_cast<T *>(p.out_w);
-    if (out_c) out_c += (long long)frame * p.c_bstride;
-    if (out_w) out_w += (long long)frame * p.w_bstride;
+    T *c_ptr = reinterpret_cast<T *>(p.out_c);
+    T *w_ptr = reinterpret_cast<T *>(p.out_w);
+    // first output row of this block; the pointers advance by one chain step (d rows) per output row
+    const long long orow = (long long)r + (long long)i0 * p.d;
+    if (c_ptr) c_ptr += (long long)frame * p.c_bstride + (orow + p.row_off_c) * p.c_pitch;
+    if (w_ptr) w_ptr += (long long)frame * p.w_bstride + (orow + p.row_off_w) * p.w_pitch;
+    const long long c_step = (long long)p.d * p.c_pitch, w_step = (long long)p.d * p.w_pitch;
 
     WhitenEpilogue<T> epi;
     if constexpr (OP == OP_WHITEN) epi.init(p, frame);
+    const uint64_t pol_keep = policy_evict_last();  // c_{s+1}: the next scale reads it back
+    const bool hints = p.l2_hints != 0;
 
     int xg[NG];
+    uint32_t xb[NG];  // byte offset of this thread's own vector inside a staged row
     bool act[NG];
-    TapPlan<NV> plan[NG];
+    BytePlan<NV> plan[NG];
 #pragma unroll
     for (int q = 0; q < NG; ++q) {
         xg[q] = x0 + (q * nt + tid) * V;
-        act[q] = xg[q] < p.W;
-        plan[q] = make_tap_plan<V, NV>(act[q] ? xg[q] : x0, DMODE == 0 ? p.d : V, p.W, lo);
+        act[q] = xg[q] < p.W && xg[q] < x0 + p.wt;
+        if (!act[q]) xg[q] = x0;  // idle threads shadow the first vector of the strip; only their stores are masked
+        xb[q] = (uint32_t)(xg[q] - lo) * (uint32_t)sizeof(T);
+        const TapPlan<NV> tp = make_tap_plan<V, NV>(xg[q], DMODE == 0 ? p.d : V, p.W, lo);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) plan[q].off[k] = (uint32_t)tp.off[k] * (uint32_t)sizeof(T);
+        plan[q].rev = tp.rev;
     }
 
-    Pack<T, V> ring[TAPS][NG];
+    // running column sums (col_feed): TAPS-1 live values per element, no register-ring rotation
+    T S[NG][V][TAPS - 1];
 #pragma unroll
-    for (int k = 0; k < TAPS; ++k)
+    for (int q = 0; q < NG; ++q)
 #pragma unroll
-        for (int q = 0; q < NG; ++q)
+        for (int e = 0; e < V; ++e)
 #pragma unroll
-            for (int e = 0; e < V; ++e) ring[k][q].v[e] = T(0);
+            for (int t = 0; t < TAPS - 1; ++t) S[q][e][t] = T(0);
 
-    // first output row of this block and the per-row pointer increments
-    long long orow = (long long)r + (long long)i0 * p.d;
-    int slot = 0, cslot = 0;  // ring slot of row j and of the centre row j - C (the next one to be released)
+    const uint32_t RB = (uint32_t)p.row_stride * (uint32_t)sizeof(T);
+    const uint32_t ring_base = smem_u32(rows), ring_end = ring_base + (uint32_t)p.slots * RB;
+    uint32_t row_addr = ring_base, crow_addr = ring_base;  // staged row j and centre row j - C
+    int slot = 0, cslot = 0;
     uint32_t parity = 0;
     for (int j = 0; j < n_load; ++j) {
         mbar_wait(&full[slot], parity);
-        const T *srow = rows + (size_t)slot * p.row_stride;
-
+        Pack<T, V> cv[NG];
 #pragma unroll
-        for (int k = 0; k + 1 < TAPS; ++k)
+        for (int q = 0; q < NG; ++q) {
+            const Pack<T, V> v = row_pass_b<T, TAPS, DMODE, OP == OP_WHITEN>(row_addr, plan[q]);
 #pragma unroll
-            for (int q = 0; q < NG; ++q) ring[k][q] = ring[k + 1][q];
-#pragma unroll
-        for (int q = 0; q < NG; ++q)
-            if (act[q]) ring[TAPS - 1][q] = row_pass<T, TAPS, DMODE, OP == OP_WHITEN>(srow, plan[q]);
-
+            for (int e = 0; e < V; ++e) cv[q].v[e] = col_feed<T, TAPS>(S[q][e], v.v[e]);
+        }
         if (j >= 2 * C) {
-            const T *crow = rows + (size_t)cslot * p.row_stride - lo;
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
-                if (!act[q]) continue;
-                Pack<T, V> c;
-#pragma unroll
-                for (int e = 0; e < V; ++e) c.v[e] = col_pass<T, TAPS, NG>(ring, q, e);
                 if constexpr (OP == OP_TRANSFORM) {
-                    if (out_c) st_vec(out_c + (orow + p.row_off_c) * p.c_pitch + xg[q], c);
-                    if (out_w) {
-                        Pack<T, V> raw = ld_vec(crow + xg[q]);
+                    if (c_ptr && act[q]) {
+                        if (hints) st_vec_hint(c_ptr + xg[q], cv[q], pol_keep);
+                        else st_vec(c_ptr + xg[q], cv[q]);
+                    }
+                    if (w_ptr) {
+                        Pack<T, V> raw = lds_vec<T>(crow_addr + xb[q]);
 #pragma unroll
-                        for (int e = 0; e < V; ++e) raw.v[e] -= c.v[e];
-                        st_vec_cs(out_w + (orow + p.row_off_w) * p.w_pitch + xg[q], raw);
+                        for (int e = 0; e < V; ++e) raw.v[e] -= cv[q].v[e];
+                        if (act[q]) st_vec_cs(w_ptr + xg[q], raw);
                     }
                 } else {
-                    Pack<T, V> raw = ld_vec(crow + xg[q]);
+                    Pack<T, V> raw = lds_vec<T>(crow_addr + xb[q]);
 #pragma unroll
-                    for (int e = 0; e < V; ++e) raw.v[e] = epi.apply(raw.v[e], c.v[e]);
-                    st_vec_cs(out_w + (orow + p.row_off_w) * p.w_pitch + xg[q], raw);
+                    for (int e = 0; e < V; ++e) raw.v[e] = epi.apply(raw.v[e], cv[q].v[e]);
+                    if (act[q]) st_vec_cs(w_ptr + xg[q], raw);
                 }
             }
-            orow += p.d;
+            if (c_ptr) c_ptr += c_step;
+            if (w_ptr) w_ptr += w_step;
         }
         if (j >= C) {
             // the raw row j-C is not needed any more: hand its slot back to the producer
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[cslot]);
-            if (++cslot == p.slots) cslot = 0;
+            crow_addr += RB;
+            if (++cslot == p.slots) { cslot = 0; crow_addr = ring_base; }
         }
-        if (++slot == p.slots) { slot = 0; parity ^= 1; }
+        row_addr += RB;
+        if (++slot == p.slots) { slot = 0; row_addr = ring_base; parity ^= 1; }
     }
+    (void)ring_end;
 }
 
 // Generic path: one thread per output pixel, full modular reflection, any shape / alignment.
@@ -274,6 +289,7 @@ static int scale_impl(const void *in, void *out_c, void *out_w, int batch, int H
     p.in_pitch = in_pitch; p.in_bstride = in_bstride;
     p.c_pitch = c_pitch; p.c_bstride = c_bstride;
     p.w_pitch = w_pitch; p.w_bstride = w_bstride;
+    p.l2_hints = l2_hints_enabled();
     return dispatch_typed<OP_TRANSFORM>(p, batch, scale, taps, dtype, st);
 }
 

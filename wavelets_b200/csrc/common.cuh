@@ -108,6 +108,38 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                  : "memory");
 }
 
+// L2 eviction-priority policies (createpolicy) for the per-access cache hints below.  The running smooth plane c_{s+1}
+// written by one scale is the ONLY data the next launch re-reads: it is stored evict-last while everything that is
+// dead after this launch (the c_s rows being read, the detail plane w_s) goes evict-first, so that the 64 MiB plane
+// survives in the 126 MB L2 until the next scale consumes it.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void st_vec_hint(float *p, const Pack<float, 4> &r, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
+                 "f"(r.v[2]), "f"(r.v[3]), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void st_vec_hint(double *p, const Pack<double, 2> &r, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(r.v[0]), "d"(r.v[1]), "l"(policy)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------------------
@@ -121,6 +153,16 @@ inline int check_common(int batch, int H, int W, int taps, int dtype) {
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// WB_L2_HINTS=0 in the environment disables the L2 eviction-priority hints (A/B measurements).
+inline int l2_hints_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("WB_L2_HINTS");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
 
 // Launch-time error check that does not synchronise.
 inline int launch_status() {

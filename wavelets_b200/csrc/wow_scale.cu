@@ -30,105 +30,6 @@ static constexpr int kInRing = 8;  // input rows staged by TMA (C+1 live, the re
 static constexpr int kWRing = 4;   // raw w_s rows (read back by the writing thread C+1 steps later)
 static constexpr int kW2Ring = 2;  // w_s^2 rows (cross-thread, guarded by the split-phase barriers)
 
-// 16-byte shared-memory accesses on 32-bit shared-window addresses (address = per-thread offset + block-uniform base,
-// which ptxas folds into the [R + UR] addressing mode: no per-load address arithmetic).
-__device__ __forceinline__ Pack<float, 4> lds_vec_f(uint32_t a) {
-    Pack<float, 4> r;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(a));
-    return r;
-}
-__device__ __forceinline__ Pack<double, 2> lds_vec_d(uint32_t a) {
-    Pack<double, 2> r;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(a));
-    return r;
-}
-template <typename T> __device__ __forceinline__ Pack<T, VecOf<T>::V> lds_vec(uint32_t a);
-template <> __device__ __forceinline__ Pack<float, 4> lds_vec<float>(uint32_t a) { return lds_vec_f(a); }
-template <> __device__ __forceinline__ Pack<double, 2> lds_vec<double>(uint32_t a) { return lds_vec_d(a); }
-__device__ __forceinline__ void sts_vec(uint32_t a, const Pack<float, 4> &r) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3])
-                 : "memory");
-}
-__device__ __forceinline__ void sts_vec(uint32_t a, const Pack<double, 2> &r) {
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(r.v[0]), "d"(r.v[1]) : "memory");
-}
-// non-blocking probe of an mbarrier phase
-__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-
-// Per-thread tap plan in BYTES for one column vector (see TapPlan in pipeline.cuh).
-template <int NV> struct BytePlan {
-    uint32_t off[NV];
-    unsigned rev;
-};
-
-// Row pass of one vector from the staged row at shared address `base` (block-uniform).  SQUARE filters the squares.
-template <typename T, int TAPS, int DMODE, bool SQUARE, bool MIRROR>
-__device__ __forceinline__ Pack<T, VecOf<T>::V> row_pass_b_impl(uint32_t base, const BytePlan<PlanSize<TAPS, DMODE>::NV> &tp) {
-    constexpr int V = VecOf<T>::V;
-    constexpr int C = TAPS / 2;
-    Pack<T, V> acc;
-    if constexpr (DMODE == 0) {
-#pragma unroll
-        for (int k = 0; k < TAPS; ++k) {
-            Pack<T, V> t = lds_vec<T>(base + tp.off[k]);
-            if (MIRROR && ((tp.rev >> k) & 1u)) reverse_vec<T, V>(t);
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-                const T v = SQUARE ? t.v[e] * t.v[e] : t.v[e];
-                acc.v[e] = (k == 0) ? Taps<T, TAPS>::h(0) * v : fma_t<T>(Taps<T, TAPS>::h(k), v, acc.v[e]);
-            }
-        }
-    } else {
-        T win[3 * V];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            Pack<T, V> t = lds_vec<T>(base + tp.off[k]);
-            if (MIRROR && ((tp.rev >> k) & 1u)) reverse_vec<T, V>(t);
-#pragma unroll
-            for (int e = 0; e < V; ++e) win[k * V + e] = SQUARE ? t.v[e] * t.v[e] : t.v[e];
-        }
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-#pragma unroll
-            for (int k = 0; k < TAPS; ++k) {
-                const T v = win[V + e + (k - C) * DMODE];
-                acc.v[e] = (k == 0) ? Taps<T, TAPS>::h(0) * v : fma_t<T>(Taps<T, TAPS>::h(k), v, acc.v[e]);
-            }
-        }
-    }
-    return acc;
-}
-template <typename T, int TAPS, int DMODE, bool SQUARE>
-__device__ __forceinline__ Pack<T, VecOf<T>::V> row_pass_b(uint32_t base, const BytePlan<PlanSize<TAPS, DMODE>::NV> &tp) {
-    if (tp.rev == 0) return row_pass_b_impl<T, TAPS, DMODE, SQUARE, false>(base, tp);
-    return row_pass_b_impl<T, TAPS, DMODE, SQUARE, true>(base, tp);
-}
-
-// Column pass as running partial sums: S[t] is the partial sum of the output row that completes t+1 rows from now.
-// Feeding the row-filtered vector v of the newest row returns the completed output (centre = C rows ago):
-//     out = S[0] + h_{T-1} v;  S[t] = S[t+1] + h_{T-2-t} v;  S[T-2] = h_0 v
-// i.e. ((((h_0 r_0) + h_1 r_1) + h_2 r_2) + ...) oldest row first -- the same order as K1's col_pass -- with every FMA
-// writing the register the next step reads: no ring rotation, no moves, TAPS-1 live values per element.
-template <typename T, int TAPS>
-__device__ __forceinline__ T col_feed(T (&S)[TAPS - 1], T v) {
-    const T out = fma_t<T>(Taps<T, TAPS>::h(TAPS - 1), v, S[0]);
-#pragma unroll
-    for (int t = 0; t + 2 < TAPS; ++t) S[t] = fma_t<T>(Taps<T, TAPS>::h(TAPS - 2 - t), v, S[t + 1]);
-    S[TAPS - 2] = Taps<T, TAPS>::h(0) * v;
-    return out;
-}
-
 template <typename T, int TAPS, int DMODE, int NG>
 __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
     constexpr int V = VecOf<T>::V;
