@@ -362,6 +362,7 @@ int wb_wow_whiten_scale(const void *w_raw, void *out, int batch, int H, int W, l
     p.w_pitch = out_pitch; p.w_bstride = out_bstride;
     p.sig_mode = sig_mode; p.sigma = sigma; p.sigma_e = sigma_e;
     p.noise_host = noise_host; p.noise_dev = noise_dev; p.weight = weight;
+    p.l2_hints = wb::l2_hints_enabled();
     return wb::dispatch_typed<wb::OP_WHITEN>(p, batch, scale, taps, dtype, (cudaStream_t)stream);
 }
 

@@ -278,7 +278,7 @@ __device__ __forceinline__ void pair_taps(uint32_t rowb, const uint32_t (&colb)[
 template <int TAPS, int DMODE, bool OLD, bool NEW>
 __device__ __forceinline__ void pair_step(u64 (&D)[TAPS][TAPS], u64 &xc_old, u64 &nhi, const uint32_t (&rowb)[TAPS],
                                           uint32_t cb, const uint32_t (&colb)[PairPlan<TAPS, DMODE>::NL], unsigned rev,
-                                          float var_factor, float *c_dst, float *w_dst, bool act) {
+                                          float var_factor, float *c_dst, float *w_dst, bool act, uint64_t pol_keep) {
     constexpr int C = TAPS / 2;
     const float kc = Taps<float, TAPS>::h(C) * Taps<float, TAPS>::h(C);
     u64 xc = 0ull;
@@ -320,7 +320,12 @@ __device__ __forceinline__ void pair_step(u64 (&D)[TAPS][TAPS], u64 &xc_old, u64
         up2(xc_old, x0v, x1v);
         const float c0 = x0v - n0 * rcp_fast(d0), c1 = x1v - n1 * rcp_fast(d1);
         if (act) {
-            if (c_dst) *reinterpret_cast<float2 *>(c_dst) = make_float2(c0, c1);
+            if (c_dst) {
+                if (pol_keep)
+                    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(c_dst), "f"(c0), "f"(c1), "l"(pol_keep) : "memory");
+                else
+                    *reinterpret_cast<float2 *>(c_dst) = make_float2(c0, c1);
+            }
             if (w_dst) __stcs(reinterpret_cast<float2 *>(w_dst), make_float2(x0v - c0, x1v - c1));
         }
     }
@@ -382,13 +387,15 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
     if (warp == nwc) {
         if (lane == 0) {
             const float *src = reinterpret_cast<const float *>(p.in) + (long long)frame * p.in_bstride + lo;
+            const uint64_t pol_in = policy_evict_first();  // c_s is dead once this launch has read it
             int slot = 0;
             uint32_t round = 0;
             for (int j = 0; j < n_load; ++j) {
                 if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
                 const long long y = reflect_any(p.gwy0 + r + (long long)(i0 - C + j) * p.d, p.Hg) - p.gwy0 + p.row_off_in;
                 mbar_arrive_expect_tx(&full[slot], row_bytes);
-                tma_load_1d(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[slot]);
+                if (p.l2_hints) tma_load_1d_hint(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[slot], pol_in);
+                else tma_load_1d(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[slot]);
                 if (++slot == p.slots) { slot = 0; ++round; }
             }
         }
@@ -416,6 +423,7 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
     const uint32_t cb = (uint32_t)(xg - lo) * 4u;
     const uint32_t smem_base = smem_u32(rows);
     const float var_factor = (float)bp.var_factor;
+    const uint64_t pol_keep = p.l2_hints ? policy_evict_last() : 0ull;  // c_{s+1}: the next scale reads it back
 
     // Per output row: pass 1 (differences + variance sums from the window rows in shared memory, FMA pipe only), then
     // pass 2 (range weights from the differences kept in registers: 2 MUFU per packed tap).  Warps drift freely (no
@@ -438,11 +446,11 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
             }
             float *c_dst = out_c ? out_c + orow * p.c_pitch + xg : nullptr;
             float *w_dst = out_w ? out_w + orow * p.w_pitch + xg : nullptr;
-            pair_step<TAPS, DMODE, false, true>(D, xc_old, nhi, rowb, cb, colb, rev, var_factor, c_dst, w_dst, act);
+            pair_step<TAPS, DMODE, false, true>(D, xc_old, nhi, rowb, cb, colb, rev, var_factor, c_dst, w_dst, act, pol_keep);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[fslot]);  // the window rows are only read in pass 1
             if (++fslot == p.slots) fslot = 0;
-            pair_step<TAPS, DMODE, true, false>(D, xc_old, nhi, rowb, cb, colb, rev, var_factor, c_dst, w_dst, act);
+            pair_step<TAPS, DMODE, true, false>(D, xc_old, nhi, rowb, cb, colb, rev, var_factor, c_dst, w_dst, act, pol_keep);
             orow += p.d;
         }
         if (++slot == p.slots) { slot = 0; parity ^= 1; }
@@ -639,6 +647,7 @@ int wb_atrous_scale_bilateral(const void *in, void *out_c, void *out_w, int batc
     p.c_pitch = out_c_pitch; p.c_bstride = out_c_bstride;
     p.w_pitch = out_w_pitch; p.w_bstride = out_w_bstride;
     bp.var_factor = var_factor;
+    p.l2_hints = wb::l2_hints_enabled();
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == WB_F32)
         return taps == 3 ? wb::dispatch_bilateral<float, 3>(bp, batch, st) : wb::dispatch_bilateral<float, 5>(bp, batch, st);

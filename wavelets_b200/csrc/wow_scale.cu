@@ -30,7 +30,7 @@ static constexpr int kInRing = 8;  // input rows staged by TMA (C+1 live, the re
 static constexpr int kWRing = 4;   // raw w_s rows (read back by the writing thread C+1 steps later)
 static constexpr int kW2Ring = 2;  // w_s^2 rows (cross-thread, guarded by the split-phase barriers)
 
-template <typename T, int TAPS, int DMODE, int NG>
+template <typename T, int TAPS, int DMODE, int NG, bool HINTS>
 __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
     constexpr int V = VecOf<T>::V;
     constexpr int C = TAPS / 2;
@@ -60,6 +60,9 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
     const T *src = reinterpret_cast<const T *>(p.in) + (long long)frame * p.in_bstride;
     const long long y_first = (long long)r + (long long)(i0 - 2 * C) * p.d;  // image row of input row 0
 
+    const uint64_t pol_in = policy_evict_first();   // c_s is dead once this launch has read it
+    const uint64_t pol_keep = policy_evict_last();  // c_{s+1}: the next scale reads it back
+    constexpr bool hints = HINTS, hints_c = HINTS;
     int next_load = 0;  // thread 0: next chain row to request
     if (tid == 0) {
         for (int s = 0; s < kInRing; ++s) mbar_init(&full[s], 1);
@@ -69,7 +72,8 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
         for (; next_load < n0; ++next_load) {
             const long long y = reflect_any(y_first + (long long)next_load * p.d, p.H);
             mbar_arrive_expect_tx(&full[next_load], row_bytes);
-            tma_load_1d(smem_raw + (size_t)next_load * RB, src + y * p.in_pitch, row_bytes, &full[next_load]);
+            if (hints) tma_load_1d_hint(smem_raw + (size_t)next_load * RB, src + y * p.in_pitch, row_bytes, &full[next_load], pol_in);
+            else tma_load_1d(smem_raw + (size_t)next_load * RB, src + y * p.in_pitch, row_bytes, &full[next_load]);
         }
     }
     __syncthreads();
@@ -132,7 +136,8 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
                     const int sl = next_load & (kInRing - 1);
                     const long long y = reflect_any(y_first + (long long)next_load * p.d, p.H);
                     mbar_arrive_expect_tx(&full[sl], row_bytes);
-                    tma_load_1d(smem_raw + (size_t)sl * RB, src + y * p.in_pitch, row_bytes, &full[sl]);
+                    if (hints) tma_load_1d_hint(smem_raw + (size_t)sl * RB, src + y * p.in_pitch, row_bytes, &full[sl], pol_in);
+                    else tma_load_1d(smem_raw + (size_t)sl * RB, src + y * p.in_pitch, row_bytes, &full[sl]);
                     ++next_load;
                 }
             }
@@ -165,7 +170,10 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
             const uint32_t w2row = w2_base + (uint32_t)(mc & (kW2Ring - 1)) * RB;
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
-                if (store_c && act[q]) st_vec(c_ptr + xg[q], cv[q]);
+                if (store_c && act[q]) {
+                    if (hints_c) st_vec_hint(c_ptr + xg[q], cv[q], pol_keep);
+                    else st_vec(c_ptr + xg[q], cv[q]);
+                }
                 Pack<T, V> raw = lds_vec<T>(crow + xb[q]);
                 Pack<T, V> sq;
 #pragma unroll
@@ -228,9 +236,9 @@ static bool plan_wow(ScaleParams &p, int taps, int esize, int batch, WowGeom *ge
     return true;
 }
 
-template <typename T, int TAPS, int DMODE>
-static int launch_wow(const ScaleParams &p, int batch, const WowGeom &geo, cudaStream_t st) {
-    auto kern = wow_rows_kernel<T, TAPS, DMODE, 2>;
+template <typename T, int TAPS, int DMODE, bool HINTS>
+static int launch_wow_h(const ScaleParams &p, int batch, const WowGeom &geo, cudaStream_t st) {
+    auto kern = wow_rows_kernel<T, TAPS, DMODE, 2, HINTS>;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -242,6 +250,12 @@ static int launch_wow(const ScaleParams &p, int batch, const WowGeom &geo, cudaS
     dim3 grid((unsigned)((long long)p.d * p.n_seg), (unsigned)batch);
     kern<<<grid, geo.nt, geo.smem, st>>>(p);
     return launch_status();
+}
+
+template <typename T, int TAPS, int DMODE>
+static int launch_wow(const ScaleParams &p, int batch, const WowGeom &geo, cudaStream_t st) {
+    return p.l2_hints ? launch_wow_h<T, TAPS, DMODE, true>(p, batch, geo, st)
+                      : launch_wow_h<T, TAPS, DMODE, false>(p, batch, geo, st);
 }
 
 template <typename T, int TAPS>
@@ -270,6 +284,14 @@ static int fill_wow_params(ScaleParams &p, const void *in, void *out_c, void *ou
     p.in_pitch = in_pitch; p.in_bstride = in_bstride;
     p.c_pitch = c_pitch; p.c_bstride = c_bstride;
     p.w_pitch = w_pitch; p.w_bstride = w_bstride;
+    {
+        static int v = -1;  // WB_L2_HINTS_WOW=0/1/2/3 (bit 0: input evict-first, bit 1: c_{s+1} evict-last); A/B measurements
+        if (v < 0) {
+            const char *e = getenv("WB_L2_HINTS_WOW");
+            v = e ? atoi(e) : 3;
+        }
+        p.l2_hints = l2_hints_enabled() ? v : 0;
+    }
     return WB_OK;
 }
 
