@@ -30,6 +30,7 @@ extern "C" {
 #endif
 
 #define WB_ABI_VERSION 1
+#define WB_MAX_PEERS 16 /* ranks of one NVLink domain whose band buffers wb_atrous_scale_band_p2p can address */
 
 enum { WB_F32 = 0, WB_F64 = 1 };
 enum { WB_TRIANGLE = 3, WB_B3SPLINE = 5 };
@@ -95,6 +96,24 @@ int wb_atrous_scale_band(const void *in, void *out_c, void *out_w, int band_rows
                          long long out_c_row_offset, long long out_c_pitch,
                          long long out_w_row_offset, long long out_w_pitch,
                          int scale, int taps, int dtype, void *stream);
+
+/*
+ * Row-band scale with the halo rows read IN PLACE from the neighbours' band buffers over NVLink (no halo copy, no
+ * padded buffer, no reference equivalent).  The running smooth plane c_s of a global_H-row image is distributed over
+ * n_peers ranks: rank k owns global rows [peer_y0[k], peer_y0[k+1]) (peer_y0 has n_peers + 1 entries, peer_y0[0] = 0,
+ * peer_y0[n_peers] = global_H) in a buffer that starts at peer_in[k] -- an address valid ON THIS DEVICE (the local
+ * buffer for k == rank, peer-mapped memory otherwise: CUDA IPC / symmetric memory).  All buffers share `in_pitch`.
+ * The kernel resolves every chain row (after the symmetric reflection about global_H) to its owner and fetches it
+ * with the same TMA bulk copy as a local row.  Output row i (global row peer_y0[rank] + i) goes to row i of
+ * out_c / out_w (local memory).  `peer_in` and `peer_y0` are HOST arrays, copied into the launch parameters.
+ * The caller orders the ranks: every rank must have finished writing its c_s (and reading the buffer that out_c
+ * overwrites) before any rank launches this scale -- one device-side barrier per scale.  Same arithmetic as
+ * wb_atrous_scale, hence bit-identical to the unsharded cascade.
+ */
+int wb_atrous_scale_band_p2p(const void *const *peer_in, const long long *peer_y0, int n_peers, int rank,
+                             void *out_c, void *out_w, int W, int global_H, long long in_pitch,
+                             long long out_c_pitch, long long out_w_pitch, int scale, int taps, int dtype,
+                             void *stream);
 
 /*
  * One scale of the BILATERAL cascade.  Replaces, per scale, watroo/wavelets.py:433-442: sdev_loc (:24-32), the

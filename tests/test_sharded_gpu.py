@@ -44,6 +44,46 @@ def test_band_window_equals_rows_of_full_transform(dt):
                 assert torch.equal(out_c[pad:pad + rows], c[s + 1][y0:y1]), (sf.__name__, rank, s)
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+@pytest.mark.parametrize("shape,world", [((384, 512), 3), ((200, 264), 5), ((96, 130), 2)])
+def test_peer_window_scale_equals_rows_of_full_transform(dt, shape, world):
+    """wb_atrous_scale_band_p2p with the ranks' band buffers as separate allocations of ONE device (the address
+    arithmetic is the same as with NVLink-mapped peers): every band of every scale must equal the unsharded cascade
+    bit for bit, including halos that span several bands / several reflections and the generic (unaligned) kernel."""
+    import wavelets_b200 as wb
+    from wavelets_b200.sharded import band_range, band_scale_p2p
+    h, w = shape
+    level = 6
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    img = torch.randn((h, w), generator=gen, device="cuda", dtype=torch.float32).to(dt)
+    for sf in (wb.B3spline, wb.Triangle):
+        full = wb.AtrousTransform(sf)(img, level).data
+        c = [img]
+        for s in range(level):
+            c.append(wb.atrous_scale(c[-1], s, sf(2), out_w=False)[0])
+        y0s = [band_range(h, k, world)[0] for k in range(world)] + [h]
+        for s in range(level):
+            bands = [c[s][y0s[k]:y0s[k + 1]].clone() for k in range(world)]  # separate allocations
+            ptrs = [b.data_ptr() for b in bands]
+            for rank in range(world):
+                rows = y0s[rank + 1] - y0s[rank]
+                out_c = torch.empty((rows, w), dtype=dt, device="cuda")
+                out_w = torch.empty((rows, w), dtype=dt, device="cuda")
+                band_scale_p2p(ptrs, y0s, rank, out_c, out_w, w, w, s, sf.taps_code, dt, img.device)
+                assert torch.equal(out_w, full[s, y0s[rank]:y0s[rank + 1]]), (sf.__name__, rank, s)
+                assert torch.equal(out_c, c[s + 1][y0s[rank]:y0s[rank + 1]]), (sf.__name__, rank, s)
+
+
+def test_peer_window_rejects_bad_arguments():
+    from wavelets_b200.sharded import band_scale_p2p
+    a = torch.zeros((8, 64), device="cuda")
+    o = torch.zeros((8, 64), device="cuda")
+    with pytest.raises(RuntimeError):  # boundaries must start at 0 and every rank must own a row
+        band_scale_p2p([a.data_ptr(), a.data_ptr()], [0, 8, 8], 0, o, None, 64, 64, 0, 5, torch.float32, a.device)
+    with pytest.raises(RuntimeError):  # output aliases an input window
+        band_scale_p2p([a.data_ptr()], [0, 8], 0, a, None, 64, 64, 0, 5, torch.float32, a.device)
+
+
 def test_banded_two_ranks_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -53,3 +93,4 @@ def test_banded_two_ranks_nccl():
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
     assert '"bit_identical": true' in proc.stdout
+    assert "p2p   banded == unsharded on all ranks: True" in proc.stdout  # in-kernel NVLink halo reads

@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--levels", type=int, default=10)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-check", action="store_true", help="skip the unsharded comparison (image too large for one GPU)")
+    ap.add_argument("--quick", action="store_true", help="B3spline fp32 only")
+    ap.add_argument("--modes", default="nccl,p2p", help="halo transport: nccl (send/recv exchange), p2p (in-kernel peer reads)")
+    ap.add_argument("--out", default="", help="also write the JSON summary to this file (rank 0)")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -35,8 +38,11 @@ def main():
     y0, y1 = band_range(h, rank, world)
     ok = True
     results = {}
-    for sf in (wb.B3spline, wb.Triangle):
-        for dt in (torch.float32, torch.float64):
+    modes = [m for m in args.modes.split(",") if m]
+    cases = [(wb.B3spline, torch.float32)] if args.quick else [
+        (sf, dt) for sf in (wb.B3spline, wb.Triangle) for dt in (torch.float32, torch.float64)]
+    for sf, dt in cases:
+        if True:
             gen = torch.Generator(device=dev).manual_seed(7)
             if args.no_check:
                 # every rank generates only its band (seeded per rank)
@@ -45,38 +51,47 @@ def main():
             else:
                 img = torch.randn((h, w), generator=gen, device=dev, dtype=torch.float32).to(dt)
                 band = img[y0:y1].contiguous()
-            bt = BandedTransform(sf, poison=True)
-            planes = bt(band, args.levels, h)
-            torch.cuda.synchronize()
-            if not args.no_check:
-                full = wb.AtrousTransform(sf)(img, args.levels).data
-                same = torch.equal(planes, full[:, y0:y1])
-                flag = torch.tensor([1 if same else 0], device=dev)
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                ok = ok and bool(flag.item())
-                if rank == 0:
-                    print(f"{sf.__name__:9s} {str(dt):14s} banded == unsharded on all ranks: {bool(flag.item())}", flush=True)
+            full = None if args.no_check else wb.AtrousTransform(sf)(img, args.levels).data
+            for mode in modes:
+                bt = BandedTransform(sf, poison=True, p2p=(mode == "p2p"))
+                planes = bt(band, args.levels, h)
+                torch.cuda.synchronize()
+                if full is not None:
+                    same = torch.equal(planes, full[:, y0:y1])
+                    flag = torch.tensor([1 if same else 0], device=dev)
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                    ok = ok and bool(flag.item())
+                    if rank == 0:
+                        print(f"{sf.__name__:9s} {str(dt):14s} {mode:5s} banded == unsharded on all ranks: "
+                              f"{bool(flag.item())}", flush=True)
+                del planes
+                # timing of the sharded cascade (device time, max over ranks)
+                bt = BandedTransform(sf, p2p=(mode == "p2p"))
+                for _ in range(2):
+                    bt(band, args.levels, h)
+                dist.barrier(); torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.reps):
+                    bt(band, args.levels, h)
+                e1.record()
+                dist.barrier(); torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / args.reps], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                results[f"{sf.__name__}_{str(dt).split('.')[-1]}_{mode}"] = {
+                    "ms": t.item(), "mpx_scales_per_s": h * w * args.levels / t.item() / 1e3}
+                del bt
+            if full is not None:
                 del full, img
-            # timing of the sharded cascade (device time, max over ranks)
-            bt = BandedTransform(sf)
-            for _ in range(2):
-                bt(band, args.levels, h)
-            dist.barrier(); torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.reps):
-                bt(band, args.levels, h)
-            e1.record()
-            dist.barrier(); torch.cuda.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1) / args.reps], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            results[f"{sf.__name__}_{str(dt).split('.')[-1]}"] = {
-                "ms": t.item(), "mpx_scales_per_s": h * w * args.levels / t.item() / 1e3}
-            del planes, band
+            del band
             torch.cuda.empty_cache()
     if rank == 0:
-        print(json.dumps({"check": "banded_vs_unsharded", "n_gpus": world, "side": [h, w], "levels": args.levels,
-                          "bit_identical": ok if not args.no_check else None, "timing": results}), flush=True)
+        line = json.dumps({"check": "banded_vs_unsharded", "n_gpus": world, "side": [h, w], "levels": args.levels,
+                           "bit_identical": ok if not args.no_check else None, "timing": results})
+        print(line, flush=True)
+        if args.out:
+            with open(args.out, "w") as fh:
+                fh.write(line + "\n")
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

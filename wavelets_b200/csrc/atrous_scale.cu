@@ -71,18 +71,19 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
     if (warp == nwc) {
         // ---------------- producer warp: one lane streams the chain rows into the ring ----------------
         if (lane == 0) {
-            const T *src = reinterpret_cast<const T *>(p.in) + (long long)frame * p.in_bstride + lo;
+            const long long foff = (long long)frame * p.in_bstride + lo;
             const uint64_t pol_in = policy_evict_first();  // c_s is dead once this launch has read it
             int slot = 0;
             uint32_t round = 0;
             for (int j = 0; j < n_load; ++j) {
                 if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
-                const long long y = reflect_any(p.gwy0 + r + (long long)(i0 - C + j) * p.d, p.Hg) - p.gwy0 + p.row_off_in;
+                // the row may live in a neighbour's band buffer (peer-window mode): same bulk copy, over NVLink
+                const T *src = input_row<T>(p, reflect_any(p.gwy0 + r + (long long)(i0 - C + j) * p.d, p.Hg)) + foff;
                 mbar_arrive_expect_tx(&full[slot], row_bytes);
                 if (p.l2_hints)
-                    tma_load_1d_hint(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[slot], pol_in);
+                    tma_load_1d_hint(rows + (size_t)slot * p.row_stride, src, row_bytes, &full[slot], pol_in);
                 else
-                    tma_load_1d(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[slot]);
+                    tma_load_1d(rows + (size_t)slot * p.row_stride, src, row_bytes, &full[slot]);
                 if (++slot == p.slots) { slot = 0; ++round; }
             }
         }
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256) atrous_generic_kernel(const ScaleParams p
     constexpr int C = TAPS / 2;
     const long long n = (long long)p.H * p.W;
     const int frame = blockIdx.y;
-    const T *in = reinterpret_cast<const T *>(p.in) + (long long)frame * p.in_bstride;
+    const long long foff = (long long)frame * p.in_bstride;
     T *out_c = reinterpret_cast<T *>(p.out_c);
     T *out_w = reinterpret_cast<T *>(p.out_w);
     WhitenEpilogue<T> epi;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(256) atrous_generic_kernel(const ScaleParams p
         T acc = T(0);
 #pragma unroll
         for (int i = 0; i < TAPS; ++i) {
-            const T *row = in + (reflect_any(p.gwy0 + y + (long long)(i - C) * p.d, p.Hg) - p.gwy0 + p.row_off_in) * p.in_pitch;
+            const T *row = input_row<T>(p, reflect_any(p.gwy0 + y + (long long)(i - C) * p.d, p.Hg)) + foff;
             T ra = T(0);
 #pragma unroll
             for (int k = 0; k < TAPS; ++k) {
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(256) atrous_generic_kernel(const ScaleParams p
             }
             acc = (i == 0) ? Taps<T, TAPS>::h(0) * ra : fma_t<T>(Taps<T, TAPS>::h(i), ra, acc);
         }
-        const T raw = in[((long long)y + p.row_off_in) * p.in_pitch + x];
+        const T raw = (input_row<T>(p, p.gwy0 + y) + foff)[x];
         if constexpr (OP == OP_TRANSFORM) {
             if (out_c) out_c[(long long)frame * p.c_bstride + ((long long)y + p.row_off_c) * p.c_pitch + x] = acc;
             if (out_w) out_w[(long long)frame * p.w_bstride + ((long long)y + p.row_off_w) * p.w_pitch + x] = raw - acc;
@@ -342,6 +343,42 @@ int wb_atrous_scale_band(const void *in, void *out_c, void *out_w, int band_rows
     p.H = band_rows; p.W = W; p.d = 1 << scale; p.Hg = global_H;
     p.gwy0 = band_y0; p.row_off_in = in_row_offset; p.row_off_c = out_c_row_offset; p.row_off_w = out_w_row_offset;
     p.in_pitch = in_pitch; p.c_pitch = out_c_pitch; p.w_pitch = out_w_pitch;
+    return wb::dispatch_typed<wb::OP_TRANSFORM>(p, 1, scale, taps, dtype, (cudaStream_t)stream);
+}
+
+int wb_atrous_scale_band_p2p(const void *const *peer_in, const long long *peer_y0, int n_peers, int rank,
+                             void *out_c, void *out_w, int W, int global_H, long long in_pitch,
+                             long long out_c_pitch, long long out_w_pitch, int scale, int taps, int dtype,
+                             void *stream) {
+    if (!peer_in || !peer_y0) return WB_EINVAL_POINTER;
+    if (n_peers < 1 || n_peers > WB_MAX_PEERS || rank < 0 || rank >= n_peers) return WB_EINVAL_ARG;
+    if (peer_y0[0] != 0 || peer_y0[n_peers] != global_H) return WB_EINVAL_ARG;
+    for (int k = 0; k < n_peers; ++k) {
+        if (peer_y0[k + 1] <= peer_y0[k]) return WB_EINVAL_ARG;  // every rank owns at least one row
+        if (!peer_in[k] || peer_in[k] == out_c || peer_in[k] == out_w) return WB_EINVAL_POINTER;
+    }
+    const long long band_rows = peer_y0[rank + 1] - peer_y0[rank];
+    if (band_rows > 0x7fffffffLL) return WB_EINVAL_SHAPE;
+    int rc = wb::check_common(1, (int)band_rows, W, taps, dtype);
+    if (rc) return rc;
+    if (scale < 0 || scale > 30) return WB_EINVAL_SCALE;
+    if (!out_c && !out_w) return WB_EINVAL_POINTER;
+    if (in_pitch < W || (out_c && out_c_pitch < W) || (out_w && out_w_pitch < W)) return WB_EINVAL_ARG;
+    wb::ScaleParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = peer_in[rank]; p.out_c = out_c; p.out_w = out_w;
+    p.H = (int)band_rows; p.W = W; p.d = 1 << scale; p.Hg = global_H;
+    p.gwy0 = peer_y0[rank];
+    p.in_pitch = in_pitch; p.c_pitch = out_c_pitch; p.w_pitch = out_w_pitch;
+    p.n_peers = n_peers;
+    for (int k = 0; k < n_peers; ++k) {
+        p.peer_in[k] = peer_in[k];
+        p.peer_y0[k] = peer_y0[k];
+        // the vector path needs every window 16-byte aligned; otherwise the generic kernel takes the launch
+        if (!wb::aligned16(peer_in[k])) p.in = peer_in[k];
+    }
+    p.peer_y0[n_peers] = peer_y0[n_peers];
+    p.l2_hints = wb::l2_hints_enabled();
     return wb::dispatch_typed<wb::OP_TRANSFORM>(p, 1, scale, taps, dtype, (cudaStream_t)stream);
 }
 

@@ -214,27 +214,6 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
 // Differences to the scalar formulation (all far below the fp32 parity budget): the tap weight enters through the
 // exponent (2^(a + log2 k) instead of k 2^a), 1/(2V) and the final num/den use rcp.approx.
 // ---------------------------------------------------------------------------------------------------------------
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk2(float lo, float hi) {
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void up2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ u64 lds64(uint32_t a) {
-    u64 r;
-    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(a));
-    return r;
-}
-__device__ __forceinline__ u64 swap2(u64 v) { float lo, hi; up2(v, lo, hi); return pk2(hi, lo); }
 __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // log2 of the taps (dyadic rationals except 3/8): log2(h_i h_k) = l_i + l_k

@@ -141,6 +141,54 @@ __device__ __forceinline__ void st_vec_hint(double *p, const Pack<double, 2> &r,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2): two IEEE fp32 operations per lane per issue slot on a
+// 64-bit register pair.  Same roundings as the scalar instructions, half the issue slots (tools/fma2bench.cu).
+// ---------------------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void up2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 lds64(uint32_t a) {
+    u64 r;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ u64 swap2(u64 v) { float lo, hi; up2(v, lo, hi); return pk2(hi, lo); }
+// four consecutive fp32 (one 16-byte vector) as two packed pairs
+struct P4 { u64 lo, hi; };
+__device__ __forceinline__ P4 lds_p4(uint32_t a) {
+    P4 r;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(r.lo), "=l"(r.hi) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts_p4(uint32_t a, const P4 &v) {
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(v.lo), "l"(v.hi) : "memory");
+}
+__device__ __forceinline__ void stg_p4(float *p, const P4 &v) {
+    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(v.lo), "l"(v.hi) : "memory");
+}
+__device__ __forceinline__ void stg_p4_cs(float *p, const P4 &v) {
+    asm volatile("st.global.cs.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(v.lo), "l"(v.hi) : "memory");
+}
+__device__ __forceinline__ void stg_p4_hint(float *p, const P4 &v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.b64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(v.lo), "l"(v.hi), "l"(policy)
+                 : "memory");
+}
+// the mirrored vector read backwards
+__device__ __forceinline__ P4 reverse_p4(const P4 &t) { return P4{swap2(t.hi), swap2(t.lo)}; }
+
+// ---------------------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------------------
 inline int dtype_size(int dtype) { return dtype == WB_F32 ? 4 : (dtype == WB_F64 ? 8 : 0); }

@@ -6,6 +6,8 @@
 
 namespace wb {
 
+static constexpr int kMaxPeers = WB_MAX_PEERS;
+
 struct ScaleParams {
     const void *in;
     void *out_c;
@@ -33,7 +35,22 @@ struct ScaleParams {
     const double *noise_dev;   // device scalar per frame (from wb_abs_median), or nullptr
     double weight;             // recomposition weight of this plane
     int l2_hints;              // 1: L2 eviction-priority hints on loads / stores (see common.cuh)
+    // --- peer-window mode (wb_atrous_scale_band_p2p): the rows of c_s live in the band buffers of ALL ranks, every
+    // one mapped into this process (NVLink peer memory).  Rank k's buffer starts at peer_in[k] and its row 0 is global
+    // row peer_y0[k]; peer_y0[n_peers] = Hg.  n_peers == 0: a single window `in` (everything above).
+    int n_peers;
+    long long peer_y0[kMaxPeers + 1];
+    const void *peer_in[kMaxPeers];
 };
+
+// Address of global input row gy (already reflected into [0, Hg)) of this launch's frame-0 window.
+template <typename T>
+__device__ __forceinline__ const T *input_row(const ScaleParams &p, long long gy) {
+    if (p.n_peers == 0) return reinterpret_cast<const T *>(p.in) + (gy - p.gwy0 + p.row_off_in) * p.in_pitch;
+    int k = 0;
+    while (k + 1 < p.n_peers && gy >= p.peer_y0[k + 1]) ++k;
+    return reinterpret_cast<const T *>(p.peer_in[k]) + (gy - p.peer_y0[k]) * p.in_pitch;
+}
 
 enum { OP_TRANSFORM = 0, OP_WHITEN = 1 };
 
@@ -225,6 +242,66 @@ __device__ __forceinline__ T col_feed(T (&S)[TAPS - 1], T v) {
 #pragma unroll
     for (int t = 0; t + 2 < TAPS; ++t) S[t] = fma_t<T>(Taps<T, TAPS>::h(TAPS - 2 - t), v, S[t + 1]);
     S[TAPS - 2] = Taps<T, TAPS>::h(0) * v;
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Packed fp32x2 forms of the row pass and of the running column sums (fp32, DMODE 0 or 2: every tap of a pixel pair
+// is again an aligned pair).  Same operations in the same order as row_pass_b / col_feed, two pixels per issue slot.
+// ---------------------------------------------------------------------------------------------------------------
+template <int TAPS> struct PackedTaps {
+    u64 h[TAPS];
+    __device__ __forceinline__ PackedTaps() {
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) h[k] = pk2(Taps<float, TAPS>::h(k), Taps<float, TAPS>::h(k));
+    }
+};
+
+template <int TAPS, int DMODE, bool MIRROR>
+__device__ __forceinline__ P4 row_pass_p_impl(uint32_t base, const BytePlan<PlanSize<TAPS, DMODE>::NV> &tp,
+                                              const PackedTaps<TAPS> &H) {
+    static_assert(DMODE == 0 || DMODE == 2, "packed row pass: d % 4 == 0 or d == 2");
+    constexpr int C = TAPS / 2;
+    P4 acc;
+    if constexpr (DMODE == 0) {
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            P4 t = lds_p4(base + tp.off[k]);
+            if (MIRROR && ((tp.rev >> k) & 1u)) t = reverse_p4(t);
+            acc.lo = (k == 0) ? mul2(H.h[0], t.lo) : fma2(H.h[k], t.lo, acc.lo);
+            acc.hi = (k == 0) ? mul2(H.h[0], t.hi) : fma2(H.h[k], t.hi, acc.hi);
+        }
+    } else {
+        u64 win[6];  // previous, current, next vector as six pixel pairs
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            P4 t = lds_p4(base + tp.off[k]);
+            if (MIRROR && ((tp.rev >> k) & 1u)) t = reverse_p4(t);
+            win[2 * k] = t.lo;
+            win[2 * k + 1] = t.hi;
+        }
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            const int i = 2 + (k - C);  // pair that holds tap k of pixels (0, 1); pixels (2, 3) use the next pair
+            acc.lo = (k == 0) ? mul2(H.h[0], win[i]) : fma2(H.h[k], win[i], acc.lo);
+            acc.hi = (k == 0) ? mul2(H.h[0], win[i + 1]) : fma2(H.h[k], win[i + 1], acc.hi);
+        }
+    }
+    return acc;
+}
+template <int TAPS, int DMODE>
+__device__ __forceinline__ P4 row_pass_p(uint32_t base, const BytePlan<PlanSize<TAPS, DMODE>::NV> &tp,
+                                         const PackedTaps<TAPS> &H) {
+    if (tp.rev == 0) return row_pass_p_impl<TAPS, DMODE, false>(base, tp, H);
+    return row_pass_p_impl<TAPS, DMODE, true>(base, tp, H);
+}
+
+template <int TAPS>
+__device__ __forceinline__ u64 col_feed_p(u64 (&S)[TAPS - 1], u64 v, const PackedTaps<TAPS> &H) {
+    const u64 out = fma2(H.h[TAPS - 1], v, S[0]);
+#pragma unroll
+    for (int t = 0; t + 2 < TAPS; ++t) S[t] = fma2(H.h[TAPS - 2 - t], v, S[t + 1]);
+    S[TAPS - 2] = mul2(H.h[0], v);
     return out;
 }
 

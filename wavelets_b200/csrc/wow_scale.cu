@@ -194,6 +194,169 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// fp32, d % 4 == 0 or d == 2: the same kernel on PACKED pixel pairs (FFMA2 / FMUL2 / FADD2).  The scalar kernel is
+// bound by instruction issue, not by HBM (37 M warp instructions per 4096^2 plane, 57 % issue-active, DRAM 30 %); with
+// every tap of a pixel pair being an aligned pair again, each 16-byte vector is carried as two 64-bit register pairs
+// from LDS.128 to STG.128 and every filter FMA, the subtraction, the square and the epilogue multiplies issue once
+// per two pixels.  Operation order and roundings are those of the scalar kernel: the planes are bit-identical.
+// ---------------------------------------------------------------------------------------------------------------
+template <int TAPS, int DMODE, bool HINTS>
+__global__ void __launch_bounds__(512, 1) wow_rows_packed_kernel(const ScaleParams p) {
+    using T = float;
+    constexpr int V = 4, NG = 2;
+    constexpr int C = TAPS / 2;
+    constexpr int NV = PlanSize<TAPS, DMODE>::NV;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t RB = (uint32_t)p.row_stride * (uint32_t)sizeof(T);
+    const uint32_t in_base = smem_u32(smem_raw);
+    const uint32_t w_base = in_base + (uint32_t)kInRing * RB;
+    const uint32_t w2_base = w_base + (uint32_t)kWRing * RB;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(kInRing + kWRing + kW2Ring) * RB);
+    uint64_t *wbar = full + kInRing;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+
+    int bx = blockIdx.x;
+    const int r = bx % p.d;
+    const int g = bx / p.d;
+    const int frame = blockIdx.y;
+
+    const int n_chain = (r < p.H) ? (p.H - r + p.d - 1) / p.d : 0;
+    const int i0 = g * p.seg;
+    const int n_out = min(p.seg, n_chain - i0);
+    if (n_out <= 0) return;
+    const int n_load = n_out + 4 * C;
+    const uint32_t row_bytes = (uint32_t)p.W * (uint32_t)sizeof(T);
+    const T *src = reinterpret_cast<const T *>(p.in) + (long long)frame * p.in_bstride;
+    const long long y_first = (long long)r + (long long)(i0 - 2 * C) * p.d;
+
+    const uint64_t pol_in = policy_evict_first();
+    const uint64_t pol_keep = policy_evict_last();
+    int next_load = 0;
+    if (tid == 0) {
+        for (int s = 0; s < kInRing; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kW2Ring; ++s) mbar_init(&wbar[s], blockDim.x >> 5);
+        fence_mbar_init();
+        const int n0 = min(kInRing, n_load);
+        for (; next_load < n0; ++next_load) {
+            const long long y = reflect_any(y_first + (long long)next_load * p.d, p.H);
+            mbar_arrive_expect_tx(&full[next_load], row_bytes);
+            if (HINTS) tma_load_1d_hint(smem_raw + (size_t)next_load * RB, src + y * p.in_pitch, row_bytes, &full[next_load], pol_in);
+            else tma_load_1d(smem_raw + (size_t)next_load * RB, src + y * p.in_pitch, row_bytes, &full[next_load]);
+        }
+    }
+    __syncthreads();
+
+    WhitenEpilogue<T> epi;
+    epi.init(p, frame);
+    const PackedTaps<TAPS> H;
+
+    uint32_t xb[NG];
+    int xg[NG];
+    bool act[NG];
+    BytePlan<NV> plan[NG];
+#pragma unroll
+    for (int q = 0; q < NG; ++q) {
+        xg[q] = (q * (int)blockDim.x + tid) * V;
+        act[q] = xg[q] < p.W;
+        if (!act[q]) xg[q] = 0;
+        xb[q] = (uint32_t)xg[q] * (uint32_t)sizeof(T);
+        const TapPlan<NV> tp = make_tap_plan<V, NV>(xg[q], DMODE == 0 ? p.d : V, p.W, 0);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) plan[q].off[k] = (uint32_t)tp.off[k] * (uint32_t)sizeof(T);
+        plan[q].rev = tp.rev;
+    }
+
+    u64 SA[NG][2][TAPS - 1], SB[NG][2][TAPS - 1];  // running column sums, one pixel pair per entry
+#pragma unroll
+    for (int q = 0; q < NG; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int t = 0; t < TAPS - 1; ++t) { SA[q][e][t] = 0ull; SB[q][e][t] = 0ull; }
+
+    T *c_ptr = reinterpret_cast<T *>(p.out_c) + (long long)frame * p.c_bstride +
+               ((long long)r + (long long)(i0 - C) * p.d) * p.c_pitch;
+    T *o_ptr = reinterpret_cast<T *>(p.out_w) + (long long)frame * p.w_bstride +
+               ((long long)r + (long long)i0 * p.d) * p.w_pitch;
+    const long long c_step = (long long)p.d * p.c_pitch, o_step = (long long)p.d * p.w_pitch;
+
+    // same step structure as wow_rows_kernel: A (input row j), B (power of the w^2 row of step j-1), C (c / w / w^2)
+    for (int j = 0; j <= n_load; ++j) {
+        P4 cv[NG];
+        if (j < n_load) {
+            mbar_wait(&full[j & (kInRing - 1)], (uint32_t)(j / kInRing) & 1u);
+            const uint32_t row = in_base + (uint32_t)(j & (kInRing - 1)) * RB;
+#pragma unroll
+            for (int q = 0; q < NG; ++q) {
+                const P4 v = row_pass_p<TAPS, DMODE>(row, plan[q], H);
+                cv[q].lo = col_feed_p<TAPS>(SA[q][0], v.lo, H);
+                cv[q].hi = col_feed_p<TAPS>(SA[q][1], v.hi, H);
+            }
+        }
+        if (j > 2 * C) {
+            const int mb = j - 1 - 2 * C;
+            mbar_wait(&wbar[mb & (kW2Ring - 1)], (uint32_t)(mb / kW2Ring) & 1u);
+            if (tid == 0) {
+                while (next_load < n_load && next_load - kInRing <= j - 1 - C) {
+                    const int sl = next_load & (kInRing - 1);
+                    const long long y = reflect_any(y_first + (long long)next_load * p.d, p.H);
+                    mbar_arrive_expect_tx(&full[sl], row_bytes);
+                    if (HINTS) tma_load_1d_hint(smem_raw + (size_t)sl * RB, src + y * p.in_pitch, row_bytes, &full[sl], pol_in);
+                    else tma_load_1d(smem_raw + (size_t)sl * RB, src + y * p.in_pitch, row_bytes, &full[sl]);
+                    ++next_load;
+                }
+            }
+            const uint32_t row = w2_base + (uint32_t)(mb & (kW2Ring - 1)) * RB;
+            P4 pw[NG];
+#pragma unroll
+            for (int q = 0; q < NG; ++q) {
+                const P4 v = row_pass_p<TAPS, DMODE>(row, plan[q], H);
+                pw[q].lo = col_feed_p<TAPS>(SB[q][0], v.lo, H);
+                pw[q].hi = col_feed_p<TAPS>(SB[q][1], v.hi, H);
+            }
+            if (j > 4 * C) {
+                const uint32_t wrow = w_base + (uint32_t)((j - 1 - 3 * C) & (kWRing - 1)) * RB;
+#pragma unroll
+                for (int q = 0; q < NG; ++q) {
+                    P4 raw = lds_p4(wrow + xb[q]);
+                    raw.lo = epi.apply2(raw.lo, pw[q].lo);
+                    raw.hi = epi.apply2(raw.hi, pw[q].hi);
+                    if (act[q]) stg_p4_cs(o_ptr + xg[q], raw);
+                }
+                o_ptr += o_step;
+            }
+        }
+        if (j >= 2 * C && j < n_load) {
+            const int mc = j - 2 * C;
+            const bool store_c = (mc >= C) && (mc - C < n_out);
+            const uint32_t crow = in_base + (uint32_t)((j - C) & (kInRing - 1)) * RB;
+            const uint32_t wrow = w_base + (uint32_t)(mc & (kWRing - 1)) * RB;
+            const uint32_t w2row = w2_base + (uint32_t)(mc & (kW2Ring - 1)) * RB;
+#pragma unroll
+            for (int q = 0; q < NG; ++q) {
+                if (store_c && act[q]) {
+                    if (HINTS) stg_p4_hint(c_ptr + xg[q], cv[q], pol_keep);
+                    else stg_p4(c_ptr + xg[q], cv[q]);
+                }
+                P4 raw = lds_p4(crow + xb[q]);
+                raw.lo = sub2(raw.lo, cv[q].lo);
+                raw.hi = sub2(raw.hi, cv[q].hi);
+                const P4 sq{mul2(raw.lo, raw.lo), mul2(raw.hi, raw.hi)};
+                if (act[q]) {
+                    sts_p4(wrow + xb[q], raw);
+                    sts_p4(w2row + xb[q], sq);
+                }
+            }
+            c_ptr += c_step;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&wbar[mc & (kW2Ring - 1)]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Host
 // ---------------------------------------------------------------------------------------------------------------
 struct WowGeom { int nt, ng; size_t smem; };
@@ -236,16 +399,35 @@ static bool plan_wow(ScaleParams &p, int taps, int esize, int batch, WowGeom *ge
     return true;
 }
 
+// WB_WOW_PACKED=0 in the environment selects the scalar fp32 kernel (A/B measurements, bit-identity tests).
+static bool wow_packed_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("WB_WOW_PACKED");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+template <typename T, int TAPS, int DMODE, bool HINTS>
+static auto wow_kernel_for(bool packed) -> void (*)(const ScaleParams) {
+    if constexpr (sizeof(T) == 4 && (DMODE == 0 || DMODE == 2)) {
+        if (packed) return wow_rows_packed_kernel<TAPS, DMODE, HINTS>;
+    }
+    return wow_rows_kernel<T, TAPS, DMODE, 2, HINTS>;
+}
+
 template <typename T, int TAPS, int DMODE, bool HINTS>
 static int launch_wow_h(const ScaleParams &p, int batch, const WowGeom &geo, cudaStream_t st) {
-    auto kern = wow_rows_kernel<T, TAPS, DMODE, 2, HINTS>;
-    static bool configured[64] = {};
+    const bool packed = wow_packed_enabled();
+    auto kern = wow_kernel_for<T, TAPS, DMODE, HINTS>(packed);
+    static bool configured[2][64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
+    if (dev < 0 || dev >= 64 || !configured[packed][dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
         if (e != cudaSuccess) return (int)e;
-        if (dev >= 0 && dev < 64) configured[dev] = true;
+        if (dev >= 0 && dev < 64) configured[packed][dev] = true;
     }
     dim3 grid((unsigned)((long long)p.d * p.n_seg), (unsigned)batch);
     kern<<<grid, geo.nt, geo.smem, st>>>(p);

@@ -11,6 +11,11 @@ Two modes, one process per GPU (``torch.distributed``, NCCL on GPUs, gloo in the
   global top/bottom come from the symmetric reflection about the GLOBAL height, which always lands inside a band's
   own window.  Each band then runs ``wb_atrous_scale_band`` -- the same kernel and arithmetic as the single-device
   path, so the sharded planes are bit-identical to the unsharded ones.
+  ``BandedTransform(p2p=True)`` removes the exchange altogether: the ping-pong band buffers live in symmetric memory
+  (``torch.distributed._symmetric_memory``: every rank's buffer is mapped into every process over NVLink) and
+  ``wb_atrous_scale_band_p2p`` fetches each halo row straight from its owner's buffer with the same TMA bulk copy as
+  a local row -- compute and communication are one kernel; the only synchronisation is one device-side barrier per
+  scale on the launch stream (no host sync, no staging copy, no padded buffer).
 """
 from __future__ import annotations
 
@@ -20,7 +25,8 @@ import torch.distributed as dist
 from . import _lib
 from .scaling import B3spline
 
-__all__ = ["frame_shard", "band_range", "halo_rows", "exchange_plan", "exchange_halos", "BandedTransform"]
+__all__ = ["frame_shard", "band_range", "halo_rows", "exchange_plan", "exchange_halos", "BandedTransform",
+           "band_scale_p2p", "PeerBandBuffers"]
 
 
 def frame_shard(n_frames: int, rank: int, world: int) -> range:
@@ -104,6 +110,49 @@ def _cuda_band_scale(ext_in, pad, ext_out, out_pad, w_out, band_rows, width, hei
                                             _lib.stream_ptr(ext_in.device)))
 
 
+def band_scale_p2p(peer_ptrs, peer_y0, rank, out_c, out_w, width, pitch, scale, taps_code, dtype, device):
+    """One scale of band ``rank`` with every input row read from its owner's buffer: wb_atrous_scale_band_p2p.
+
+    ``peer_ptrs[k]`` is the address (valid on ``device``) of row 0 of rank k's band of c_s, ``peer_y0`` the
+    ``world + 1`` band boundaries.  ``out_c`` / ``out_w`` are local ``(band_rows, width)`` tensors (or None)."""
+    import ctypes
+    lib = _lib.load(require_cuda=True)
+    n = len(peer_ptrs)
+    ptrs = (ctypes.c_void_p * n)(*[int(a) for a in peer_ptrs])
+    y0s = (ctypes.c_longlong * (n + 1))(*[int(y) for y in peer_y0])
+    with torch.cuda.device(device):
+        _lib.check(lib.wb_atrous_scale_band_p2p(
+            ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(y0s, ctypes.c_void_p), n, rank,
+            out_c.data_ptr() if out_c is not None else None, out_w.data_ptr() if out_w is not None else None,
+            width, int(peer_y0[-1]), pitch, out_c.stride(0) if out_c is not None else 0,
+            out_w.stride(0) if out_w is not None else 0, scale, taps_code, _lib.dtype_code(dtype),
+            _lib.stream_ptr(device)))
+
+
+_PEER_BUFFERS: dict = {}
+
+
+class PeerBandBuffers:
+    """Ping-pong buffers for the running smooth plane c_s of one band, allocated in symmetric memory so that every
+    rank of the group can address every other rank's rows (NVLink peer mapping).  ``buf[b]`` is this rank's
+    ``(rows_max, width)`` half b; ``ptrs(b)[k]`` is the address of rank k's half b as seen from this device."""
+
+    def __init__(self, rows_max: int, width: int, dtype: torch.dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.buf = symm_mem.empty((2, rows_max, width), dtype=dtype, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        half = rows_max * width * self.buf.element_size()
+        self._ptrs = [[int(base) + b * half for base in self.handle.buffer_ptrs] for b in range(2)]
+
+    def ptrs(self, b: int):
+        return self._ptrs[b]
+
+    def barrier(self):
+        """Device-side barrier of all ranks on the current stream (signal pads in symmetric memory)."""
+        self.handle.barrier(channel=0)
+
+
 class BandedTransform:
     """Plain à trous cascade of ONE image sharded by row bands over the ranks of a process group.
 
@@ -111,11 +160,34 @@ class BandedTransform:
     CPU tensor with a custom ``scale_fn`` in the gloo tests).  Returns this rank's rows of the coefficient planes,
     shape ``(level + 1, band_rows, W)``.  ``scale_fn`` computes one scale of one band (default: the CUDA kernel)."""
 
-    def __init__(self, scaling_function_class=B3spline, group=None, scale_fn=None, poison=False):
+    def __init__(self, scaling_function_class=B3spline, group=None, scale_fn=None, poison=False, p2p=False):
         self.scaling_function_class = scaling_function_class
         self.group = group
         self.scale_fn = scale_fn or _cuda_band_scale
         self.poison = poison  # tests: NaN-fill the padded buffers so that any read of an unfilled halo row shows up
+        self.p2p = p2p        # halo rows read in place from the neighbours' buffers (NVLink), no exchange
+
+    def _call_p2p(self, band, planes, level, global_height, sf, rank, world):
+        rows, width = band.shape
+        rows_max = band_range(global_height, 0, world)[1]
+        # symmetric allocations are collective and never shrink: keep one set per (group, geometry) for the process
+        key = (id(self.group), rows_max, width, band.dtype, band.device.index)
+        peer = _PEER_BUFFERS.get(key)
+        if peer is None:
+            peer = _PEER_BUFFERS[key] = PeerBandBuffers(rows_max, width, band.dtype, band.device, self.group)
+        if self.poison:
+            peer.buf.fill_(float("nan"))  # safe: the previous call ended with a barrier
+        y0s = [band_range(global_height, k, world)[0] for k in range(world)] + [global_height]
+        peer.buf[0, :rows].copy_(band)
+        for s in range(level):
+            # every rank has written its c_s and has finished reading the half this scale overwrites
+            peer.barrier()
+            last = s == level - 1
+            out_c = planes[level] if last else peer.buf[(s + 1) & 1]
+            band_scale_p2p(peer.ptrs(s & 1), y0s, rank, out_c, planes[s], width, width, s, sf.taps_code, band.dtype,
+                           band.device)
+        peer.barrier()  # nobody may refill the buffers (next call) while a neighbour still reads them
+        return planes
 
     def __call__(self, band: torch.Tensor, level: int, global_height: int) -> torch.Tensor:
         sf = self.scaling_function_class(2)
@@ -129,6 +201,8 @@ class BandedTransform:
         if level == 0:
             planes[0].copy_(band)
             return planes
+        if self.p2p and world > 1:
+            return self._call_p2p(band, planes, level, global_height, sf, rank, world)
         pad = halo_rows(level - 1, n_taps) if world > 1 else 0
         pad = min(pad, global_height)
         # two padded buffers hold the running smooth plane c_s (ping-pong); row pad + i <-> global row y0 + i
