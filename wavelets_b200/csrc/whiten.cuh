@@ -58,17 +58,19 @@ template <typename T> struct WhitenEpilogue {
         }
         return w * g;
     }
-    // Two pixels at once (fp32 only): the same operations as apply() with the multiplies packed.
+    // Two pixels at once (fp32 only): the same operations as apply() with the multiplies packed.  MODE is the
+    // significance mode the kernel was compiled for; `mode` can still be 0 at run time (noise == 0).
+    template <int MODE>
     __device__ __forceinline__ u64 apply2(u64 w2, u64 power2) const {
         float p0, p1, w0, w1;
         up2(power2, p0, p1);
         p0 = (p0 <= 0.f) ? 1e-15f : p0;
         p1 = (p1 <= 0.f) ? 1e-15f : p1;
         const u64 g2 = mul2(pk2((float)weight, (float)weight), pk2(rsqrt_fast(p0), rsqrt_fast(p1)));
-        if (mode == 1) {
+        if (MODE == 1 && mode == 1) {
             up2(w2, w0, w1);
             w2 = mul2(w2, pk2(erff(fabsf(w0 * (float)inv_thr)), erff(fabsf(w1 * (float)inv_thr))));
-        } else if (mode == 2) {
+        } else if (MODE == 2 && mode == 2) {
             up2(w2, w0, w1);
             w2 = pk2((fabsf(w0) > (float)thr_cmp) ? w0 : 0.f, (fabsf(w1) > (float)thr_cmp) ? w1 : 0.f);
         }

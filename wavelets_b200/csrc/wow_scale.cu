@@ -194,25 +194,134 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// fp32, d % 4 == 0 or d == 2: the same kernel on PACKED pixel pairs (FFMA2 / FMUL2 / FADD2).  The scalar kernel is
-// bound by instruction issue, not by HBM (37 M warp instructions per 4096^2 plane, 57 % issue-active, DRAM 30 %); with
-// every tap of a pixel pair being an aligned pair again, each 16-byte vector is carried as two 64-bit register pairs
-// from LDS.128 to STG.128 and every filter FMA, the subtraction, the square and the epilogue multiplies issue once
-// per two pixels.  Operation order and roundings are those of the scalar kernel: the planes are bit-identical.
+// fp32 fast path: the same pipeline, LEAN.  ncu on the kernel above (4096^2, scale 3): 37-47 M warp instructions per
+// plane of which only ~110 of 580 per warp-step are floating point -- the rest is ring-index arithmetic, tap offsets
+// rematerialised under register pressure, loop conditionals, a 64-bit modulo in the loader (warp 0 becomes the
+// straggler every step, 32 polls of the row barrier per step in every other warp) and barrier polling; TMA never
+// waits.  This version removes the overhead instead of the arithmetic:
+//   * the step loop is unrolled by 8 (= the input ring; the w / w^2 rings divide it) and ring slots have a fixed
+//     16 KiB stride, so every shared-memory access is [per-thread register + immediate] -- no index arithmetic;
+//   * pixel pairs are carried as 64-bit register pairs (FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issue
+//     slot, same roundings as the scalar instructions) from LDS.128 to STG.128;
+//   * the loader walks the reflected row index incrementally (no division);
+//   * output pointers are per-thread and advance by one add per row; the second column vector is +8 KiB.
+// Operation order and roundings are those of wow_rows_kernel: the planes are bit-identical.
 // ---------------------------------------------------------------------------------------------------------------
-template <int TAPS, int DMODE, bool HINTS>
-__global__ void __launch_bounds__(512, 1) wow_rows_packed_kernel(const ScaleParams p) {
-    using T = float;
-    constexpr int V = 4, NG = 2;
+static constexpr uint32_t kLeanRB = 16384;  // bytes per ring slot (4096 fp32 columns)
+
+template <int OFF> __device__ __forceinline__ P4 lds_p4_imm(uint32_t a) {
+    P4 r;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+%3];" : "=l"(r.lo), "=l"(r.hi) : "r"(a), "n"(OFF));
+    return r;
+}
+template <int OFF> __device__ __forceinline__ void sts_p4_imm(uint32_t a, const P4 &v) {
+    asm volatile("st.shared.v2.b64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "l"(v.lo), "l"(v.hi) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void mbar_wait_imm(uint32_t bar0, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WB_LWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0+%1], %2, %3;\n"
+        "@p bra WB_LDONE_%=;\n"
+        "bra WB_LWAIT_%=;\n"
+        "WB_LDONE_%=:\n"
+        "}\n" ::"r"(bar0), "n"(OFF), "r"(parity), "r"(kMbarSuspendHintNs)
+        : "memory");
+}
+template <int OFF> __device__ __forceinline__ void mbar_arrive_imm(uint32_t bar0) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(bar0), "n"(OFF) : "memory");
+}
+
+// Row pass of one 16-byte vector from ring slot offset OFF; a[k] are the per-thread tap addresses in slot 0.
+// SQUARE filters the squares of the staged values (the local power reads the raw w_s rows).  MIRROR (warp-uniform
+// variant for warps that own border columns): a reflected tap is the mirrored vector read backwards -- a per-thread
+// select, no branch.
+template <int TAPS, int DMODE, int OFF, bool SQUARE, bool MIRROR>
+__device__ __forceinline__ P4 lean_row_pass(const uint32_t (&a)[PlanSize<TAPS, DMODE>::NV], unsigned rev,
+                                            const PackedTaps<TAPS> &H) {
     constexpr int C = TAPS / 2;
     constexpr int NV = PlanSize<TAPS, DMODE>::NV;
+    P4 t[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        t[k] = lds_p4_imm<OFF>(a[k]);
+        if constexpr (MIRROR) {
+            const bool m = (rev >> k) & 1u;
+            const P4 u = reverse_p4(t[k]);
+            t[k].lo = m ? u.lo : t[k].lo;
+            t[k].hi = m ? u.hi : t[k].hi;
+        }
+        if constexpr (SQUARE) {
+            t[k].lo = mul2(t[k].lo, t[k].lo);
+            t[k].hi = mul2(t[k].hi, t[k].hi);
+        }
+    }
+    P4 acc;
+    if constexpr (DMODE == 0) {
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            acc.lo = (k == 0) ? mul2(H.h[0], t[k].lo) : fma2(H.h[k], t[k].lo, acc.lo);
+            acc.hi = (k == 0) ? mul2(H.h[0], t[k].hi) : fma2(H.h[k], t[k].hi, acc.hi);
+        }
+    } else if constexpr (DMODE == 2) {
+        // d == 2: previous, current, next vector as six pixel pairs; every tap of a pair is again an aligned pair
+        const u64 win[6] = {t[0].lo, t[0].hi, t[1].lo, t[1].hi, t[2].lo, t[2].hi};
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            const int i = 2 + (k - C);
+            acc.lo = (k == 0) ? mul2(H.h[0], win[i]) : fma2(H.h[k], win[i], acc.lo);
+            acc.hi = (k == 0) ? mul2(H.h[0], win[i + 1]) : fma2(H.h[k], win[i + 1], acc.hi);
+        }
+    } else {
+        // d == 1: taps of a pixel pair straddle register pairs -> scalar FMAs on the 12-element window
+        float win[12];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            up2(t[k].lo, win[4 * k], win[4 * k + 1]);
+            up2(t[k].hi, win[4 * k + 2], win[4 * k + 3]);
+        }
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+            for (int k = 0; k < TAPS; ++k) {
+                const float v = win[4 + e + (k - C)];
+                o[e] = (k == 0) ? Taps<float, TAPS>::h(0) * v : fmaf(Taps<float, TAPS>::h(k), v, o[e]);
+            }
+        }
+        acc.lo = pk2(o[0], o[1]);
+        acc.hi = pk2(o[2], o[3]);
+    }
+    return acc;
+}
+
+template <int I> struct IC { static constexpr int value = I; };
+
+// A value ptxas may not rematerialise: under register pressure it otherwise recomputes the reflected tap offsets
+// from threadIdx inside the step loop (60 integer instructions per step) instead of holding them.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
+// MODE: significance compiled into the epilogue (0 none, 1 soft, 2 hard); the step loop is small enough to stay in
+// the instruction cache only without the inlined erff of the modes that are not used.
+template <int TAPS, int DMODE, bool HINTS, int MODE>
+__global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams p) {
+    using T = float;
+    constexpr int V = 4, NG = 2, NT = 512;
+    constexpr int C = TAPS / 2;
+    constexpr int NV = PlanSize<TAPS, DMODE>::NV;
+    constexpr int RB = (int)kLeanRB;
+    constexpr int W_OFF = kInRing * RB;  // the w ring follows the input ring
+    static_assert(kInRing == 8 && kWRing == 4, "the step loop is unrolled by the w ring; the input ring is twice that");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t RB = (uint32_t)p.row_stride * (uint32_t)sizeof(T);
     const uint32_t in_base = smem_u32(smem_raw);
-    const uint32_t w_base = in_base + (uint32_t)kInRing * RB;
-    const uint32_t w2_base = w_base + (uint32_t)kWRing * RB;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(kInRing + kWRing + kW2Ring) * RB);
-    uint64_t *wbar = full + kInRing;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(kInRing + kWRing) * RB);
+    uint64_t *wbar = full + kInRing;  // "raw w row complete" barriers (one per w slot), one arrival per warp
+    const uint32_t full0 = smem_u32(full), wbar0 = smem_u32(wbar);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -226,25 +335,36 @@ __global__ void __launch_bounds__(512, 1) wow_rows_packed_kernel(const ScalePara
     const int i0 = g * p.seg;
     const int n_out = min(p.seg, n_chain - i0);
     if (n_out <= 0) return;
-    const int n_load = n_out + 4 * C;
+    const int n_load = n_out + 4 * C;  // input rows i0-2C .. i0+n_out+2C-1 of the chain (virtual rows are reflected)
     const uint32_t row_bytes = (uint32_t)p.W * (uint32_t)sizeof(T);
     const T *src = reinterpret_cast<const T *>(p.in) + (long long)frame * p.in_bstride;
-    const long long y_first = (long long)r + (long long)(i0 - 2 * C) * p.d;
 
+    // loader state (thread 0): position of the next row in the 2H-periodic symmetric extension, walked incrementally
     const uint64_t pol_in = policy_evict_first();
     const uint64_t pol_keep = policy_evict_last();
     int next_load = 0;
+    const int period = 2 * p.H;
+    const int d_mod = p.d % period;
+    int m_pos = 0;
+    auto issue_load = [&]() {
+        const int y = m_pos < p.H ? m_pos : period - 1 - m_pos;
+        const int sl = next_load & (kInRing - 1);
+        mbar_arrive_expect_tx(&full[sl], row_bytes);
+        if (HINTS) tma_load_1d_hint(smem_raw + (size_t)sl * RB, src + (long long)y * p.in_pitch, row_bytes, &full[sl], pol_in);
+        else tma_load_1d(smem_raw + (size_t)sl * RB, src + (long long)y * p.in_pitch, row_bytes, &full[sl]);
+        ++next_load;
+        m_pos += d_mod;
+        if (m_pos >= period) m_pos -= period;
+    };
     if (tid == 0) {
         for (int s = 0; s < kInRing; ++s) mbar_init(&full[s], 1);
-        for (int s = 0; s < kW2Ring; ++s) mbar_init(&wbar[s], blockDim.x >> 5);
+        for (int s = 0; s < kWRing; ++s) mbar_init(&wbar[s], NT >> 5);
         fence_mbar_init();
+        long long m0 = ((long long)r + (long long)(i0 - 2 * C) * p.d) % period;
+        if (m0 < 0) m0 += period;
+        m_pos = (int)m0;
         const int n0 = min(kInRing, n_load);
-        for (; next_load < n0; ++next_load) {
-            const long long y = reflect_any(y_first + (long long)next_load * p.d, p.H);
-            mbar_arrive_expect_tx(&full[next_load], row_bytes);
-            if (HINTS) tma_load_1d_hint(smem_raw + (size_t)next_load * RB, src + y * p.in_pitch, row_bytes, &full[next_load], pol_in);
-            else tma_load_1d(smem_raw + (size_t)next_load * RB, src + y * p.in_pitch, row_bytes, &full[next_load]);
-        }
+        while (next_load < n0) issue_load();
     }
     __syncthreads();
 
@@ -252,21 +372,36 @@ __global__ void __launch_bounds__(512, 1) wow_rows_packed_kernel(const ScalePara
     epi.init(p, frame);
     const PackedTaps<TAPS> H;
 
-    uint32_t xb[NG];
-    int xg[NG];
+    // per-thread addresses inside ring slot 0: own vector and taps, for both column groups
+    uint32_t own[NG], tap[NG][NV];
+    unsigned rev[NG];
     bool act[NG];
-    BytePlan<NV> plan[NG];
+    int xg0 = 0;
 #pragma unroll
     for (int q = 0; q < NG; ++q) {
-        xg[q] = (q * (int)blockDim.x + tid) * V;
-        act[q] = xg[q] < p.W;
-        if (!act[q]) xg[q] = 0;
-        xb[q] = (uint32_t)xg[q] * (uint32_t)sizeof(T);
-        const TapPlan<NV> tp = make_tap_plan<V, NV>(xg[q], DMODE == 0 ? p.d : V, p.W, 0);
+        int xg = (q * NT + tid) * V;
+        act[q] = xg < p.W;
+        // idle threads shadow a vector in the middle of the row (interior unless the dilation is huge); only their
+        // stores are masked
+        if (!act[q]) xg = (p.W / 2) & ~(V - 1);
+        if (q == 0) xg0 = xg;
+        own[q] = opaque_u32(in_base + (uint32_t)xg * (uint32_t)sizeof(T));
+        const TapPlan<NV> tp = make_tap_plan<V, NV>(xg, DMODE == 0 ? p.d : V, p.W, 0);
 #pragma unroll
-        for (int k = 0; k < NV; ++k) plan[q].off[k] = (uint32_t)tp.off[k] * (uint32_t)sizeof(T);
-        plan[q].rev = tp.rev;
+        for (int k = 0; k < NV; ++k) tap[q][k] = in_base + (uint32_t)tp.off[k] * (uint32_t)sizeof(T);
+        rev[q] = tp.rev;
     }
+    const bool mirror_warp = __any_sync(0xffffffffu, (rev[0] | rev[1]) != 0);
+    if (mirror_warp) {
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) tap[q][k] = opaque_u32(tap[q][k]);
+            rev[q] = opaque_u32(rev[q]);
+        }
+    }
+    // interior warps: tap k of a vector is its own address + (k - NV/2) * step bytes (nothing to hold per tap)
+    const uint32_t tap_step = (uint32_t)(DMODE == 0 ? p.d : V) * (uint32_t)sizeof(T);
 
     u64 SA[NG][2][TAPS - 1], SB[NG][2][TAPS - 1];  // running column sums, one pixel pair per entry
 #pragma unroll
@@ -276,84 +411,105 @@ __global__ void __launch_bounds__(512, 1) wow_rows_packed_kernel(const ScalePara
 #pragma unroll
             for (int t = 0; t < TAPS - 1; ++t) { SA[q][e][t] = 0ull; SB[q][e][t] = 0ull; }
 
+    // per-thread output pointers (column group 0; group 1 is NT * V elements further when active)
     T *c_ptr = reinterpret_cast<T *>(p.out_c) + (long long)frame * p.c_bstride +
-               ((long long)r + (long long)(i0 - C) * p.d) * p.c_pitch;
+               ((long long)r + (long long)(i0 - C) * p.d) * p.c_pitch + xg0;
     T *o_ptr = reinterpret_cast<T *>(p.out_w) + (long long)frame * p.w_bstride +
-               ((long long)r + (long long)i0 * p.d) * p.w_pitch;
+               ((long long)r + (long long)i0 * p.d) * p.w_pitch + xg0;
     const long long c_step = (long long)p.d * p.c_pitch, o_step = (long long)p.d * p.w_pitch;
+    const int j_store_end = 3 * C + n_out;
 
-    // same step structure as wow_rows_kernel: A (input row j), B (power of the w^2 row of step j-1), C (c / w / w^2)
-    for (int j = 0; j <= n_load; ++j) {
-        P4 cv[NG];
+    // Step j = 4 u + I (input slot = I + 4 (u & 1): `half` is that slot's byte offset, 0 or 4 RB):
+    //   A  input row j lands -> row pass -> column feed -> c row j-C: store (rows of the segment), w = raw - c into the
+    //      w ring, arrive on that row's barrier;
+    //   B  wait until every warp has written w row j-1-2C -> row pass over its squares -> column feed -> P of row
+    //      j-1-3C, epilogue with this thread's own raw w of that row -> streaming store.
+    // One drain step (j == n_load) runs part B only.  A slot of the w ring is rewritten 4 steps after it was filled;
+    // its cross-thread readers finished 3 steps earlier (no warp is more than one step behind a passed barrier).
+    auto step = [&](auto ic, auto mirror, const int j, const uint32_t half, const uint32_t half_c, const uint32_t par_in) {
+        constexpr int I = decltype(ic)::value;
+        constexpr bool MIRROR = decltype(mirror)::value != 0;
+        if (j > n_load) return;
         if (j < n_load) {
-            mbar_wait(&full[j & (kInRing - 1)], (uint32_t)(j / kInRing) & 1u);
-            const uint32_t row = in_base + (uint32_t)(j & (kInRing - 1)) * RB;
+            mbar_wait_imm<8 * I>(full0 + (half >> 11), par_in);  // barrier of slot I + 4 (u & 1): 8 bytes per slot
+            P4 cv[NG];
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
-                const P4 v = row_pass_p<TAPS, DMODE>(row, plan[q], H);
+                uint32_t a[NV];
+#pragma unroll
+                for (int k = 0; k < NV; ++k)
+                    a[k] = (MIRROR ? tap[q][k] : own[q] + (uint32_t)(k - NV / 2) * tap_step) + half;
+                const P4 v = lean_row_pass<TAPS, DMODE, I * RB, false, MIRROR>(a, rev[q], H);
                 cv[q].lo = col_feed_p<TAPS>(SA[q][0], v.lo, H);
                 cv[q].hi = col_feed_p<TAPS>(SA[q][1], v.hi, H);
             }
+            if (j >= 2 * C) {
+                // raw centre row j-C: slot (I - C) mod 4 of the half that row was loaded into
+                constexpr int SC = (I - C + 4) & 3;
+                constexpr bool other_half = I < C;
+                constexpr int SW = (I - 2 * C + 8) & (kWRing - 1);  // w row j-2C
+                const bool store_c = (j >= 3 * C) && (j < j_store_end);
+#pragma unroll
+                for (int q = 0; q < NG; ++q) {
+                    if (store_c && act[q]) {
+                        if (HINTS) stg_p4_hint(c_ptr + q * (NT * V), cv[q], pol_keep);
+                        else stg_p4(c_ptr + q * (NT * V), cv[q]);
+                    }
+                    P4 raw = lds_p4_imm<SC * RB>(own[q] + (other_half ? half_c : half));
+                    raw.lo = sub2(raw.lo, cv[q].lo);
+                    raw.hi = sub2(raw.hi, cv[q].hi);
+                    if (act[q]) sts_p4_imm<W_OFF + SW * RB>(own[q], raw);
+                }
+                c_ptr += c_step;
+                __syncwarp();
+                if (lane == 0) mbar_arrive_imm<8 * SW>(wbar0);
+            }
         }
         if (j > 2 * C) {
-            const int mb = j - 1 - 2 * C;
-            mbar_wait(&wbar[mb & (kW2Ring - 1)], (uint32_t)(mb / kW2Ring) & 1u);
+            constexpr int SP = (I - 1 - 2 * C + 16) & (kWRing - 1);  // w row j-1-2C (all threads' columns)
+            mbar_wait_imm<8 * SP>(wbar0, ((uint32_t)(j - 1 - 2 * C) >> 2) & 1u);
             if (tid == 0) {
-                while (next_load < n_load && next_load - kInRing <= j - 1 - C) {
-                    const int sl = next_load & (kInRing - 1);
-                    const long long y = reflect_any(y_first + (long long)next_load * p.d, p.H);
-                    mbar_arrive_expect_tx(&full[sl], row_bytes);
-                    if (HINTS) tma_load_1d_hint(smem_raw + (size_t)sl * RB, src + y * p.in_pitch, row_bytes, &full[sl], pol_in);
-                    else tma_load_1d(smem_raw + (size_t)sl * RB, src + y * p.in_pitch, row_bytes, &full[sl]);
-                    ++next_load;
-                }
+                // every warp is past part A of step j-1: input rows <= j-1-C are free
+                while (next_load < n_load && next_load - kInRing <= j - 1 - C) issue_load();
             }
-            const uint32_t row = w2_base + (uint32_t)(mb & (kW2Ring - 1)) * RB;
             P4 pw[NG];
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
-                const P4 v = row_pass_p<TAPS, DMODE>(row, plan[q], H);
+                uint32_t a[NV];
+#pragma unroll
+                for (int k = 0; k < NV; ++k) a[k] = MIRROR ? tap[q][k] : own[q] + (uint32_t)(k - NV / 2) * tap_step;
+                const P4 v = lean_row_pass<TAPS, DMODE, W_OFF + SP * RB, true, MIRROR>(a, rev[q], H);
                 pw[q].lo = col_feed_p<TAPS>(SB[q][0], v.lo, H);
                 pw[q].hi = col_feed_p<TAPS>(SB[q][1], v.hi, H);
             }
             if (j > 4 * C) {
-                const uint32_t wrow = w_base + (uint32_t)((j - 1 - 3 * C) & (kWRing - 1)) * RB;
+                constexpr int SE = (I - 1 - 3 * C + 16) & (kWRing - 1);  // own raw w of the completed P row
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
-                    P4 raw = lds_p4(wrow + xb[q]);
-                    raw.lo = epi.apply2(raw.lo, pw[q].lo);
-                    raw.hi = epi.apply2(raw.hi, pw[q].hi);
-                    if (act[q]) stg_p4_cs(o_ptr + xg[q], raw);
+                    P4 raw = lds_p4_imm<W_OFF + SE * RB>(own[q]);
+                    raw.lo = epi.template apply2<MODE>(raw.lo, pw[q].lo);
+                    raw.hi = epi.template apply2<MODE>(raw.hi, pw[q].hi);
+                    if (act[q]) stg_p4_cs(o_ptr + q * (NT * V), raw);
                 }
                 o_ptr += o_step;
             }
         }
-        if (j >= 2 * C && j < n_load) {
-            const int mc = j - 2 * C;
-            const bool store_c = (mc >= C) && (mc - C < n_out);
-            const uint32_t crow = in_base + (uint32_t)((j - C) & (kInRing - 1)) * RB;
-            const uint32_t wrow = w_base + (uint32_t)(mc & (kWRing - 1)) * RB;
-            const uint32_t w2row = w2_base + (uint32_t)(mc & (kW2Ring - 1)) * RB;
-#pragma unroll
-            for (int q = 0; q < NG; ++q) {
-                if (store_c && act[q]) {
-                    if (HINTS) stg_p4_hint(c_ptr + xg[q], cv[q], pol_keep);
-                    else stg_p4(c_ptr + xg[q], cv[q]);
-                }
-                P4 raw = lds_p4(crow + xb[q]);
-                raw.lo = sub2(raw.lo, cv[q].lo);
-                raw.hi = sub2(raw.hi, cv[q].hi);
-                const P4 sq{mul2(raw.lo, raw.lo), mul2(raw.hi, raw.hi)};
-                if (act[q]) {
-                    sts_p4(wrow + xb[q], raw);
-                    sts_p4(w2row + xb[q], sq);
-                }
-            }
-            c_ptr += c_step;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&wbar[mc & (kW2Ring - 1)]);
+    };
+    auto run = [&](auto mirror) {
+#pragma unroll 1
+        for (int jb = 0; jb <= n_load; jb += 4) {
+            const uint32_t half = (jb & 4) ? 4u * RB : 0u;   // input slots 4..7 on odd iterations
+            const uint32_t half_c = half ^ (4u * RB);        // the half loaded one iteration earlier
+            const uint32_t par_in = (uint32_t)(jb >> 3) & 1u;
+            step(IC<0>{}, mirror, jb + 0, half, half_c, par_in);
+            step(IC<1>{}, mirror, jb + 1, half, half_c, par_in);
+            step(IC<2>{}, mirror, jb + 2, half, half_c, par_in);
+            step(IC<3>{}, mirror, jb + 3, half, half_c, par_in);
         }
-    }
+    };
+    // warps that own no border column (the vast majority at shallow scales) run the variant without the selects
+    if (mirror_warp) run(IC<1>{});
+    else run(IC<0>{});
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -399,38 +555,45 @@ static bool plan_wow(ScaleParams &p, int taps, int esize, int batch, WowGeom *ge
     return true;
 }
 
-// WB_WOW_PACKED=0 in the environment selects the scalar fp32 kernel (A/B measurements, bit-identity tests).
+// WB_WOW_LEAN=0 in the environment selects the generic kernel for fp32 too (A/B measurements, bit-identity tests).
 static bool wow_packed_enabled() {
     static int v = -1;
     if (v < 0) {
-        const char *e = getenv("WB_WOW_PACKED");
+        const char *e = getenv("WB_WOW_LEAN");
         v = (e && e[0] == '0') ? 0 : 1;
     }
     return v != 0;
 }
 
 template <typename T, int TAPS, int DMODE, bool HINTS>
-static auto wow_kernel_for(bool packed) -> void (*)(const ScaleParams) {
-    if constexpr (sizeof(T) == 4 && (DMODE == 0 || DMODE == 2)) {
-        if (packed) return wow_rows_packed_kernel<TAPS, DMODE, HINTS>;
+static auto wow_kernel_for(bool packed, int sig_mode) -> void (*)(const ScaleParams) {
+    if constexpr (sizeof(T) == 4) {
+        if (packed)
+            return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 0>
+                                 : (sig_mode == 1 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 1>
+                                                  : wow_rows_lean_kernel<TAPS, DMODE, HINTS, 2>);
     }
     return wow_rows_kernel<T, TAPS, DMODE, 2, HINTS>;
 }
 
 template <typename T, int TAPS, int DMODE, bool HINTS>
 static int launch_wow_h(const ScaleParams &p, int batch, const WowGeom &geo, cudaStream_t st) {
-    const bool packed = wow_packed_enabled();
-    auto kern = wow_kernel_for<T, TAPS, DMODE, HINTS>(packed);
-    static bool configured[2][64] = {};
+    // the lean kernel always runs 512 threads x 2 vectors on 16 KiB ring slots: use it when the row needs them
+    const bool packed = sizeof(T) == 4 && p.W > 2048 && wow_packed_enabled();
+    auto kern = wow_kernel_for<T, TAPS, DMODE, HINTS>(packed, p.sig_mode);
+    const int nt = packed ? 512 : geo.nt;
+    const size_t smem = packed ? (size_t)(kInRing + kWRing) * kLeanRB + 8 * (size_t)(kInRing + kWRing) : geo.smem;
+    static bool configured[4][64] = {};  // generic, lean x 3 significance modes; per device
+    const int kidx = packed ? 1 + p.sig_mode : 0;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[packed][dev]) {
+    if (dev < 0 || dev >= 64 || !configured[kidx][dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
         if (e != cudaSuccess) return (int)e;
-        if (dev >= 0 && dev < 64) configured[packed][dev] = true;
+        if (dev >= 0 && dev < 64) configured[kidx][dev] = true;
     }
     dim3 grid((unsigned)((long long)p.d * p.n_seg), (unsigned)batch);
-    kern<<<grid, geo.nt, geo.smem, st>>>(p);
+    kern<<<grid, nt, smem, st>>>(p);
     return launch_status();
 }
 
