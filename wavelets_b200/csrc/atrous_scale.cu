@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)p.slots * p.row_stride * sizeof(T));
     uint64_t *empty = full + p.slots;
 
+    pdl_launch_dependents();
     const int nt = blockDim.x - 32;  // consumer threads; the last warp is the TMA producer
     const int nwc = nt >> 5;
     const int tid = threadIdx.x;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
         fence_mbar_init();
     }
     __syncthreads();
+    pdl_wait();  // everything below touches global memory written or read by the previous launch
 
     if (warp == nwc) {
         // ---------------- producer warp: one lane streams the chain rows into the ring ----------------
@@ -180,6 +182,171 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
     (void)ring_end;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K1, fp32 whole-row strips: the same pipeline, LEAN (see wow_scale.cu for the measurements behind the recipe).  The
+// kernel above spends ~330 warp instructions per warp-step of which ~100 are floating point (ncu: 22.5 M warp
+// instructions per 4096^2 plane, 67 % issue-active).  Here the consumer loop is unrolled by the 8-slot ring, ring
+// slots have a fixed 16 KiB stride (every LDS is [register + immediate]), pixel pairs are carried as 64-bit
+// register pairs (FFMA2 / FMUL2 / FADD2, same roundings as the scalar instructions) and the output pointers are
+// per-thread and advance by one add per row.  Same operation order as atrous_rows_kernel: bit-identical planes.
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int kLeanSlots = 8;
+
+template <int TAPS, int DMODE, bool HINTS>
+__global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams p) {
+    using T = float;
+    constexpr int V = 4, NG = 2;
+    constexpr int C = TAPS / 2;
+    constexpr int NV = PlanSize<TAPS, DMODE>::NV;
+    constexpr int RB = (int)kLeanRB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t in_base = smem_u32(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kLeanSlots * RB);
+    uint64_t *empty = full + kLeanSlots;
+    const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+
+    pdl_launch_dependents();
+    const int nt = blockDim.x - 32;  // consumer threads; the last warp is the TMA producer
+    const int nwc = nt >> 5;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    int bx = blockIdx.x;
+    const int r = bx % p.d;
+    const int g = bx / p.d;
+    const int frame = blockIdx.y;
+
+    const int n_chain = (r < p.H) ? (p.H - r + p.d - 1) / p.d : 0;
+    const int i0 = g * p.seg;
+    const int n_out = min(p.seg, n_chain - i0);
+    if (n_out <= 0) return;
+    const int n_load = n_out + 2 * C;
+    const uint32_t row_bytes = (uint32_t)p.W * (uint32_t)sizeof(T);
+
+    if (tid == 0) {
+        for (int s = 0; s < kLeanSlots; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nwc);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_wait();  // everything below touches global memory written or read by the previous launch
+
+    if (warp == nwc) {
+        // ---------------- producer warp: one lane streams the chain rows into the ring ----------------
+        if (lane == 0) {
+            const long long foff = (long long)frame * p.in_bstride;
+            const uint64_t pol_in = policy_evict_first();  // c_s is dead once this launch has read it
+            for (int j = 0; j < n_load; ++j) {
+                const int slot = j & (kLeanSlots - 1);
+                if (j >= kLeanSlots) mbar_wait(&empty[slot], (uint32_t)((j >> 3) - 1) & 1u);
+                // the row may live in a neighbour's band buffer (peer-window mode): same bulk copy, over NVLink
+                const T *src = input_row<T>(p, reflect_any(p.gwy0 + r + (long long)(i0 - C + j) * p.d, p.Hg)) + foff;
+                mbar_arrive_expect_tx(&full[slot], row_bytes);
+                if (HINTS) tma_load_1d_hint(smem_raw + (size_t)slot * RB, src, row_bytes, &full[slot], pol_in);
+                else tma_load_1d(smem_raw + (size_t)slot * RB, src, row_bytes, &full[slot]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps ----------------
+    const PackedTaps<TAPS> H;
+    const uint64_t pol_keep = policy_evict_last();  // c_{s+1}: the next scale reads it back
+
+    uint32_t own[NG], tap[NG][NV];
+    unsigned rev[NG];
+    bool act[NG];
+    int xg0 = 0;
+#pragma unroll
+    for (int q = 0; q < NG; ++q) {
+        int xg = (q * nt + tid) * V;
+        act[q] = xg < p.W;
+        if (!act[q]) xg = (p.W / 2) & ~(V - 1);  // idle threads shadow an interior vector; only their stores are masked
+        if (q == 0) xg0 = xg;
+        own[q] = opaque_u32(in_base + (uint32_t)xg * (uint32_t)sizeof(T));
+        const TapPlan<NV> tp = make_tap_plan<V, NV>(xg, DMODE == 0 ? p.d : V, p.W, 0);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) tap[q][k] = opaque_u32(in_base + (uint32_t)tp.off[k] * (uint32_t)sizeof(T));
+        rev[q] = opaque_u32(tp.rev);
+    }
+    const bool mirror_warp = __any_sync(0xffffffffu, (rev[0] | rev[1]) != 0);
+    const long long q_off = (long long)nt * V;  // column group 1 is nt vectors further (when active)
+
+    u64 S[NG][2][TAPS - 1];  // running column sums, one pixel pair per entry
+#pragma unroll
+    for (int q = 0; q < NG; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int t = 0; t < TAPS - 1; ++t) S[q][e][t] = 0ull;
+
+    T *c_ptr = reinterpret_cast<T *>(p.out_c);
+    T *w_ptr = reinterpret_cast<T *>(p.out_w);
+    const long long orow = (long long)r + (long long)i0 * p.d;  // first output row of this block
+    if (c_ptr) c_ptr += (long long)frame * p.c_bstride + (orow + p.row_off_c) * p.c_pitch + xg0;
+    if (w_ptr) w_ptr += (long long)frame * p.w_bstride + (orow + p.row_off_w) * p.w_pitch + xg0;
+    const long long c_step = (long long)p.d * p.c_pitch, w_step = (long long)p.d * p.w_pitch;
+    const bool has_c = c_ptr != nullptr, has_w = w_ptr != nullptr;
+
+    // Step j = 8 u + I: input row j lands -> row pass -> column feed -> c row j-C; w = raw centre row - c; release the
+    // centre row's slot.
+    auto step = [&](auto ic, auto mirror, const int j, const uint32_t par) {
+        constexpr int I = decltype(ic)::value;
+        constexpr bool MIRROR = decltype(mirror)::value != 0;
+        if (j >= n_load) return;
+        mbar_wait_imm<8 * I>(full0, par);
+        P4 cv[NG];
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+            const P4 v = lean_row_pass<TAPS, DMODE, I * RB, false, MIRROR>(tap[q], rev[q], H);
+            cv[q].lo = col_feed_p<TAPS>(S[q][0], v.lo, H);
+            cv[q].hi = col_feed_p<TAPS>(S[q][1], v.hi, H);
+        }
+        constexpr int SC = (I - C + 8) & (kLeanSlots - 1);  // raw centre row j-C
+        if (j >= 2 * C) {
+#pragma unroll
+            for (int q = 0; q < NG; ++q) {
+                if (has_c && act[q]) {
+                    if (HINTS) stg_p4_hint(c_ptr + q * q_off, cv[q], pol_keep);
+                    else stg_p4(c_ptr + q * q_off, cv[q]);
+                }
+                if (has_w) {
+                    P4 raw = lds_p4_imm<SC * RB>(own[q]);
+                    raw.lo = sub2(raw.lo, cv[q].lo);
+                    raw.hi = sub2(raw.hi, cv[q].hi);
+                    if (act[q]) stg_p4_cs(w_ptr + q * q_off, raw);
+                }
+            }
+            if (has_c) c_ptr += c_step;
+            if (has_w) w_ptr += w_step;
+        }
+        if (j >= C) {
+            // the raw row j-C is not needed any more: hand its slot back to the producer
+            __syncwarp();
+            if (lane == 0) mbar_arrive_imm<8 * SC>(empty0);
+        }
+    };
+    auto run = [&](auto mirror) {
+#pragma unroll 1
+        for (int jb = 0; jb < n_load; jb += 8) {
+            const uint32_t par = (uint32_t)(jb >> 3) & 1u;
+            step(IC<0>{}, mirror, jb + 0, par);
+            step(IC<1>{}, mirror, jb + 1, par);
+            step(IC<2>{}, mirror, jb + 2, par);
+            step(IC<3>{}, mirror, jb + 3, par);
+            step(IC<4>{}, mirror, jb + 4, par);
+            step(IC<5>{}, mirror, jb + 5, par);
+            step(IC<6>{}, mirror, jb + 6, par);
+            step(IC<7>{}, mirror, jb + 7, par);
+        }
+    };
+    if (mirror_warp) run(IC<1>{});
+    else run(IC<0>{});
+}
+
 // Generic path: one thread per output pixel, full modular reflection, any shape / alignment.
 template <typename T, int TAPS, int OP>
 __global__ void __launch_bounds__(256) atrous_generic_kernel(const ScaleParams p) {
@@ -239,8 +406,33 @@ static int launch_rows(const ScaleParams &p, int batch, int nt, cudaStream_t st)
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
-    kern<<<grid, nt + 32, smem, st>>>(p);
-    return launch_status();
+    return launch_pdl<ScaleParams>(kern, grid, dim3((unsigned)(nt + 32)), smem, st, p);
+}
+
+// WB_K1_LEAN=0 in the environment selects the generic row-pipeline kernel for fp32 too (A/B measurements).
+static bool k1_lean_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("WB_K1_LEAN");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+template <int TAPS, int DMODE, bool HINTS>
+static int launch_rows_lean(const ScaleParams &p, int batch, int nt, cudaStream_t st) {
+    auto kern = atrous_rows_lean_kernel<TAPS, DMODE, HINTS>;
+    const size_t smem = (size_t)kLeanSlots * kLeanRB + 16 * (size_t)kLeanSlots;
+    static bool configured[64] = {};  // per instantiation, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    dim3 grid((unsigned)((long long)p.d * p.n_seg), (unsigned)batch);
+    return launch_pdl<ScaleParams>(kern, grid, dim3((unsigned)(nt + 32)), smem, st, p);
 }
 
 template <typename T, int TAPS, int OP>
@@ -249,6 +441,18 @@ static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
     K1Config cfg;
     if (fast_path_ok(p, TAPS, (int)sizeof(T)) && plan_fast(p, TAPS, (int)sizeof(T), batch, scale, &cfg)) {
         const int dmode = (p.d % V == 0) ? 0 : p.d;
+        if constexpr (sizeof(T) == 4 && OP == OP_TRANSFORM) {
+            // whole-row strips with two vectors per thread and the default ring: the lean kernel
+            if (p.n_strips == 1 && cfg.ng == 2 && p.W > 1024 && cfg.slots == kLeanSlots && k1_lean_enabled() &&
+                !(scale < 32 && g_override_set[scale])) {
+#define WB_LEAN(DM) (p.l2_hints ? launch_rows_lean<TAPS, DM, true>(p, batch, cfg.nt, st) \
+                                : launch_rows_lean<TAPS, DM, false>(p, batch, cfg.nt, st))
+                if (dmode == 0) return WB_LEAN(0);
+                if (dmode == 1) return WB_LEAN(1);
+                if (dmode == 2) return WB_LEAN(2);
+#undef WB_LEAN
+            }
+        }
 #define WB_LAUNCH(DM)                                                                   \
     (cfg.ng == 1 ? launch_rows<T, TAPS, DM, 1, OP>(p, batch, cfg.nt, st)                \
                  : launch_rows<T, TAPS, DM, 2, OP>(p, batch, cfg.nt, st))

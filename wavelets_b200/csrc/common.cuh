@@ -189,6 +189,17 @@ __device__ __forceinline__ void stg_p4_hint(float *p, const P4 &v, uint64_t poli
 __device__ __forceinline__ P4 reverse_p4(const P4 &t) { return P4{swap2(t.hi), swap2(t.lo)}; }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the scale kernels of a cascade are launched back to back on one stream, each one
+// consuming what the previous one wrote.  With the stream-serialisation attribute (launch_pdl below) the blocks of
+// scale s+1 are scheduled as the blocks of scale s retire and run their prologue (barrier init, tap plans) while the
+// tail of scale s is still in flight; griddepcontrol.wait then blocks until the previous grid has completed and its
+// writes are visible.  Every global access of the kernel (reads AND writes: the ping-pong scratch is rewritten) comes
+// after the wait.  Without the launch attribute both instructions are no-ops.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------------------
 inline int dtype_size(int dtype) { return dtype == WB_F32 ? 4 : (dtype == WB_F64 ? 8 : 0); }
@@ -215,6 +226,39 @@ inline int l2_hints_enabled() {
 // Launch-time error check that does not synchronise.
 inline int launch_status() {
     cudaError_t e = cudaGetLastError();
+    return (int)e;
+}
+
+// WB_PDL=0 in the environment launches the cascade kernels without programmatic dependent launch (A/B measurements).
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("WB_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+// Launch `kern(param)` with the programmatic-stream-serialisation attribute (the kernel must call pdl_wait() before
+// its first global access).
+template <typename P>
+inline int launch_pdl(void (*kern)(const P), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const P &param) {
+    if (!pdl_enabled()) {
+        kern<<<grid, block, smem, st>>>(param);
+        return launch_status();
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, param);
     return (int)e;
 }
 

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(kInRing + kWRing + kW2Ring) * RB);
     uint64_t *wbar = full + kInRing;  // split-phase "w / w^2 row complete" barriers, one arrival per warp
 
+    pdl_launch_dependents();
     const int tid = threadIdx.x;
     const int lane = tid & 31;
 
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
     const uint64_t pol_keep = policy_evict_last();  // c_{s+1}: the next scale reads it back
     constexpr bool hints = HINTS, hints_c = HINTS;
     int next_load = 0;  // thread 0: next chain row to request
+    pdl_wait();  // everything below touches global memory written or read by the previous launch
     if (tid == 0) {
         for (int s = 0; s < kInRing; ++s) mbar_init(&full[s], 1);
         for (int s = 0; s < kW2Ring; ++s) mbar_init(&wbar[s], blockDim.x >> 5);
@@ -207,105 +209,6 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
 //   * output pointers are per-thread and advance by one add per row; the second column vector is +8 KiB.
 // Operation order and roundings are those of wow_rows_kernel: the planes are bit-identical.
 // ---------------------------------------------------------------------------------------------------------------
-static constexpr uint32_t kLeanRB = 16384;  // bytes per ring slot (4096 fp32 columns)
-
-template <int OFF> __device__ __forceinline__ P4 lds_p4_imm(uint32_t a) {
-    P4 r;
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+%3];" : "=l"(r.lo), "=l"(r.hi) : "r"(a), "n"(OFF));
-    return r;
-}
-template <int OFF> __device__ __forceinline__ void sts_p4_imm(uint32_t a, const P4 &v) {
-    asm volatile("st.shared.v2.b64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "l"(v.lo), "l"(v.hi) : "memory");
-}
-template <int OFF> __device__ __forceinline__ void mbar_wait_imm(uint32_t bar0, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WB_LWAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0+%1], %2, %3;\n"
-        "@p bra WB_LDONE_%=;\n"
-        "bra WB_LWAIT_%=;\n"
-        "WB_LDONE_%=:\n"
-        "}\n" ::"r"(bar0), "n"(OFF), "r"(parity), "r"(kMbarSuspendHintNs)
-        : "memory");
-}
-template <int OFF> __device__ __forceinline__ void mbar_arrive_imm(uint32_t bar0) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(bar0), "n"(OFF) : "memory");
-}
-
-// Row pass of one 16-byte vector from ring slot offset OFF; a[k] are the per-thread tap addresses in slot 0.
-// SQUARE filters the squares of the staged values (the local power reads the raw w_s rows).  MIRROR (warp-uniform
-// variant for warps that own border columns): a reflected tap is the mirrored vector read backwards -- a per-thread
-// select, no branch.
-template <int TAPS, int DMODE, int OFF, bool SQUARE, bool MIRROR>
-__device__ __forceinline__ P4 lean_row_pass(const uint32_t (&a)[PlanSize<TAPS, DMODE>::NV], unsigned rev,
-                                            const PackedTaps<TAPS> &H) {
-    constexpr int C = TAPS / 2;
-    constexpr int NV = PlanSize<TAPS, DMODE>::NV;
-    P4 t[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        t[k] = lds_p4_imm<OFF>(a[k]);
-        if constexpr (MIRROR) {
-            const bool m = (rev >> k) & 1u;
-            const P4 u = reverse_p4(t[k]);
-            t[k].lo = m ? u.lo : t[k].lo;
-            t[k].hi = m ? u.hi : t[k].hi;
-        }
-        if constexpr (SQUARE) {
-            t[k].lo = mul2(t[k].lo, t[k].lo);
-            t[k].hi = mul2(t[k].hi, t[k].hi);
-        }
-    }
-    P4 acc;
-    if constexpr (DMODE == 0) {
-#pragma unroll
-        for (int k = 0; k < TAPS; ++k) {
-            acc.lo = (k == 0) ? mul2(H.h[0], t[k].lo) : fma2(H.h[k], t[k].lo, acc.lo);
-            acc.hi = (k == 0) ? mul2(H.h[0], t[k].hi) : fma2(H.h[k], t[k].hi, acc.hi);
-        }
-    } else if constexpr (DMODE == 2) {
-        // d == 2: previous, current, next vector as six pixel pairs; every tap of a pair is again an aligned pair
-        const u64 win[6] = {t[0].lo, t[0].hi, t[1].lo, t[1].hi, t[2].lo, t[2].hi};
-#pragma unroll
-        for (int k = 0; k < TAPS; ++k) {
-            const int i = 2 + (k - C);
-            acc.lo = (k == 0) ? mul2(H.h[0], win[i]) : fma2(H.h[k], win[i], acc.lo);
-            acc.hi = (k == 0) ? mul2(H.h[0], win[i + 1]) : fma2(H.h[k], win[i + 1], acc.hi);
-        }
-    } else {
-        // d == 1: taps of a pixel pair straddle register pairs -> scalar FMAs on the 12-element window
-        float win[12];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            up2(t[k].lo, win[4 * k], win[4 * k + 1]);
-            up2(t[k].hi, win[4 * k + 2], win[4 * k + 3]);
-        }
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-#pragma unroll
-            for (int k = 0; k < TAPS; ++k) {
-                const float v = win[4 + e + (k - C)];
-                o[e] = (k == 0) ? Taps<float, TAPS>::h(0) * v : fmaf(Taps<float, TAPS>::h(k), v, o[e]);
-            }
-        }
-        acc.lo = pk2(o[0], o[1]);
-        acc.hi = pk2(o[2], o[3]);
-    }
-    return acc;
-}
-
-template <int I> struct IC { static constexpr int value = I; };
-
-// A value ptxas may not rematerialise: under register pressure it otherwise recomputes the reflected tap offsets
-// from threadIdx inside the step loop (60 integer instructions per step) instead of holding them.
-__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
-    return r;
-}
-
 // MODE: significance compiled into the epilogue (0 none, 1 soft, 2 hard); the step loop is small enough to stay in
 // the instruction cache only without the inlined erff of the modes that are not used.
 template <int TAPS, int DMODE, bool HINTS, int MODE>
@@ -323,6 +226,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
     uint64_t *wbar = full + kInRing;  // "raw w row complete" barriers (one per w slot), one arrival per warp
     const uint32_t full0 = smem_u32(full), wbar0 = smem_u32(wbar);
 
+    pdl_launch_dependents();
     const int tid = threadIdx.x;
     const int lane = tid & 31;
 
@@ -356,6 +260,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
         m_pos += d_mod;
         if (m_pos >= period) m_pos -= period;
     };
+    pdl_wait();  // everything below touches global memory written or read by the previous launch
     if (tid == 0) {
         for (int s = 0; s < kInRing; ++s) mbar_init(&full[s], 1);
         for (int s = 0; s < kWRing; ++s) mbar_init(&wbar[s], NT >> 5);
@@ -593,8 +498,7 @@ static int launch_wow_h(const ScaleParams &p, int batch, const WowGeom &geo, cud
         if (dev >= 0 && dev < 64) configured[kidx][dev] = true;
     }
     dim3 grid((unsigned)((long long)p.d * p.n_seg), (unsigned)batch);
-    kern<<<grid, nt, smem, st>>>(p);
-    return launch_status();
+    return launch_pdl<ScaleParams>(kern, grid, dim3((unsigned)nt), smem, st, p);
 }
 
 template <typename T, int TAPS, int DMODE>
