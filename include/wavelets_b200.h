@@ -34,6 +34,9 @@ extern "C" {
 
 enum { WB_F32 = 0, WB_F64 = 1 };
 enum { WB_TRIANGLE = 3, WB_B3SPLINE = 5 };
+/* border rule of wb_atrous_axis: half-sample symmetric (cv2.BORDER_REFLECT, every 2-D / 3-D pass of the reference) or
+ * whole-sample mirror (scipy.ndimage mode='mirror', the reference's 1-D signals) */
+enum { WB_BORDER_SYMMETRIC = 0, WB_BORDER_MIRROR = 1 };
 
 enum {
     WB_OK = 0,
@@ -206,6 +209,20 @@ int wb_denoise_plane(void *w, long long n, int batch, long long bstride, int dty
  */
 int wb_residual_rescale(void *c, long long n, int batch, long long bstride, int dtype, const double *moments,
                         double weight, void *stream);
+
+/*
+ * One dilated filter pass along ONE axis of a C-contiguous (n_outer, n_axis, n_inner) array: what the 1-D and 3-D
+ * branches of `convolution` need beyond the 2-D kernels (watroo/wavelets.py:46-69):
+ *   - 1-D signal of n samples: n_outer = 1, n_axis = n, n_inner = 1, border = WB_BORDER_MIRROR
+ *     (scipy.ndimage.convolve(arr, atrous_kernel(s), mode='mirror'), :64-69);
+ *   - depth pass of a (D, H, W) volume after wb_atrous_scale has smoothed every slice: n_outer = 1, n_axis = D,
+ *     n_inner = H*W, border = WB_BORDER_SYMMETRIC (cv2.filter2D with the (K,1) kernel on every [:, :, i] slice, :55-63).
+ *     out_c[i] = sum_k h_k in[.., R(a + (k-c) 2^scale), ..]        out_w = sub_from - out_c
+ * `sub_from` is the plane the detail coefficients refer to (c_s, watroo/wavelets.py:442); it may equal `in` (1-D) or
+ * be the unsmoothed volume (3-D).  `out_w` may be NULL (then `sub_from` is ignored), `out_c` may be NULL.
+ */
+int wb_atrous_axis(const void *in, const void *sub_from, void *out_c, void *out_w, long long n_outer, long long n_axis,
+                   long long n_inner, int scale, int taps, int dtype, int border, void *stream);
 
 /*
  * Synthesis: out = ((p_0 + p_1) + p_2) + ... over `nplanes` planes `plane_stride` elements apart, in the plane

@@ -105,7 +105,7 @@ def smooth(arr: np.ndarray, name: str, s: int = 0, backend: str | None = None) -
     backend 'numpy' : separable gather, float64 accumulation, one rounding to the image dtype.
     """
     if arr.ndim != 2:
-        raise ValueError("oracle covers the 2-D path only")
+        return smooth_nd(arr, name, s)
     backend = backend or default_backend()
     taps = TAPS[name]
     if backend == "cv2":
@@ -124,6 +124,47 @@ def smooth(arr: np.ndarray, name: str, s: int = 0, backend: str | None = None) -
     ys = np.arange(h)
     for i, t in enumerate(taps):
         out += t * rows[reflect_index(ys + (i - c) * d, h), :]
+    return out.astype(arr.dtype)
+
+
+def mirror_index(i, n):
+    """Whole-sample reflection of integer index(es) ``i`` into [0, n): ``dcb|abcd|cba`` -- scipy.ndimage mode='mirror'
+    (wavelets.py:69, the 1-D branch), for any number of reflections (period 2n - 2)."""
+    if n == 1:
+        return np.zeros_like(np.asarray(i))
+    m = np.mod(i, 2 * n - 2)
+    return np.where(m < n, m, 2 * n - 2 - m)
+
+
+def smooth_nd(arr: np.ndarray, name: str, s: int = 0) -> np.ndarray:
+    """c_{s+1} = S_s[c_s] for 1-D signals and 3-D volumes (wavelets.py:46-69), float64 accumulation, one rounding.
+
+    1-D (:64-69): scipy.ndimage.convolve(arr, atrous_kernel(s), mode='mirror') -- whole-sample reflection.
+    3-D (:46-63): the 2-D dilated smooth of every arr[i] slice (cv2.BORDER_REFLECT), then the dilated 1-D filter
+    along axis 0 of every [:, :, i] slice (cv2.filter2D with the (K, 1) kernel, BORDER_REFLECT): half-sample
+    symmetric reflection on all three axes."""
+    taps = TAPS[name]
+    c = len(taps) // 2
+    d = 2 ** s
+    a64 = arr.astype(np.float64)
+    if arr.ndim == 1:
+        xs = np.arange(arr.shape[0])
+        out = np.zeros(arr.shape, dtype=np.float64)
+        for j, t in enumerate(taps):
+            out += t * a64[mirror_index(xs + (j - c) * d, arr.shape[0])]
+        return out.astype(arr.dtype)
+    if arr.ndim != 3:
+        raise ValueError("Unsupported number of dimensions")
+    out = a64
+    for axis in (2, 1, 0):
+        n = arr.shape[axis]
+        idx = np.arange(n)
+        acc = np.zeros(arr.shape, dtype=np.float64)
+        for j, t in enumerate(taps):
+            acc += t * np.take(out, reflect_index(idx + (j - c) * d, n), axis=axis)
+        out = acc
+        if axis == 1:
+            out = out.astype(arr.dtype).astype(np.float64)  # the reference rounds to the volume dtype between its passes
     return out.astype(arr.dtype)
 
 
@@ -187,8 +228,10 @@ def atrous_transform(arr: np.ndarray, level: int, name: str = "b3spline", bilate
 
     Planes [w_0 .. w_{L-1}, c_L] with c_0 = arr, c_{s+1} = S_s[c_s] (or its bilateral variant), w_s = c_s - c_{s+1}.
     Integer and big-endian inputs are recast to float64 (wavelets.py:297,319-320); the input is never modified."""
-    if arr.ndim != 2:
-        raise ValueError("oracle covers the 2-D path only")
+    if arr.ndim > 3:
+        raise ValueError("Unsupported number of dimensions")  # wavelets.py:316-317
+    if arr.ndim != 2 and bilateral is not None:
+        raise ValueError("oracle: the bilateral cascade is restated for 2-D images only")
     if arr.dtype in _RECAST:
         arr = np.float64(arr)
     sb = _bilateral_list(bilateral, level)

@@ -36,9 +36,30 @@ def save(name, **arrays):
     print(f"{name:36s} {os.path.getsize(path) / 1024:8.1f} KiB")
 
 
+def main_nd():
+    """1-D signals and 3-D volumes (wavelets.py:46-69): plain transform + denoise of the planes."""
+    for sf in SF:
+        for dt in ("float32", "float64"):
+            out = {}
+            cases = [((257,), 5), ((64,), 3), ((9,), 2), ((12, 20, 28), 3), ((5, 33, 16), 2)]
+            for k, (shape, level) in enumerate(cases):
+                arr = gaussian(shape, 20 + k, dt) * 3 + 10
+                co = AtrousTransform(SF[sf])(arr, level)
+                out[f"in{k}"] = arr
+                out[f"out{k}"] = co.data.copy()
+                out[f"level{k}"] = np.int64(level)
+                out[f"noise{k}"] = np.float64(co.get_noise())
+                co.denoise([3, 2][:level], soft_threshold=True)
+                out[f"den{k}"] = co.data.copy()
+            save(f"transform_nd_{sf}_{dt}", n=np.int64(len(cases)), **out)
+
+
 def main():
     assert watroo.__version__ == "0.0.4", watroo.__version__
     warnings.simplefilter("ignore")
+    if "--nd" in sys.argv:  # only the 1-D / 3-D fixtures (added later; the others are unchanged)
+        return main_nd()
+    main_nd()
 
     # ---- plain transform: wavelets.py:408-444 via :307 ------------------------------------------------------
     cases = [((64, 64), 4), ((37, 53), 4), ((6, 7), 3), ((96, 64), 6), ((24, 256), 5)]

@@ -49,6 +49,33 @@ def test_transform_golden(sf, dt, backend):
         assert orc.emax(out.sum(axis=0), img) < (1e-5 if dt == "float32" else 1e-13)
 
 
+def test_mirror_index_matches_np_pad_reflect():
+    for n in (1, 2, 5, 8):
+        base = np.arange(n)
+        padded = np.pad(base, (3 * n + 1, 3 * n + 2), mode="reflect") if n > 1 else np.zeros(7 * n + 3, dtype=int)
+        idx = np.arange(-(3 * n + 1), n + 3 * n + 2)
+        assert np.array_equal(orc.mirror_index(idx, n), padded)
+
+
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+@pytest.mark.parametrize("sf", ["b3spline", "triangle"])
+def test_transform_nd_golden(sf, dt):
+    """1-D signals (scipy 'mirror' border) and 3-D volumes (2-D smooth per slice + depth pass) of the real reference
+    (wavelets.py:46-69), incl. MAD noise and soft denoise of the planes."""
+    g = load_golden(f"transform_nd_{sf}_{dt}")
+    for k in range(int(g["n"])):
+        arr = g[f"in{k}"]
+        level = int(g[f"level{k}"])
+        out = orc.atrous_transform(arr, level, sf)
+        ref = g[f"out{k}"]
+        assert out.shape == ref.shape and out.dtype == ref.dtype
+        floor = 4 * np.finfo(ref.dtype).eps * np.abs(arr).max()
+        for p in range(level + 1):
+            err = np.abs(out[p].astype(np.float64) - ref[p]).max()
+            assert err <= max(TOL[dt] * np.abs(ref[p]).max(), floor), (k, p, err)
+        assert orc.emax(out.sum(axis=0), arr) < (1e-5 if dt == "float32" else 1e-13)
+
+
 @pytest.mark.parametrize("backend", BACKENDS)
 def test_integer_input_is_recast_to_float64(backend):
     g = load_golden("transform_int16")

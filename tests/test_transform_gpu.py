@@ -41,6 +41,32 @@ def test_golden_transform(sf, dt):
         assert_planes_close(out, g[f"out{k}"], np.dtype(dt).type, np.abs(img).max(), f"case{k}")
 
 
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+@pytest.mark.parametrize("sf", SF_NAMES)
+def test_golden_transform_1d_and_3d(sf, dt):
+    """1-D signals (whole-sample 'mirror' border) and 3-D volumes (slice-wise 2-D smooth + depth pass) against the
+    real reference (watroo/wavelets.py:46-69): planes, MAD noise, soft denoise of the planes, reconstruction."""
+    import wavelets_b200 as wb
+    g = load_golden(f"transform_nd_{sf}_{dt}")
+    npdt = np.dtype(dt).type
+    for k in range(int(g["n"])):
+        arr = g[f"in{k}"]
+        level = int(g[f"level{k}"])
+        co = wb.AtrousTransform(_sf(sf))(arr, level)
+        assert co.scaling_function.n_dim == arr.ndim and co.data.shape == (level + 1,) + arr.shape
+        out = co.data.cpu().numpy()
+        assert_planes_close(out, g[f"out{k}"], npdt, np.abs(arr).max(), f"case{k}")
+        assert orc.emax(out.sum(axis=0), arr) < (1e-5 if dt == "float32" else 1e-12)
+        noise = co.get_noise()
+        assert abs(noise - float(g[f"noise{k}"])) <= (2e-5 if dt == "float32" else 1e-12) * float(g[f"noise{k}"])
+        co.denoise([3, 2][:level], soft_threshold=True)
+        den = co.data.cpu().numpy()
+        tol = 2e-5 if dt == "float32" else 1e-11
+        for p in range(level + 1):
+            ref = g[f"den{k}"][p]
+            assert np.abs(den[p].astype(np.float64) - ref).max() <= tol * max(np.abs(ref).max(), 1e-30), (k, p)
+
+
 def test_reference_kat_ones():
     """The reference's own test (tests/test_wavelets.py:8-13): ones -> zero detail planes, unit residual."""
     import wavelets_b200 as wb
@@ -59,8 +85,8 @@ def test_integer_recast_and_errors():
     assert_planes_close(co.data.cpu().numpy(), g["out"], np.float64, np.abs(g["img"]).max())
     with pytest.raises(ValueError, match="Unsupported number of dimensions"):
         wb.AtrousTransform()(np.zeros((2, 2, 2, 2)), 1)
-    with pytest.raises(NotImplementedError):
-        wb.AtrousTransform()(np.zeros((4, 8, 8)), 1)
+    with pytest.raises(NotImplementedError):  # bilateral cascade: 2-D only
+        wb.AtrousTransform(bilateral=1)(np.zeros((4, 8, 8)), 1)
     with pytest.raises(TypeError):
         wb.AtrousTransform()(np.zeros((8, 8), dtype=np.uint8), 1)
 

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_PKG, "libwavelets_b200.so")
 
 WB_F32, WB_F64 = 0, 1
 WB_TRIANGLE, WB_B3SPLINE = 3, 5
+WB_BORDER_SYMMETRIC, WB_BORDER_MIRROR = 0, 1
 WB_ENOT_FUSABLE = -7
 ABI_VERSION = 1
 
@@ -57,6 +58,7 @@ SIGNATURES = {
     "wb_residual_rescale": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_int, _c_vp, _c_dbl, _c_vp]),
     "wb_synthesis": (_c_int, [_c_vp, _c_int, _c_ll, _c_ll, _c_int, _c_ll, _c_vp, _c_ll, _c_int, _c_vp]),
     "wb_randn_f32": (_c_int, [_c_vp, _c_ll, _c_ull, _c_ull, _c_vp]),
+    "wb_atrous_axis": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_ll, _c_ll, _c_ll, _c_int, _c_int, _c_int, _c_int, _c_vp]),
 }
 # development hooks exported by the library but not part of the stable ABI
 _EXTRA = {

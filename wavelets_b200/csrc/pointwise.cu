@@ -183,6 +183,43 @@ static unsigned grid_for(long long work_items) {
     return (unsigned)blocks;
 }
 
+
+// One dilated filter pass along ONE axis of an (outer, axis, inner) row-major array -- the pieces of the 1-D and 3-D
+// transforms that the 2-D row-pipeline kernels do not cover:
+//   * 1-D signals (watroo/wavelets.py:64-69): scipy.ndimage.convolve(..., mode='mirror'), whole-sample reflection;
+//   * the depth pass of a volume (watroo/wavelets.py:55-63): cv2.filter2D with the (K, 1) column kernel on every
+//     [:, :, i] slice, BORDER_REFLECT (half-sample reflection), after the 2-D smooth of every [i] slice.
+// out_c = filtered(in); out_w = sub_from - out_c (the detail plane refers to the plane BEFORE any pass of this scale).
+// One thread per element, taps gathered straight from global memory (adjacent threads read adjacent addresses).
+template <typename T, int TAPS>
+__global__ void __launch_bounds__(256) axis_filter_kernel(const T *in, const T *sub_from, T *out_c, T *out_w,
+                                                          long long n_axis, long long n_inner, long long total,
+                                                          long long d, int border) {
+    constexpr int C = TAPS / 2;
+    const long long period = border == WB_BORDER_MIRROR ? 2 * (n_axis - 1) : 2 * n_axis;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long a = (idx / n_inner) % n_axis;
+        const long long base = idx - a * n_inner;
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            long long m = a + (long long)(k - C) * d;
+            if (period > 0) {
+                m %= period;
+                if (m < 0) m += period;
+                if (m >= n_axis) m = (border == WB_BORDER_MIRROR) ? period - m : period - 1 - m;
+            } else {
+                m = 0;  // a single sample mirrors onto itself
+            }
+            const T v = in[base + m * n_inner];
+            acc = (k == 0) ? Taps<T, TAPS>::h(0) * v : fma_t<T>(Taps<T, TAPS>::h(k), v, acc);
+        }
+        if (out_c) out_c[idx] = acc;
+        if (out_w) out_w[idx] = sub_from[idx] - acc;
+    }
+}
+
 }  // namespace wb
 
 extern "C" {
@@ -261,6 +298,32 @@ int wb_randn_f32(float *out, long long n, unsigned long long seed, unsigned long
     if (n < 1) return WB_EINVAL_SHAPE;
     if (!out) return WB_EINVAL_POINTER;
     wb::randn_kernel<<<wb::grid_for(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
+    return wb::launch_status();
+}
+
+int wb_atrous_axis(const void *in, const void *sub_from, void *out_c, void *out_w, long long n_outer, long long n_axis,
+                   long long n_inner, int scale, int taps, int dtype, int border, void *stream) {
+    if (dtype != WB_F32 && dtype != WB_F64) return WB_EINVAL_DTYPE;
+    if (taps != WB_TRIANGLE && taps != WB_B3SPLINE) return WB_EINVAL_TAPS;
+    if (n_outer < 1 || n_axis < 1 || n_inner < 1) return WB_EINVAL_SHAPE;
+    if (scale < 0 || scale > 30) return WB_EINVAL_SCALE;
+    if (border != WB_BORDER_SYMMETRIC && border != WB_BORDER_MIRROR) return WB_EINVAL_ARG;
+    if (!in || (!out_c && !out_w) || (out_w && !sub_from) || in == out_c || in == out_w) return WB_EINVAL_POINTER;
+    const long long total = n_outer * n_axis * n_inner;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = wb::grid_for(total);
+    const long long d = 1LL << scale;
+#define WB_AXIS(T, TAPS)                                                                                          \
+    wb::axis_filter_kernel<T, TAPS><<<grid, 256, 0, st>>>(reinterpret_cast<const T *>(in),                         \
+                                                         reinterpret_cast<const T *>(sub_from),                   \
+                                                         reinterpret_cast<T *>(out_c), reinterpret_cast<T *>(out_w), \
+                                                         n_axis, n_inner, total, d, border)
+    if (dtype == WB_F32) {
+        if (taps == WB_TRIANGLE) WB_AXIS(float, 3); else WB_AXIS(float, 5);
+    } else {
+        if (taps == WB_TRIANGLE) WB_AXIS(double, 3); else WB_AXIS(double, 5);
+    }
+#undef WB_AXIS
     return wb::launch_status();
 }
 

@@ -337,6 +337,13 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
         if (j > n_load) return;
         if (j < n_load) {
             mbar_wait_imm<8 * I>(full0 + (half >> 11), par_in);  // barrier of slot I + 4 (u & 1): 8 bytes per slot
+            // raw centre row j-C (slot (I - C) mod 4 of the half that row was loaded into), requested first so that its
+            // latency hides behind the row pass
+            constexpr int SC = (I - C + 4) & 3;
+            constexpr bool other_half = I < C;
+            P4 rawc[NG];
+#pragma unroll
+            for (int q = 0; q < NG; ++q) rawc[q] = lds_p4_imm<SC * RB>(own[q] + (other_half ? half_c : half));
             P4 cv[NG];
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
@@ -349,9 +356,6 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
                 cv[q].hi = col_feed_p<TAPS>(SA[q][1], v.hi, H);
             }
             if (j >= 2 * C) {
-                // raw centre row j-C: slot (I - C) mod 4 of the half that row was loaded into
-                constexpr int SC = (I - C + 4) & 3;
-                constexpr bool other_half = I < C;
                 constexpr int SW = (I - 2 * C + 8) & (kWRing - 1);  // w row j-2C
                 const bool store_c = (j >= 3 * C) && (j < j_store_end);
 #pragma unroll
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
                         if (HINTS) stg_p4_hint(c_ptr + q * (NT * V), cv[q], pol_keep);
                         else stg_p4(c_ptr + q * (NT * V), cv[q]);
                     }
-                    P4 raw = lds_p4_imm<SC * RB>(own[q] + (other_half ? half_c : half));
+                    P4 raw = rawc[q];
                     raw.lo = sub2(raw.lo, cv[q].lo);
                     raw.hi = sub2(raw.hi, cv[q].hi);
                     if (act[q]) sts_p4_imm<W_OFF + SW * RB>(own[q], raw);
@@ -372,11 +376,15 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
         }
         if (j > 2 * C) {
             constexpr int SP = (I - 1 - 2 * C + 16) & (kWRing - 1);  // w row j-1-2C (all threads' columns)
-            mbar_wait_imm<8 * SP>(wbar0, ((uint32_t)(j - 1 - 2 * C) >> 2) & 1u);
+            mbar_wait_imm<8 * SP>(wbar0, ((uint32_t)(j - 1 - 2 * C) >> 2) & 1u, (uint32_t)p.suspend_ns);
             if (tid == 0) {
                 // every warp is past part A of step j-1: input rows <= j-1-C are free
                 while (next_load < n_load && next_load - kInRing <= j - 1 - C) issue_load();
             }
+            constexpr int SE = (I - 1 - 3 * C + 16) & (kWRing - 1);  // own raw w of the P row completed in this step
+            P4 roww[NG];
+#pragma unroll
+            for (int q = 0; q < NG; ++q) roww[q] = lds_p4_imm<W_OFF + SE * RB>(own[q]);
             P4 pw[NG];
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
@@ -388,10 +396,9 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
                 pw[q].hi = col_feed_p<TAPS>(SB[q][1], v.hi, H);
             }
             if (j > 4 * C) {
-                constexpr int SE = (I - 1 - 3 * C + 16) & (kWRing - 1);  // own raw w of the completed P row
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
-                    P4 raw = lds_p4_imm<W_OFF + SE * RB>(own[q]);
+                    P4 raw = roww[q];
                     raw.lo = epi.template apply2<MODE>(raw.lo, pw[q].lo);
                     raw.hi = epi.template apply2<MODE>(raw.hi, pw[q].hi);
                     if (act[q]) stg_p4_cs(o_ptr + q * (NT * V), raw);
@@ -540,6 +547,14 @@ static int fill_wow_params(ScaleParams &p, const void *in, void *out_c, void *ou
             v = e ? atoi(e) : 3;
         }
         p.l2_hints = l2_hints_enabled() ? v : 0;
+    }
+    {
+        static int ns = -1;
+        if (ns < 0) {
+            const char *e = getenv("WB_MBAR_SUSPEND_NS");
+            ns = e ? atoi(e) : (int)kMbarSuspendHintNs;
+        }
+        p.suspend_ns = ns;
     }
     return WB_OK;
 }

@@ -1,7 +1,7 @@
 """Scaling functions of the à trous transform: taps, 2-D kernels and noise-normalisation tables.
 
 Mirror of the reference's ``AbstractScalingFunction`` / ``Triangle`` / ``B3spline`` (watroo/wavelets.py:152-287)
-for the 2-D hot path: same attribute and method names (``name``, ``n_dim``, ``kernel``, ``coefficients_1d``,
+(2-D hot path, plus the 1-D / 3-D tables): same attribute and method names (``name``, ``n_dim``, ``kernel``, ``coefficients_1d``,
 ``coefficients_2d``, ``atrous_kernel(scale)``, ``sigma_e(bilateral)``, ``compute_noise_weights``).  The device
 kernels never build the dense dilated kernel -- ``atrous_kernel`` exists for API compatibility only.
 """
@@ -21,7 +21,10 @@ class AbstractScalingFunction:
     taps_code = None          # WB_TRIANGLE / WB_B3SPLINE of the C ABI
     sigma_e_1d = None
     sigma_e_2d = None
+    sigma_e_3d = None
+    sigma_e_1d_bilateral = None
     sigma_e_2d_bilateral = None
+    sigma_e_3d_bilateral = None
 
     def __init__(self, name, n_dim):
         if n_dim not in (1, 2, 3):
@@ -50,11 +53,11 @@ class AbstractScalingFunction:
         return dense
 
     def sigma_e(self, bilateral=None):
-        """Std of each wavelet plane for unit white noise (watroo/wavelets.py:199-219).  Only the 2-D tables are
-        carried; the bilateral table is selected whenever ``bilateral is not None``."""
-        if self.n_dim != 2:
-            raise NotImplementedError("wavelets_b200 covers the 2-D path only")
-        return self.sigma_e_2d if bilateral is None else self.sigma_e_2d_bilateral
+        """Std of each wavelet plane for unit white noise (watroo/wavelets.py:199-219): the table of this
+        dimensionality; the bilateral table whenever ``bilateral is not None`` (None where the reference has none)."""
+        plain = {1: self.sigma_e_1d, 2: self.sigma_e_2d, 3: self.sigma_e_3d}
+        bil = {1: self.sigma_e_1d_bilateral, 2: self.sigma_e_2d_bilateral, 3: self.sigma_e_3d_bilateral}
+        return (plain if bilateral is None else bil)[self.n_dim]
 
     def compute_noise_weights(self, n_scales, n_trials=100, bilateral=None, fields=None, seed=None):
         """Monte-Carlo estimate of ``sigma_e`` (watroo/wavelets.py:221-229), entirely on the GPU.
@@ -76,6 +79,8 @@ class Triangle(AbstractScalingFunction):
                            0.03529812, 0.02409187, 0.01722846, 0.01144442])
     sigma_e_2d = np.array([0.7999247, 0.27308452, 0.11998217, 0.05793947, 0.0288104, 0.01447795, 0.00733832,
                            0.0037203, 0.00192882, 0.00098568, 0.00048533])
+    sigma_e_3d = np.array([0.89736751, 0.19514386, 0.06239262, 0.02311278, 0.00939645])
+    sigma_e_3d_bilateral = np.array([0.3828863, 0.36182913, 0.19520299, 0.08498861, 0.03363142])
     sigma_e_2d_bilateral = np.array([0.31063172, 0.34575647, 0.23712331, 0.13559906, 0.07172004, 0.03665405,
                                      0.01850046, 0.00928768, 0.00465967, 0.00234445, 0.00119249])
 
@@ -92,6 +97,8 @@ class B3spline(AbstractScalingFunction):
                            0.02919823, 0.01805671, 0.01383672, 0.00943623])
     sigma_e_2d = np.array([8.907e-01, 2.0072e-01, 8.5551e-02, 4.1261e-02, 2.0470e-02, 1.0232e-02, 5.1435e-03,
                            2.6008e-03, 1.3161e-03, 6.7359e-04, 4.0040e-04])
+    sigma_e_3d = np.array([0.95633954, 0.12491933, 0.03933029, 0.01489642, 0.0064108])
+    sigma_e_3d_bilateral = np.array([0.44111772, 0.3552894, 0.16137159, 0.05769064, 0.01932497])
     # NB: 10 entries, one fewer than Triangle's (watroo/wavelets.py:280-281)
     sigma_e_2d_bilateral = np.array([0.38234752, 0.24305799, 0.16012153, 0.10633541, 0.07083733, 0.04728659,
                                      0.03163678, 0.02122341, 0.01429102, 0.00952376])

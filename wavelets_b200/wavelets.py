@@ -59,8 +59,8 @@ def to_device_image(arr, ndim_ok=(2,)):
     if t.ndim not in ndim_ok:
         if t.ndim == 3 or t.ndim == 1:
             raise NotImplementedError(
-                "wavelets_b200 accelerates the 2-D path; a 3-D input is a volume in the reference "
-                "(watroo/wavelets.py:322), not a batch -- use AtrousTransform.batch() for stacks of frames")
+                "this entry point takes 2-D images; a 3-D input is a volume in the reference "
+                "(watroo/wavelets.py:322), not a batch -- use AtrousTransform.batch() / wow_batch() for stacks of frames")
         raise ValueError("Unsupported number of dimensions")
     return t, was_numpy
 
@@ -255,7 +255,10 @@ class Coefficients:
         return np.float64(self._estimate_noise().item())
 
     def _estimate_noise(self):
-        return abs_median_noise(self.data[0], self.sigma_e[0])
+        plane = self.data[0]
+        if plane.ndim != 2:  # 1-D signal / 3-D volume: one frame of numel() samples
+            plane = plane.reshape(1, -1)
+        return abs_median_noise(plane, self.sigma_e[0])
 
     def _noise_arg(self, sigma):
         """Resolve ``self.noise`` for a threshold kernel, estimating it lazily like the reference
@@ -339,15 +342,55 @@ class AtrousTransform:
         self.bilateral_scaling = bilateral_scaling
 
     def __call__(self, arr, level, recursive=False):
-        """Transform a 2-D image over ``level`` scales -> ``Coefficients`` with ``level + 1`` planes.
+        """Transform an image over ``level`` scales -> ``Coefficients`` with ``level + 1`` planes.
+
+        2-D images take the row-pipeline kernels.  1-D signals (whole-sample 'mirror' border, watroo/wavelets.py:64-69)
+        and 3-D volumes (2-D smooth of every slice, then the depth pass, watroo/wavelets.py:46-63) run the plain
+        cascade through ``wb_atrous_axis``; their bilateral variants are not built.
 
         ``recursive`` is accepted for signature compatibility and ignored: the reference's recursive variant is a
         CPU-side optimisation of the same transform (it differs from the standard one only near the borders,
         watroo/wavelets.py:394-395); the device kernels always implement the standard algorithm."""
-        img, _ = to_device_image(arr)
+        img, _ = to_device_image(arr, ndim_ok=(1, 2, 3))
         scaling_function = self.scaling_function_class(img.ndim)
-        planes = self._run(img, int(level), scaling_function)
+        if img.ndim == 2:
+            planes = self._run(img, int(level), scaling_function)
+        else:
+            if self.bilateral is not None:
+                raise NotImplementedError("wavelets_b200: the bilateral cascade is built for 2-D images only")
+            planes = self._run_nd(img, int(level), scaling_function)
         return Coefficients(planes, scaling_function, self.bilateral)
+
+    def _run_nd(self, arr, level, scaling_function):
+        """Plain cascade of a 1-D signal or a 3-D volume: planes ``(level + 1, *arr.shape)``."""
+        if level < 0:
+            raise ValueError("level must be >= 0")
+        lib = _lib.load(require_cuda=True)
+        arr = arr.contiguous()
+        planes = torch.empty((level + 1,) + tuple(arr.shape), dtype=arr.dtype, device=arr.device)
+        if level == 0:
+            planes[0].copy_(arr)
+            return planes
+        code, taps = _lib.dtype_code(arr.dtype), scaling_function.taps_code
+        scratch = [torch.empty_like(arr) for _ in range(2 if level > 1 else 0)]
+        sf2 = self.scaling_function_class(2)
+        tmp = torch.empty_like(arr) if arr.ndim == 3 else None
+        src = arr
+        with torch.cuda.device(arr.device):
+            for s in range(level):
+                dst_c = planes[level] if s == level - 1 else scratch[s & 1]
+                if arr.ndim == 1:
+                    _lib.check(lib.wb_atrous_axis(src.data_ptr(), src.data_ptr(), dst_c.data_ptr(), planes[s].data_ptr(),
+                                                  1, arr.shape[0], 1, s, taps, code, _lib.WB_BORDER_MIRROR,
+                                                  _lib.stream_ptr(arr.device)))
+                else:
+                    depth, h, w = arr.shape
+                    atrous_scale(src, s, sf2, out_c=tmp, out_w=False)  # every [i] slice, one launch
+                    _lib.check(lib.wb_atrous_axis(tmp.data_ptr(), src.data_ptr(), dst_c.data_ptr(), planes[s].data_ptr(),
+                                                  1, depth, h * w, s, taps, code, _lib.WB_BORDER_SYMMETRIC,
+                                                  _lib.stream_ptr(arr.device)))
+                src = dst_c
+        return planes
 
     def batch(self, frames, level):
         """NEW entry point (no reference equivalent): transform a stack ``(B, H, W)`` of independent frames with one
