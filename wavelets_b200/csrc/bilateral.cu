@@ -235,7 +235,10 @@ __device__ __forceinline__ void pair_taps(uint32_t rowb, const uint32_t (&colb)[
 #pragma unroll
         for (int k = 0; k < TAPS; ++k) {
             u64 t = lds64(rowb + colb[k]);
-            if (MIRROR && ((rev >> k) & 1u)) t = swap2(t);
+            if (MIRROR) {
+                const u64 u = swap2(t);
+                t = ((rev >> k) & 1u) ? u : t;
+            }
             out[k] = t;
         }
     } else {
@@ -243,7 +246,10 @@ __device__ __forceinline__ void pair_taps(uint32_t rowb, const uint32_t (&colb)[
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             u64 t = lds64(rowb + colb[k]);
-            if (MIRROR && ((rev >> k) & 1u)) t = swap2(t);
+            if (MIRROR) {
+                const u64 u = swap2(t);
+                t = ((rev >> k) & 1u) ? u : t;
+            }
             up2(t, win[2 * k], win[2 * k + 1]);
         }
 #pragma unroll
@@ -251,12 +257,38 @@ __device__ __forceinline__ void pair_taps(uint32_t rowb, const uint32_t (&colb)[
     }
 }
 
+// Row statistics for the variance (law of total variance over the window rows).  For one staged row and this thread's
+// pixel pair, relative to the row's own centre-column pixel x_c:   a = sum_k h_k (x_k - x_c),  b = sum_k h_k (x_k - x_c)^2.
+// They depend on (row, column) only, so they are computed ONCE per input row (when it becomes the newest window row)
+// and kept in a per-thread shared-memory ring for the 2C later windows that contain the row.  With e_i = x_ic - x_cc
+// (row centre minus window centre) the window moments are
+//     s1 = sum_i h_i (a_i + e_i),      s2 = sum_i h_i (b_i + e_i (2 a_i + e_i)),      var = s2 - s1^2
+// -- still differences only (no cancellation), 60 packed operations per pixel pair instead of 96.
+static constexpr long long kPairStats = 256 * 16;  // bytes of row statistics per ring slot (256 consumer threads)
+
+template <int TAPS>
+__device__ __forceinline__ P4 row_stats(const u64 (&tv)[TAPS]) {
+    constexpr int C = TAPS / 2;
+    u64 a = 0ull, b = 0ull;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const float hk = Taps<float, TAPS>::h(k);
+        const u64 dl = sub2(tv[k], tv[C]), dr = sub2(tv[TAPS - 1 - k], tv[C]);
+        const u64 sum = add2(dl, dr);
+        const u64 sq = fma2(dr, dr, mul2(dl, dl));
+        a = (k == 0) ? mul2(pk2(hk, hk), sum) : fma2(pk2(hk, hk), sum, a);
+        b = (k == 0) ? mul2(pk2(hk, hk), sq) : fma2(pk2(hk, hk), sq, b);
+    }
+    return P4{a, b};
+}
+
 // One step of the software pipeline (see the kernel): range weights + output of the OLD row from the differences in
 // D, differences + variance sums of the NEW row into D.  OLD / NEW are compile-time so the prologue (NEW only) and
 // the drain (OLD only) cost no selects in the steady state.
-template <int TAPS, int DMODE, bool OLD, bool NEW>
+template <int TAPS, int DMODE, bool OLD, bool NEW, bool MIRROR>
 __device__ __forceinline__ void pair_step(u64 (&D)[TAPS][TAPS], u64 &xc_old, u64 &nhi, const uint32_t (&rowb)[TAPS],
-                                          uint32_t cb, const uint32_t (&colb)[PairPlan<TAPS, DMODE>::NL], unsigned rev,
+                                          const uint32_t (&statb)[TAPS], uint32_t cb,
+                                          const uint32_t (&colb)[PairPlan<TAPS, DMODE>::NL], unsigned rev,
                                           float var_factor, float *c_dst, float *w_dst, bool act, uint64_t pol_keep) {
     constexpr int C = TAPS / 2;
     const float kc = Taps<float, TAPS>::h(C) * Taps<float, TAPS>::h(C);
@@ -267,10 +299,7 @@ __device__ __forceinline__ void pair_step(u64 (&D)[TAPS][TAPS], u64 &xc_old, u64
 #pragma unroll
     for (int i = 0; i < TAPS; ++i) {
         u64 tv[TAPS];
-        if (NEW) {
-            if (rev == 0) pair_taps<TAPS, DMODE, false>(rowb[i], colb, rev, tv);
-            else pair_taps<TAPS, DMODE, true>(rowb[i], colb, rev, tv);
-        }
+        if (NEW) pair_taps<TAPS, DMODE, MIRROR>(rowb[i], colb, rev, tv);
 #pragma unroll
         for (int k = 0; k < TAPS; ++k) {
             if (OLD && !(i == C && k == C)) {
@@ -282,13 +311,31 @@ __device__ __forceinline__ void pair_step(u64 (&D)[TAPS][TAPS], u64 &xc_old, u64
                 den = add2(den, gw);
                 num = fma2(gw, dd, num);
             }
-            if (NEW) {
-                const float kk = Taps<float, TAPS>::h(i) * Taps<float, TAPS>::h(k);
-                const u64 dn = sub2(xc, tv[k]);
-                D[i][k] = dn;
-                const u64 kd = mul2(pk2(kk, kk), dn);
-                s1 = add2(s1, kd);
-                s2 = fma2(kd, dn, s2);
+            if (NEW) D[i][k] = sub2(xc, tv[k]);
+        }
+        if (NEW) {
+            // window moments from the row statistics: the newest row's are computed here (and stored for the next
+            // 2C windows), the others come from the ring
+            const float hi = Taps<float, TAPS>::h(i);
+            P4 st;
+            if (i == TAPS - 1) {
+                st = row_stats<TAPS>(tv);
+                sts_p4(statb[i], st);
+            } else {
+                st = lds_p4(statb[i]);
+            }
+            if (i == C) {
+                s1 = fma2(pk2(-hi, -hi), st.lo, s1);
+                s2 = fma2(pk2(hi, hi), st.hi, s2);
+            } else {
+                // e = x_ic - x_cc = -D[i][C];  2 a + e = 2 a - D;  b + e (2 a + e) = b - D (2 a - D)
+                // with dc = D[i][C] = -e:  s1 accumulates -(a + e) = dc - a (only s1^2 is used);
+                // b + e (2 a + e) = b + dc (dc - 2 a)
+                const u64 dc = D[i][C];
+                const u64 t = fma2(pk2(-2.0f, -2.0f), st.lo, dc);
+                const u64 u = fma2(dc, t, st.hi);
+                s1 = fma2(pk2(hi, hi), sub2(dc, st.lo), s1);
+                s2 = fma2(pk2(hi, hi), u, s2);
             }
         }
     }
@@ -328,6 +375,8 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
     float *rows = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)p.slots * p.row_stride * sizeof(float));
     uint64_t *empty = full + p.slots;
+    // per-thread row statistics (a, b) of every staged row: slots x 256 threads x 16 bytes, same slot index as the row
+    const uint32_t stats_base = smem_u32(empty + p.slots);
 
     const int nt = blockDim.x - 32;  // 8 consumer warps; the last warp is the TMA producer
     const int nwc = nt >> 5;
@@ -370,7 +419,11 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
             int slot = 0;
             uint32_t round = 0;
             for (int j = 0; j < n_load; ++j) {
-                if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
+                if (round > 0) {
+                    // the producer runs rows ahead of the consumers: poll rarely, its spinning would take issue slots
+                    // from the warps doing the arithmetic (the kernel is issue / pipe bound)
+                    while (!mbar_test(&empty[slot], (round - 1) & 1)) __nanosleep(2000);
+                }
                 const long long y = reflect_any(p.gwy0 + r + (long long)(i0 - C + j) * p.d, p.Hg) - p.gwy0 + p.row_off_in;
                 mbar_arrive_expect_tx(&full[slot], row_bytes);
                 if (p.l2_hints) tma_load_1d_hint(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[slot], pol_in);
@@ -396,11 +449,12 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
         const int pcol = xg + (k - NL / 2) * (DMODE == 0 ? p.d : 2);  // even; one reflection at most
         const bool left = pcol < 0, right = pcol >= p.W;
         const int q = left ? (-2 - pcol) : (right ? (2 * p.W - 2 - pcol) : pcol);
-        colb[k] = (uint32_t)(q - lo) * 4u;
+        // per-thread tap addresses in slot 0; a window row adds a block-uniform slot offset ([R + UR] addressing)
+        colb[k] = smem_u32(rows) + (uint32_t)(q - lo) * 4u;  // absolute address of the tap in ring slot 0
         if (left || right) rev |= 1u << k;
     }
-    const uint32_t cb = (uint32_t)(xg - lo) * 4u;
-    const uint32_t smem_base = smem_u32(rows);
+    const uint32_t cb = smem_u32(rows) + (uint32_t)(xg - lo) * 4u;
+    const uint32_t stat_t = stats_base + (uint32_t)tid * 16u;  // this thread's entry in stats slot 0
     const float var_factor = (float)bp.var_factor;
     const uint64_t pol_keep = p.l2_hints ? policy_evict_last() : 0ull;  // c_{s+1}: the next scale reads it back
 
@@ -408,32 +462,45 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
     // pass 2 (range weights from the differences kept in registers: 2 MUFU per packed tap).  Warps drift freely (no
     // block barrier), so the passes of different warps overlap on the FMA and MUFU pipes.  [A variant that interleaves
     // pass 2 of row n-1 with pass 1 of row n inside each thread (pair_step<.., true, true>) measured 20 % slower.]
-    long long orow = (long long)r + (long long)i0 * p.d;
-    int slot = 0, fslot = 0;  // slot of chain row j, slot of row j - 2C (first row of the window, next to be released)
-    uint32_t parity = 0;
-    u64 D[TAPS][TAPS];
-    u64 xc_old = 0ull, nhi = 0ull;
-    for (int j = 0; j < n_load; ++j) {
-        mbar_wait(&full[slot], parity);
-        if (j >= 2 * C) {
-            uint32_t rowb[TAPS];
-            int ws = fslot;
+    // Warps that own no reflected column (all but the first / last strip's edge warps) run the variant without the
+    // mirror selects; the choice is warp-uniform, so no thread diverges inside the step.
+    auto run = [&](auto mirror) {
+        constexpr bool MIRROR = decltype(mirror)::value != 0;
+        long long orow = (long long)r + (long long)i0 * p.d;
+        int slot = 0, fslot = 0;  // slot of chain row j, slot of row j - 2C (first row of the window, next to be released)
+        uint32_t parity = 0;
+        u64 D[TAPS][TAPS];
+        u64 xc_old = 0ull, nhi = 0ull;
+        for (int j = 0; j < n_load; ++j) {
+            mbar_wait(&full[slot], parity);
+            if (j < 2 * C) {
+                // rows that are never the newest row of a window of this segment: their statistics are computed here
+                u64 tv[TAPS];
+                pair_taps<TAPS, DMODE, MIRROR>((uint32_t)slot * RB, colb, rev, tv);
+                sts_p4(stat_t + (uint32_t)slot * (256u * 16u), row_stats<TAPS>(tv));
+            } else {
+                uint32_t rowb[TAPS], statb[TAPS];
+                int ws = fslot;
 #pragma unroll
-            for (int i = 0; i < TAPS; ++i) {
-                rowb[i] = smem_base + (uint32_t)ws * RB;
-                if (++ws == p.slots) ws = 0;
+                for (int i = 0; i < TAPS; ++i) {
+                    rowb[i] = (uint32_t)ws * RB;  // block-uniform byte offset of the window row's slot
+                    statb[i] = stat_t + (uint32_t)ws * (256u * 16u);
+                    if (++ws == p.slots) ws = 0;
+                }
+                float *c_dst = out_c ? out_c + orow * p.c_pitch + xg : nullptr;
+                float *w_dst = out_w ? out_w + orow * p.w_pitch + xg : nullptr;
+                pair_step<TAPS, DMODE, false, true, MIRROR>(D, xc_old, nhi, rowb, statb, cb, colb, rev, var_factor, c_dst, w_dst, act, pol_keep);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[fslot]);  // the window rows are only read in pass 1
+                if (++fslot == p.slots) fslot = 0;
+                pair_step<TAPS, DMODE, true, false, MIRROR>(D, xc_old, nhi, rowb, statb, cb, colb, rev, var_factor, c_dst, w_dst, act, pol_keep);
+                orow += p.d;
             }
-            float *c_dst = out_c ? out_c + orow * p.c_pitch + xg : nullptr;
-            float *w_dst = out_w ? out_w + orow * p.w_pitch + xg : nullptr;
-            pair_step<TAPS, DMODE, false, true>(D, xc_old, nhi, rowb, cb, colb, rev, var_factor, c_dst, w_dst, act, pol_keep);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[fslot]);  // the window rows are only read in pass 1
-            if (++fslot == p.slots) fslot = 0;
-            pair_step<TAPS, DMODE, true, false>(D, xc_old, nhi, rowb, cb, colb, rev, var_factor, c_dst, w_dst, act, pol_keep);
-            orow += p.d;
+            if (++slot == p.slots) { slot = 0; parity ^= 1; }
         }
-        if (++slot == p.slots) { slot = 0; parity ^= 1; }
-    }
+    };
+    if (__any_sync(0xffffffffu, rev != 0)) run(IC<1>{});
+    else run(IC<0>{});
 }
 
 template <typename T, int TAPS>
@@ -535,7 +602,7 @@ template <int TAPS, int DMODE>
 static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStream_t st) {
     auto kern = bilateral_pairs_kernel<TAPS, DMODE>;
     const ScaleParams &p = bp.sp;
-    const size_t smem = (size_t)p.slots * p.row_stride * sizeof(float) + 16 * (size_t)p.slots;
+    const size_t smem = (size_t)p.slots * p.row_stride * sizeof(float) + 16 * (size_t)p.slots + kPairStats * (size_t)p.slots;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -561,8 +628,8 @@ static bool plan_bilateral_pairs(ScaleParams &p, int taps, int batch) {
     int slots = taps + 3;
     const int min_slots = taps + 1;
     // two resident blocks per SM (register-limited anyway): keep a block under half of the shared memory if possible
-    while (slots > min_slots && (long long)slots * p.row_stride * 4 + 16LL * slots > kMaxSmem / 2 - 1024) --slots;
-    if ((long long)slots * p.row_stride * 4 + 16LL * slots > kMaxSmem) return false;
+    while (slots > min_slots && (long long)slots * (p.row_stride * 4 + 16LL + kPairStats) > kMaxSmem / 2 - 1024) --slots;
+    if ((long long)slots * (p.row_stride * 4 + 16LL + kPairStats) > kMaxSmem) return false;
     p.slots = slots;
     const int n_max = (p.H + p.d - 1) / p.d;
     // Compute-bound kernel: about 4 waves of 2 resident blocks per SM; halo rows only cost L2 reads.
