@@ -66,6 +66,7 @@ __device__ __forceinline__ void row_taps(const T *srow, const TapPlan<PlanSize<T
 template <typename T, int TAPS, int DMODE>
 __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralParams bp) {
     const ScaleParams &p = bp.sp;
+    pdl_launch_dependents();
     constexpr int V = VecOf<T>::V;
     constexpr int C = TAPS / 2;
     constexpr int NV = PlanSize<TAPS, DMODE>::NV;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
         fence_mbar_init();
     }
     __syncthreads();
+    pdl_wait();  // everything below touches global memory written or read by the previous launch
 
     if (warp == nwc) {
         if (lane == 0) {
@@ -369,6 +371,7 @@ __device__ __forceinline__ void pair_step(u64 (&D)[TAPS][TAPS], u64 &xc_old, u64
 template <int TAPS, int DMODE>
 __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const BilateralParams bp) {
     const ScaleParams &p = bp.sp;
+    pdl_launch_dependents();
     constexpr int C = TAPS / 2;
     constexpr int NL = PairPlan<TAPS, DMODE>::NL;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -411,6 +414,7 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
         fence_mbar_init();
     }
     __syncthreads();
+    pdl_wait();  // everything below touches global memory written or read by the previous launch
 
     if (warp == nwc) {
         if (lane == 0) {
@@ -564,8 +568,7 @@ static int launch_bilateral(const BilateralParams &bp, int batch, int nt, cudaSt
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
-    kern<<<grid, nt + 32, smem, st>>>(bp);
-    return launch_status();
+    return launch_pdl<BilateralParams>(kern, grid, dim3((unsigned)(nt + 32)), smem, st, bp);
 }
 
 // Geometry for K2: one vector per thread, 256 consumer threads, the ring holds the `taps` window rows plus prefetch.
@@ -612,8 +615,7 @@ static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStre
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
-    kern<<<grid, 256 + 32, smem, st>>>(bp);
-    return launch_status();
+    return launch_pdl<BilateralParams>(kern, grid, dim3(256 + 32), smem, st, bp);
 }
 
 // Geometry for the fp32 pair kernel: 256 consumer threads x 2 pixels = 512-column strips.
