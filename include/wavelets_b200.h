@@ -225,6 +225,15 @@ int wb_atrous_axis(const void *in, const void *sub_from, void *out_c, void *out_
                    long long n_inner, int scale, int taps, int dtype, int border, void *stream);
 
 /*
+ * Dense 2-D correlation with a small arbitrary kernel and the symmetric border: the PSF filters of richardson_lucy
+ * (watroo/utils.py:252-255 with the flipped PSF = convolution, :283-286 with the PSF as is = correlation; both
+ * cv2.filter2D(..., (-1,-1), 0, cv2.BORDER_REFLECT)).  `kernel` is a DEVICE array of kh*kw coefficients of the image
+ * dtype, row-major; the anchor is the kernel centre (kh/2, kw/2); flip != 0 applies the kernel rotated by 180 degrees.
+ */
+int wb_filter2d(const void *in, void *out, int H, int W, long long in_pitch, long long out_pitch, const void *kernel,
+                int kh, int kw, int flip, int dtype, void *stream);
+
+/*
  * Synthesis: out = ((p_0 + p_1) + p_2) + ... over `nplanes` planes `plane_stride` elements apart, in the plane
  * dtype and in plane order -- np.sum(coefficients, axis=0) (watroo/utils.py:98, :205).
  */

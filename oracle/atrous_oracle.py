@@ -406,6 +406,92 @@ def compute_noise_weights(name: str, n_scales: int, n_trials: int = 100, bilater
 # ---------------------------------------------------------------------------------------------------------------
 # Synthetic inputs and the parity metric shared by tests and bench  
 # ---------------------------------------------------------------------------------------------------------------
+def filter2d_reflect(img: np.ndarray, kernel: np.ndarray) -> np.ndarray:
+    """cv2.filter2D(img, -1, kernel, (-1,-1), 0, cv2.BORDER_REFLECT) restated: correlation, anchor at the kernel
+    centre (k // 2), half-sample symmetric border, float64 accumulation, one rounding (utils.py:252-255, :283-286)."""
+    kh, kw = kernel.shape
+    h, w = img.shape
+    a64 = img.astype(np.float64)
+    out = np.zeros((h, w), dtype=np.float64)
+    ys, xs = np.arange(h), np.arange(w)
+    for i in range(kh):
+        rows = a64[reflect_index(ys + i - kh // 2, h), :]
+        for j in range(kw):
+            out += float(kernel[i, j]) * rows[:, reflect_index(xs + j - kw // 2, w)]
+    return out.astype(img.dtype)
+
+
+def enhance(img: np.ndarray, name: str = "b3spline", weights=None, denoise=None, noise=None,
+            soft_threshold: bool = True) -> np.ndarray:
+    """utils.py:36-80 for one channel or three (channel first): transform with max(len(weights), len(denoise)) scales,
+    Coefficients.denoise(denoise, weights=weights), sum of the planes.  ``weights`` / ``denoise`` are per-channel
+    lists of lists for a 3-D input (scalars are broadcast like prepare_params, utils.py:10-33)."""
+    def one(ch, wgt, dns, nz):
+        wgt, dns = list(wgt), list(dns)
+        wgt += [1] * (len(dns) - len(wgt))
+        dns += [0] * (len(wgt) - len(dns))
+        planes = atrous_transform(ch, len(wgt), name)
+        if nz is None:
+            nz = get_noise(planes, name)
+        denoise_planes(planes, name, dns, weights=wgt, noise=nz, soft_threshold=soft_threshold)
+        return planes.sum(axis=0)
+
+    def norm(p, nd):
+        if nd == 2:
+            return [] if p is None else ([p] if not isinstance(p, list) else list(p))
+        if not isinstance(p, list):
+            return [[] if p is None else [p]] * nd
+        return [norm(q, 2) for q in p]
+
+    if img.ndim == 2:
+        return one(img, norm(weights, 2), norm(denoise, 2), noise)
+    w3, d3 = norm(weights, 3), norm(denoise, 3)
+    return np.stack([one(img[c], w3[c], d3[c], None if noise is None else noise[c]) for c in range(3)])
+
+
+def richardson_lucy(data: np.ndarray, psf: np.ndarray, iterations: int = 10, denoise_coefficients=(5, 2, 1),
+                    threshold_type: str = "soft", uniform_init: bool = False, persistent_mrs: bool = True) -> np.ndarray:
+    """utils.py:222-290 (fft=False route), B3spline, line by line in terms of the pieces above."""
+    soft = threshold_type == "soft"
+    level = len(denoise_coefficients)
+    name = "b3spline"
+    planes0 = atrous_transform(data, level, name)
+    noise0 = None
+    if uniform_init:
+        psi = np.ones_like(data, np.float32)
+        psi *= data.sum() / data.size
+    else:
+        noise0 = get_noise(planes0, name)
+        denoise_planes(planes0, name, list(denoise_coefficients), noise=noise0, soft_threshold=soft)
+        psi = np.sum(planes0, axis=0)
+    mrs = (np.ones if soft else np.zeros)((level,) + data.shape)
+    for iteration in range(iterations):
+        phi = filter2d_reflect(psi.astype(data.dtype), psf[::-1, ::-1])
+        res = data - phi
+        rc = atrous_transform(res, level, name)
+        nz = noise0 if noise0 is not None else get_noise(rc, name)
+        for s, c in enumerate(denoise_coefficients):
+            sig = significance(rc, name, c, s, nz, soft_threshold=soft)
+            if not soft:
+                if persistent_mrs:
+                    mrs[s][sig] = 1
+                else:
+                    mrs[s] = sig
+                rc[s] *= mrs[s]
+            else:
+                if persistent_mrs:
+                    mrs[s] *= sig
+                else:
+                    mrs[s] = sig
+                rc[s] *= mrs[s] ** (1 / (iteration + 1))
+        res = np.sum(rc, axis=0)
+        res += phi
+        res /= phi
+        conv = filter2d_reflect(res, psf)
+        psi *= conv
+    return psi
+
+
 def solar_like(n: int, seed: int = 2, flux: float = 1.0, dtype=np.float32, m: int | None = None) -> np.ndarray:
     """Synthetic solar-like frame: limb-darkened disk + exponential off-limb corona + 30 Gaussian active regions
     + background, Poisson noise.  Values are integers, hence identical in fp32 and fp64."""

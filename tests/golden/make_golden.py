@@ -54,12 +54,58 @@ def main_nd():
             save(f"transform_nd_{sf}_{dt}", n=np.int64(len(cases)), **out)
 
 
+def gaussian_psf(n, sigma):
+    ax = np.arange(n) - n // 2
+    g = np.exp(-(ax[:, None] ** 2 + ax[None, :] ** 2) / (2 * sigma ** 2))
+    g[0, 1] *= 1.3  # not symmetric: tells convolution from correlation
+    return g / g.sum()
+
+
+def main_callers():
+    """enhance (utils.py:36-80, not exported by the reference) and richardson_lucy (utils.py:222-290)."""
+    from watroo.utils import enhance, richardson_lucy
+    out = {}
+    img = solar_like(96, seed=5, flux=0.05, dtype=np.float32, m=80)
+    out["img"] = img
+    out["enh_a"] = enhance(img.copy(), weights=[1.5, 1.2, 1.0], denoise=[3, 2], scaling_function_class=B3spline)
+    out["enh_b"] = enhance(img.copy(), np.float64(2.0), weights=[2.0], denoise=[4, 2, 1], soft_threshold=False,
+                           scaling_function_class=Triangle)
+    rgb = np.stack([solar_like(64, seed=6 + c, flux=0.05, dtype=np.float64) for c in range(3)])
+    out["rgb"] = rgb
+    out["enh_rgb"] = enhance(rgb.copy(), weights=[[1.2, 1.1], [1.0], [1.5, 1.0, 1.0]], denoise=[[3], [4, 2], [2]])
+    save("enhance", **out)
+
+    out = {}
+    rng = np.random.default_rng(11)
+    truth = solar_like(72, seed=9, flux=0.05, dtype=np.float64, m=88) + 5.0
+    for dt in ("float32", "float64"):
+        psf = gaussian_psf(7, 1.4).astype(dt)
+        import cv2
+        blurred = cv2.filter2D(truth.astype(dt), -1, psf[::-1, ::-1].copy(), None, (-1, -1), 0, cv2.BORDER_REFLECT)
+        data = (blurred + rng.standard_normal(blurred.shape) * 0.5).astype(dt)
+        out[f"data_{dt}"] = data
+        out[f"psf_{dt}"] = psf
+        out[f"soft_{dt}"] = richardson_lucy(data.copy(), psf, iterations=4)
+        out[f"hard_{dt}"] = richardson_lucy(data.copy(), psf, iterations=3, denoise_coefficients=(4, 2),
+                                            threshold_type='hard')
+        out[f"soft_np_{dt}"] = richardson_lucy(data.copy(), psf, iterations=3, persistent_mrs=False)
+    out["uniform_float32"] = richardson_lucy(out["data_float32"].copy(), out["psf_float32"], iterations=3,
+                                             uniform_init=True)
+    even = out["data_float64"][:72, :88]
+    out["fft_float64"] = richardson_lucy(even.copy(), out["psf_float64"], iterations=3, fft=True)
+    save("richardson_lucy", **out)
+
+
 def main():
     assert watroo.__version__ == "0.0.4", watroo.__version__
+    if "--callers" in sys.argv:
+        warnings.simplefilter("ignore")
+        return main_callers()
     warnings.simplefilter("ignore")
     if "--nd" in sys.argv:  # only the 1-D / 3-D fixtures (added later; the others are unchanged)
         return main_nd()
     main_nd()
+    main_callers()
 
     # ---- plain transform: wavelets.py:408-444 via :307 ------------------------------------------------------
     cases = [((64, 64), 4), ((37, 53), 4), ((6, 7), 3), ((96, 64), 6), ((24, 256), 5)]

@@ -267,3 +267,31 @@ def test_backends_agree_fp64():
     b = orc.atrous_transform(img, 5, "b3spline", backend="cv2")
     for p in range(6):
         assert orc.emax(a[p], b[p]) < 1e-13
+
+
+def test_enhance_golden():
+    """enhance (utils.py:36-80): single channel (estimated and given noise, soft and hard) and three channels."""
+    g = load_golden("enhance")
+    img = g["img"]
+    a = orc.enhance(img, "b3spline", weights=[1.5, 1.2, 1.0], denoise=[3, 2])
+    assert orc.emax(a, g["enh_a"]) < 2e-5
+    b = orc.enhance(img, "triangle", weights=[2.0], denoise=[4, 2, 1], noise=np.float64(2.0), soft_threshold=False)
+    assert (np.abs(b - g["enh_b"]) > 1e-4 * np.abs(g["enh_b"]).max()).mean() < 1e-3  # hard mask: rare threshold flips
+    rgb = orc.enhance(g["rgb"], "b3spline", weights=[[1.2, 1.1], [1.0], [1.5, 1.0, 1.0]], denoise=[[3], [4, 2], [2]])
+    assert orc.emax(rgb, g["enh_rgb"]) < 1e-12
+
+
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+def test_richardson_lucy_golden(dt):
+    """richardson_lucy (utils.py:222-290), direct-filter route: soft / hard support, persistent or not, uniform init."""
+    g = load_golden("richardson_lucy")
+    data, psf = g[f"data_{dt}"], g[f"psf_{dt}"]
+    tol = 2e-4 if dt == "float32" else 1e-9
+    assert orc.emax(orc.richardson_lucy(data, psf, iterations=4), g[f"soft_{dt}"]) < tol
+    assert orc.emax(orc.richardson_lucy(data, psf, iterations=3, persistent_mrs=False), g[f"soft_np_{dt}"]) < tol
+    hard = orc.richardson_lucy(data, psf, iterations=3, denoise_coefficients=(4, 2), threshold_type="hard")
+    ref = g[f"hard_{dt}"]
+    assert (np.abs(hard - ref) > tol * np.abs(ref).max()).mean() < 2e-3  # a flipped mask pixel spreads over one PSF
+    if dt == "float32":
+        uni = orc.richardson_lucy(data, psf, iterations=3, uniform_init=True)
+        assert uni.dtype == np.float32 and orc.emax(uni, g["uniform_float32"]) < tol

@@ -220,6 +220,32 @@ __global__ void __launch_bounds__(256) axis_filter_kernel(const T *in, const T *
     }
 }
 
+
+// Dense 2-D correlation with a small arbitrary kernel (the PSF of richardson_lucy, watroo/utils.py:252-255,283-286:
+// cv2.filter2D(img, -1, psf, out, (-1,-1), 0, cv2.BORDER_REFLECT)): anchor at the kernel centre (kh/2, kw/2), half-sample
+// symmetric border.  One thread per pixel; coefficients are warp-uniform loads, pixels coalesced and L1-resident.
+// Products are accumulated in float64 and rounded once (cv2 uses a double DFT for kernels of this size).
+template <typename T>
+__global__ void __launch_bounds__(256) filter2d_kernel(const T *in, T *out, int H, int W, long long in_pitch,
+                                                       long long out_pitch, const T *kern, int kh, int kw, int flip) {
+    const long long n = (long long)H * W;
+    const int ay = kh / 2, ax = kw / 2;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(idx / W), x = (int)(idx % W);
+        double acc = 0.0;
+        for (int i = 0; i < kh; ++i) {
+            const T *row = in + (long long)reflect_any((long long)y + i - ay, H) * in_pitch;
+            const T *krow = kern + (long long)(flip ? kh - 1 - i : i) * kw;
+            for (int j = 0; j < kw; ++j) {
+                const T kv = __ldg(krow + (flip ? kw - 1 - j : j));
+                acc = fma((double)kv, (double)row[reflect_any((long long)x + j - ax, W)], acc);
+            }
+        }
+        out[(long long)y * out_pitch + x] = (T)acc;
+    }
+}
+
 }  // namespace wb
 
 extern "C" {
@@ -324,6 +350,25 @@ int wb_atrous_axis(const void *in, const void *sub_from, void *out_c, void *out_
         if (taps == WB_TRIANGLE) WB_AXIS(double, 3); else WB_AXIS(double, 5);
     }
 #undef WB_AXIS
+    return wb::launch_status();
+}
+
+int wb_filter2d(const void *in, void *out, int H, int W, long long in_pitch, long long out_pitch, const void *kernel,
+                int kh, int kw, int flip, int dtype, void *stream) {
+    if (dtype != WB_F32 && dtype != WB_F64) return WB_EINVAL_DTYPE;
+    if (H < 1 || W < 1 || kh < 1 || kw < 1) return WB_EINVAL_SHAPE;
+    if (!in || !out || !kernel || in == out) return WB_EINVAL_POINTER;
+    if (in_pitch < W || out_pitch < W) return WB_EINVAL_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = wb::grid_for((long long)H * W);
+    if (dtype == WB_F32)
+        wb::filter2d_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float *>(in), reinterpret_cast<float *>(out),
+                                                        H, W, in_pitch, out_pitch,
+                                                        reinterpret_cast<const float *>(kernel), kh, kw, flip);
+    else
+        wb::filter2d_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double *>(in),
+                                                         reinterpret_cast<double *>(out), H, W, in_pitch, out_pitch,
+                                                         reinterpret_cast<const double *>(kernel), kh, kw, flip);
     return wb::launch_status();
 }
 

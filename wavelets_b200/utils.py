@@ -17,7 +17,7 @@ from .scaling import B3spline
 from .wavelets import (AtrousTransform, Coefficients, _Noise, _frame_layout, abs_median_noise, atrous_scale,
                        bilateral_list, plane_moments, synthesis, to_device_image)
 
-__all__ = ["denoise", "wow", "wow_batch", "generalized_anscombe"]
+__all__ = ["denoise", "wow", "wow_batch", "generalized_anscombe", "enhance", "richardson_lucy"]
 
 # Development switch (tests compare the fused one-pass WOW scales against the two-pass route bit for bit).
 FUSED_WOW = True
@@ -367,3 +367,140 @@ def _wow_general(co, weights, whitening, denoise_coefficients, bilateral, soft_t
         gamma_scaled.pow_(1 / gamma)
         recon = (1 - h) * recon + h * gamma_scaled
     return recon, co
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Callers of the transform beyond denoise / wow: enhance, richardson_lucy
+# ---------------------------------------------------------------------------------------------------------------
+def prepare_params(param, ndims):
+    """Per-channel parameter lists of ``enhance`` (watroo/utils.py:10-33), quirks included (a scalar given for a
+    3-channel image becomes the SAME inner list for every channel)."""
+    if ndims == 2:
+        if param is None:
+            return []
+        if type(param) is not list:
+            return [param]
+        return copy.copy(param)
+    if type(param) is not list:
+        return [[], ] * ndims if param is None else [[param], ] * ndims
+    if len(param) != ndims:
+        raise ValueError("Invalid number of parameters")
+    out = [prepare_params(p, 2) for p in param]
+    if None in out:
+        out[out.index(None)] = []
+    return out
+
+
+def enhance(*args, weights=None, denoise=None, soft_threshold=True, out=None, **kwargs):
+    """De-noising and / or enhancement by modification of the wavelet coefficients (watroo/utils.py:36-80): per
+    channel (a 3-D input is three channels, channel first) transform -> ``Coefficients.denoise(denoise,
+    weights=weights)`` -> sum of the planes.  ``args[1]``, when given, is the noise (per channel for 3 channels);
+    ``kwargs`` go to ``AtrousTransform``.  NumPy in -> NumPy out (``out`` is filled when given)."""
+    img = args[0]
+    was_numpy = not isinstance(img, torch.Tensor)
+    ndim = img.ndim
+    channels = [0, 1, 2] if ndim == 3 else [Ellipsis]
+    weights = prepare_params(weights, ndim)
+    denoise_p = prepare_params(denoise, ndim)
+    atrous = AtrousTransform(**kwargs)
+    results = []
+    for c in channels:
+        dns = denoise_p if c is Ellipsis else denoise_p[c]
+        wgt = weights if c is Ellipsis else weights[c]
+        if len(wgt) < len(dns):
+            wgt.extend([1] * (len(dns) - len(wgt)))
+        elif len(dns) < len(wgt):
+            dns.extend([0] * (len(wgt) - len(dns)))
+        coeffs = atrous(img[c], len(wgt))
+        if len(args) == 2:
+            coeffs.noise = args[1] if c is Ellipsis else args[1][c]
+        else:
+            coeffs.noise = coeffs.get_noise()
+        coeffs.denoise(dns, weights=wgt, soft_threshold=soft_threshold)
+        results.append(synthesis(coeffs.data))
+    res = results[0] if ndim != 3 else torch.stack(results)
+    if out is not None:
+        if isinstance(out, torch.Tensor):
+            out.copy_(res)
+        else:
+            out[...] = res.cpu().numpy()
+        return out
+    return _result(res, was_numpy)
+
+
+def _filter2d(img, kernel_dev, flip):
+    """cv2.filter2D(img, -1, kernel, (-1,-1), 0, BORDER_REFLECT) on the device (wb_filter2d); flip rotates the kernel."""
+    lib = _lib.load(require_cuda=True)
+    out = torch.empty_like(img)
+    kh, kw = kernel_dev.shape
+    with torch.cuda.device(img.device):
+        _lib.check(lib.wb_filter2d(img.data_ptr(), out.data_ptr(), img.shape[0], img.shape[1], img.stride(0),
+                                   out.stride(0), kernel_dev.data_ptr(), kh, kw, 1 if flip else 0,
+                                   _lib.dtype_code(img.dtype), _lib.stream_ptr(img.device)))
+    return out
+
+
+def richardson_lucy(data, psf, iterations=10, denoise_coefficients=(5, 2, 1), threshold_type='soft',
+                    uniform_init=False, persistent_mrs=True, fft=False):
+    """Wavelet-regularised Richardson-Lucy deconvolution (watroo/utils.py:222-290), every step on the device.
+
+    Per iteration: phi = psf (*) psi (cv2.filter2D with the flipped PSF and the symmetric border, or a circular FFT
+    convolution when ``fft``), residual ``data - phi`` -> à trous transform -> significance of every scale against the
+    noise of the FIRST transform -> multiresolution support (persistent or not; hard: a mask that only grows, soft: a
+    running product applied with the exponent 1/(iteration+1)) -> synthesis -> ``(res + phi) / phi`` -> correlation
+    with the PSF -> multiplicative update of psi.  Returns psi (NumPy for NumPy input)."""
+    img, was_numpy = to_device_image(data)
+    soft = threshold_type == 'soft'
+    level = len(denoise_coefficients)
+    psf_t = torch.as_tensor(np.ascontiguousarray(psf) if not isinstance(psf, torch.Tensor) else psf)
+    psf_dev = psf_t.to(device=img.device, dtype=img.dtype).contiguous()
+    transform = AtrousTransform()
+    coefficients = transform(img, level)
+    if uniform_init:
+        psi = torch.ones(img.shape, dtype=torch.float32, device=img.device)
+        psi *= (img.sum() / img.numel()).to(torch.float32)
+    else:
+        coefficients.denoise(denoise_coefficients, soft_threshold=soft)
+        psi = synthesis(coefficients.data)
+    mrs = (torch.ones if soft else torch.zeros)((level,) + tuple(img.shape), dtype=torch.float64, device=img.device)
+    if fft:
+        h, w = psi.shape
+        kh, kw = psf_dev.shape
+        padded = torch.zeros_like(psi)
+        padded[h // 2 - kh // 2: h // 2 - kh // 2 + kh, w // 2 - kw // 2: w // 2 - kw // 2 + kw] = psf_dev
+        # np.fft computes in float64 whatever the input dtype: the reference's fft route runs in double from here on
+        fft_psf = torch.fft.rfft2(torch.roll(padded, (h // 2, w // 2), dims=(0, 1)).to(torch.float64))
+        psf_conj = fft_psf.conj()
+    for iteration in range(iterations):
+        if fft:
+            phi = torch.fft.irfft2(torch.fft.rfft2(psi.to(torch.float64)) * fft_psf, s=psi.shape)
+        else:
+            phi = _filter2d(psi.to(img.dtype) if psi.dtype != img.dtype else psi, psf_dev, flip=True)
+        res = img - phi
+        res_coefficients = transform(res, level)
+        res_coefficients._noise = coefficients._noise  # None when uniform_init: then estimated from the residual
+        for s, c in enumerate(denoise_coefficients):
+            sig = res_coefficients.significance(c, s, soft_threshold=soft)
+            plane = res_coefficients.data[s]
+            if not soft:
+                sig = sig.to(torch.bool) if sig.dtype != torch.bool else sig
+                if persistent_mrs:
+                    mrs[s][sig] = 1
+                else:
+                    mrs[s] = sig.to(torch.float64)
+                plane.copy_((plane.to(torch.float64) * mrs[s]).to(plane.dtype))
+            else:
+                if persistent_mrs:
+                    mrs[s] *= sig.to(torch.float64)
+                else:
+                    mrs[s] = sig.to(torch.float64)
+                plane.copy_((plane.to(torch.float64) * mrs[s] ** (1 / (iteration + 1))).to(plane.dtype))
+        res = synthesis(res_coefficients.data)
+        res += phi
+        res /= phi
+        if fft:
+            conv = torch.fft.irfft2(torch.fft.rfft2(res.to(torch.float64)) * psf_conj, s=res.shape)
+        else:
+            conv = _filter2d(res, psf_dev, flip=False)
+        psi = psi * conv.to(psi.dtype)
+    return _result(psi, was_numpy)
