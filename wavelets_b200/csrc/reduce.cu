@@ -17,7 +17,7 @@ namespace wb {
 
 constexpr int kBins = 2048;
 constexpr int kCollectCap = 4096;
-constexpr int kSample = 4096;
+constexpr int kSample = 2048;
 
 template <typename K> struct SelState {
     K lo, hi;                      // inclusive key bracket
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(1024) select_init_kernel(const T *x, long long
         st.done = 0;
         st.res_lo = st.res_hi = 0;
         if (m) {
-            const int margin = 160;  // 5 sigma of the sample-median rank for m = 4096
+            const int margin = 113;  // 5 sigma of the sample-median rank for m = 2048 (sqrt(m) / 2 per sigma)
             st.lo = s[m / 2 - margin];
             st.hi = s[m / 2 + margin];
             st.fresh = 1;
@@ -227,9 +227,36 @@ __global__ void __launch_bounds__(1024) select_decide_kernel(long long n, Worksp
     } else {
         // ---- count pass finished: locate the bins of the two ranks ---------------------------------------------
         const unsigned long long below = st.fresh ? st.acc_below : st.below;
-        if (threadIdx.x == 0) {
-            unsigned long long run = below;
-            for (int i = 0; i < kBins; ++i) { run += ws->hist[i]; cum[i] = run; }  // inclusive prefix
+        {
+            // inclusive prefix of the histogram by the whole block (a serial loop over 2048 bins in global memory took
+            // 60 us): each thread scans its kBins / blockDim consecutive bins, warp shuffles scan the per-thread
+            // totals, one more pass over the warp totals finishes it
+            constexpr int PER = kBins / 1024;
+            static_assert(kBins % 1024 == 0, "decide kernel: 1024 threads x PER bins");
+            __shared__ unsigned long long warp_tot[32];
+            unsigned long long loc[PER];
+            unsigned long long run = 0;
+#pragma unroll
+            for (int e = 0; e < PER; ++e) { run += ws->hist[threadIdx.x * PER + e]; loc[e] = run; }
+            unsigned long long inc = run;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((threadIdx.x & 31) >= o) inc += v;
+            }
+            if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                unsigned long long w = warp_tot[threadIdx.x];
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned long long v = __shfl_up_sync(0xffffffffu, w, o);
+                    if (threadIdx.x >= o) w += v;
+                }
+                warp_tot[threadIdx.x] = w;
+            }
+            __syncthreads();
+            const unsigned long long base = below + (inc - run) + ((threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0ull);
+#pragma unroll
+            for (int e = 0; e < PER; ++e) cum[threadIdx.x * PER + e] = base + loc[e];
         }
         __syncthreads();
         if (threadIdx.x == 0) {
