@@ -336,7 +336,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_rank": 1, "sharding": "one frame per rank, no collective",
                        "l2": "working set 14 planes x 64 MiB = 896 MiB per step >> 126 MB L2 (no flush needed)",
-                       "e2e_steps": e2e_steps, "kernel": "atrous_rows_kernel<float,5> (TMA row pipeline)"},
+                       "e2e_steps": e2e_steps, "kernel": "atrous_rows_lean_kernel<5> (TMA row pipeline, packed fp32x2, PDL)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": launch_ms},

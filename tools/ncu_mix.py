@@ -23,6 +23,8 @@ def main():
         toks = sass.split()
         op = toks[1] if toks and toks[0].startswith("@") else (toks[0] if toks else "?")
         op = op.rstrip(";")
+        if not (r[col["Instructions Executed"]] or "0").isdigit():
+            continue  # repeated header of the next captured launch
         n = int(r[col["Instructions Executed"]] or 0)
         ex[op] += n
         total += n
