@@ -101,6 +101,16 @@ int wb_atrous_scale_band(const void *in, void *out_c, void *out_w, int band_rows
                          int scale, int taps, int dtype, void *stream);
 
 /*
+ * One scale of the plain cascade with the border rule of the reference's RECURSIVE algorithm
+ * (AtrousTransform.atrous_recursive, watroo/wavelets.py:330-406, parity mode of `recursive=True`): the image is seen as
+ * its 2^scale x 2^scale decimated sub-arrays and every tap reflects (half-sample symmetric) at the edges of ITS
+ * sub-array, not of the full image.  Always the generic gather kernel (a parity mode, not a fast path).  The caller
+ * pads the image symmetrically by (taps/2) * 2^(levels-1) first and crops the planes afterwards, as the reference does.
+ */
+int wb_atrous_scale_lattice(const void *in, void *out_c, void *out_w, int H, int W, long long in_pitch,
+                            long long out_c_pitch, long long out_w_pitch, int scale, int taps, int dtype, void *stream);
+
+/*
  * Row-band scale with the halo rows read IN PLACE from the neighbours' band buffers over NVLink (no halo copy, no
  * padded buffer, no reference equivalent).  The running smooth plane c_s of a global_H-row image is distributed over
  * n_peers ranks: rank k owns global rows [peer_y0[k], peer_y0[k+1]) (peer_y0 has n_peers + 1 entries, peer_y0[0] = 0,

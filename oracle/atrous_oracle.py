@@ -71,9 +71,26 @@ def default_backend() -> str:
     return "cv2" if cv2 is not None else "numpy"
 
 
-def sigma_e(name: str, bilateral=None) -> np.ndarray:
-    """wavelets.py:199-219 (2-D branch): the bilateral table is selected whenever ``bilateral is not None``."""
-    return SIGMA_E_2D[name] if bilateral is None else SIGMA_E_2D_BILATERAL[name]
+SIGMA_E_1D = {
+    "triangle": np.array([0.60840933, 0.33000059, 0.21157957, 0.145824, 0.10158388, 0.07155912, 0.04902655,
+                          0.03529812, 0.02409187, 0.01722846, 0.01144442]),
+    "b3spline": np.array([0.72514976, 0.28538683, 0.17901161, 0.12222841, 0.08469601, 0.06027006, 0.04242257,
+                          0.02919823, 0.01805671, 0.01383672, 0.00943623]),
+}
+SIGMA_E_3D = {
+    "triangle": np.array([0.89736751, 0.19514386, 0.06239262, 0.02311278, 0.00939645]),
+    "b3spline": np.array([0.95633954, 0.12491933, 0.03933029, 0.01489642, 0.0064108]),
+}
+
+
+def sigma_e(name: str, bilateral=None, ndim: int = 2) -> np.ndarray:
+    """wavelets.py:199-219: the table of the data's dimensionality; the bilateral table (restated for 2-D only) is
+    selected whenever ``bilateral is not None``."""
+    if bilateral is not None:
+        if ndim != 2:
+            raise ValueError("oracle: bilateral tables are restated for 2-D images only")
+        return SIGMA_E_2D_BILATERAL[name]
+    return {1: SIGMA_E_1D, 2: SIGMA_E_2D, 3: SIGMA_E_3D}[ndim][name]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -168,6 +185,43 @@ def smooth_nd(arr: np.ndarray, name: str, s: int = 0) -> np.ndarray:
     return out.astype(arr.dtype)
 
 
+def atrous_transform_recursive(arr: np.ndarray, level: int, name: str = "b3spline") -> np.ndarray:
+    """AtrousTransform(sf)(arr, level, recursive=True).data for a plain 2-D transform (wavelets.py:330-406), restated
+    without the recursion: symmetric pad by (K // 2) * 2**(level - 1); at scale s every pixel's taps reflect
+    (half-sample symmetric) inside its own decimated sub-array {o, o + 2^s, o + 2*2^s, ...}, which is what filtering
+    each `conv[oy::2^s, ox::2^s]` sub-array with BORDER_REFLECT does; crop the pad at the end."""
+    if arr.dtype in _RECAST:
+        arr = np.float64(arr)
+    taps = TAPS[name]
+    c = len(taps) // 2
+    hw = c * 2 ** (level - 1)
+    cur = np.pad(arr, hw, mode="symmetric").astype(np.float64)
+    planes = np.empty((level + 1,) + cur.shape, dtype=arr.dtype)
+
+    def lattice(n, off, d):
+        i = np.arange(n)
+        o, t = i % d, i // d
+        n_sub = (n - o + d - 1) // d
+        m = np.mod(t + off, 2 * n_sub)
+        return o + np.where(m < n_sub, m, 2 * n_sub - 1 - m) * d
+
+    cur = cur.astype(arr.dtype)
+    for s in range(level):
+        d = 2 ** s
+        a64 = cur.astype(np.float64)
+        rows = np.zeros_like(a64)
+        for j, t in enumerate(taps):
+            rows += t * a64[:, lattice(cur.shape[1], j - c, d)]
+        nxt = np.zeros_like(a64)
+        for i, t in enumerate(taps):
+            nxt += t * rows[lattice(cur.shape[0], i - c, d), :]
+        nxt = nxt.astype(arr.dtype)
+        planes[s] = cur - nxt
+        cur = nxt
+    planes[level] = cur
+    return planes[:, hw:hw + arr.shape[0], hw:hw + arr.shape[1]].copy()
+
+
 def local_variance(arr: np.ndarray, name: str, s: int, backend: str | None = None) -> np.ndarray:
     """sdev_loc(..., variance=True)  (wavelets.py:24-32): S_s[x^2] - (S_s[x])^2, non-positive -> 1e-20.
 
@@ -257,7 +311,7 @@ def get_noise(planes: np.ndarray, name: str, bilateral=None):
 
     dtype flow under NumPy>=2: median keeps the plane dtype, '/0.6745' keeps it (weak Python float), '/sigma_e[0]'
     promotes to float64 (sigma_e is a float64 NumPy scalar)."""
-    return np.median(np.abs(planes[0])) / 0.6745 / sigma_e(name, bilateral)[0]
+    return np.median(np.abs(planes[0])) / 0.6745 / sigma_e(name, bilateral, planes.ndim - 1)[0]
 
 
 def significance(planes: np.ndarray, name: str, sigma, scale: int, noise, bilateral=None,
@@ -270,7 +324,7 @@ def significance(planes: np.ndarray, name: str, sigma, scale: int, noise, bilate
         if type(noise) is not np.ndarray:
             if noise == 0:
                 return np.ones_like(planes[0])
-        thr = sigma * noise * sigma_e(name, bilateral)[scale]
+        thr = sigma * noise * sigma_e(name, bilateral, planes.ndim - 1)[scale]
         if soft_threshold:
             return special.erf(np.abs(planes[scale] / thr))
         return np.abs(planes[scale]) > thr

@@ -51,7 +51,22 @@ def main_nd():
                 out[f"noise{k}"] = np.float64(co.get_noise())
                 co.denoise([3, 2][:level], soft_threshold=True)
                 out[f"den{k}"] = co.data.copy()
+                out[f"dn{k}"] = denoise(arr.copy(), [3, 2, 1][:level], scaling_function=SF[sf])  # utils.denoise, n-D
             save(f"transform_nd_{sf}_{dt}", n=np.int64(len(cases)), **out)
+
+
+def main_recursive():
+    """AtrousTransform(...)(img, level, recursive=True) (wavelets.py:330-406): differs from the standard planes near the
+    borders."""
+    for sf in SF:
+        out = {}
+        cases = [((64, 64), 4, "float64"), ((37, 53), 3, "float64"), ((96, 80), 5, "float32"), ((12, 9), 2, "float32")]
+        for k, (shape, level, dt) in enumerate(cases):
+            img = gaussian(shape, 40 + k, dt) * 3 + 10
+            out[f"in{k}"] = img
+            out[f"out{k}"] = AtrousTransform(SF[sf])(img.copy(), level, recursive=True).data
+            out[f"level{k}"] = np.int64(level)
+        save(f"transform_recursive_{sf}", n=np.int64(len(cases)), **out)
 
 
 def gaussian_psf(n, sigma):
@@ -101,11 +116,14 @@ def main():
     if "--callers" in sys.argv:
         warnings.simplefilter("ignore")
         return main_callers()
+    if "--recursive" in sys.argv:
+        return main_recursive()
     warnings.simplefilter("ignore")
     if "--nd" in sys.argv:  # only the 1-D / 3-D fixtures (added later; the others are unchanged)
         return main_nd()
     main_nd()
     main_callers()
+    main_recursive()
 
     # ---- plain transform: wavelets.py:408-444 via :307 ------------------------------------------------------
     cases = [((64, 64), 4), ((37, 53), 4), ((6, 7), 3), ((96, 64), 6), ((24, 256), 5)]

@@ -74,6 +74,8 @@ def test_transform_nd_golden(sf, dt):
             err = np.abs(out[p].astype(np.float64) - ref[p]).max()
             assert err <= max(TOL[dt] * np.abs(ref[p]).max(), floor), (k, p, err)
         assert orc.emax(out.sum(axis=0), arr) < (1e-5 if dt == "float32" else 1e-13)
+        dn = orc.denoise(arr, [3, 2, 1][:level], sf)
+        assert orc.emax(dn, g[f"dn{k}"]) < (2e-5 if dt == "float32" else 1e-12)
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
@@ -295,3 +297,21 @@ def test_richardson_lucy_golden(dt):
     if dt == "float32":
         uni = orc.richardson_lucy(data, psf, iterations=3, uniform_init=True)
         assert uni.dtype == np.float32 and orc.emax(uni, g["uniform_float32"]) < tol
+
+
+@pytest.mark.parametrize("sf", ["b3spline", "triangle"])
+def test_transform_recursive_golden(sf):
+    """recursive=True (wavelets.py:330-406) restated as a per-sub-lattice border rule: equals the reference's recursion
+    and differs from the standard algorithm near the borders."""
+    g = load_golden(f"transform_recursive_{sf}")
+    for k in range(int(g["n"])):
+        img, level, ref = g[f"in{k}"], int(g[f"level{k}"]), g[f"out{k}"]
+        out = orc.atrous_transform_recursive(img, level, sf)
+        assert out.dtype == ref.dtype and out.shape == ref.shape
+        dt = str(ref.dtype)
+        floor = 4 * np.finfo(ref.dtype).eps * np.abs(img).max()
+        for p in range(level + 1):
+            err = np.abs(out[p].astype(np.float64) - ref[p]).max()
+            assert err <= max(TOL[dt] * np.abs(ref[p]).max(), floor), (k, p, err)
+        std = orc.atrous_transform(img, level, sf)
+        assert max(orc.emax(std[p], ref[p]) for p in range(level + 1)) > 1e-2  # the two algorithms really differ

@@ -65,6 +65,23 @@ def test_golden_transform_1d_and_3d(sf, dt):
         for p in range(level + 1):
             ref = g[f"den{k}"][p]
             assert np.abs(den[p].astype(np.float64) - ref).max() <= tol * max(np.abs(ref).max(), 1e-30), (k, p)
+        dn = wb.denoise(arr.copy(), [3, 2, 1][:level], scaling_function=_sf(sf))  # utils.denoise on n-D input
+        assert dn.shape == arr.shape and dn.dtype == arr.dtype
+        assert orc.emax(dn, g[f"dn{k}"]) < tol
+
+
+@pytest.mark.parametrize("sf", SF_NAMES)
+def test_golden_transform_recursive(sf):
+    """recursive=True reproduces the planes of the reference's recursive algorithm (watroo/wavelets.py:330-406), which
+    differ from the standard ones near the borders."""
+    import wavelets_b200 as wb
+    g = load_golden(f"transform_recursive_{sf}")
+    for k in range(int(g["n"])):
+        img, level, ref = g[f"in{k}"], int(g[f"level{k}"]), g[f"out{k}"]
+        out = wb.AtrousTransform(_sf(sf))(img, level, recursive=True).data.cpu().numpy()
+        assert_planes_close(out, ref, ref.dtype.type, np.abs(img).max(), f"recursive case{k}")
+        std = wb.AtrousTransform(_sf(sf))(img, level).data.cpu().numpy()
+        assert max(orc.emax(std[p], ref[p]) for p in range(level + 1)) > 1e-2
 
 
 def test_reference_kat_ones():

@@ -363,11 +363,13 @@ __global__ void __launch_bounds__(256) atrous_generic_kernel(const ScaleParams p
         const int y = (int)(idx / p.W), x = (int)(idx % p.W);
         int xs[TAPS];
 #pragma unroll
-        for (int k = 0; k < TAPS; ++k) xs[k] = reflect_any((long long)x + (long long)(k - C) * p.d, p.W);
+        for (int k = 0; k < TAPS; ++k)
+            xs[k] = p.lattice ? reflect_lattice(x, k - C, p.d, p.W) : reflect_any((long long)x + (long long)(k - C) * p.d, p.W);
         T acc = T(0);
 #pragma unroll
         for (int i = 0; i < TAPS; ++i) {
-            const T *row = input_row<T>(p, reflect_any(p.gwy0 + y + (long long)(i - C) * p.d, p.Hg)) + foff;
+            const T *row = input_row<T>(p, p.lattice ? reflect_lattice(y, i - C, p.d, p.H)
+                                                     : reflect_any(p.gwy0 + y + (long long)(i - C) * p.d, p.Hg)) + foff;
             T ra = T(0);
 #pragma unroll
             for (int k = 0; k < TAPS; ++k) {
@@ -528,6 +530,35 @@ int wb_atrous_scale(const void *in, void *out_c, void *out_w, int batch, int H, 
                     long long out_w_bstride, int scale, int taps, int dtype, void *stream) {
     return wb::scale_impl(in, out_c, out_w, batch, H, W, in_pitch, in_bstride, out_c_pitch, out_c_bstride,
                           out_w_pitch, out_w_bstride, scale, taps, dtype, (cudaStream_t)stream);
+}
+
+int wb_atrous_scale_lattice(const void *in, void *out_c, void *out_w, int H, int W, long long in_pitch,
+                            long long out_c_pitch, long long out_w_pitch, int scale, int taps, int dtype, void *stream) {
+    int rc = wb::check_common(1, H, W, taps, dtype);
+    if (rc) return rc;
+    if (scale < 0 || scale > 30) return WB_EINVAL_SCALE;
+    if (!in || (!out_c && !out_w) || in == out_c || in == out_w) return WB_EINVAL_POINTER;
+    if (in_pitch < W || (out_c && out_c_pitch < W) || (out_w && out_w_pitch < W)) return WB_EINVAL_ARG;
+    wb::ScaleParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = in; p.out_c = out_c; p.out_w = out_w;
+    p.H = H; p.W = W; p.d = 1 << scale; p.Hg = H;
+    p.in_pitch = in_pitch; p.c_pitch = out_c_pitch; p.w_pitch = out_w_pitch;
+    p.lattice = 1;
+    const long long n = (long long)H * W;
+    long long blocks = (n + 255) / 256;
+    const long long cap = 32LL * wb::device_sm_count();
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)blocks, 1);
+    if (dtype == WB_F32) {
+        if (taps == 3) wb::atrous_generic_kernel<float, 3, wb::OP_TRANSFORM><<<grid, 256, 0, st>>>(p);
+        else wb::atrous_generic_kernel<float, 5, wb::OP_TRANSFORM><<<grid, 256, 0, st>>>(p);
+    } else {
+        if (taps == 3) wb::atrous_generic_kernel<double, 3, wb::OP_TRANSFORM><<<grid, 256, 0, st>>>(p);
+        else wb::atrous_generic_kernel<double, 5, wb::OP_TRANSFORM><<<grid, 256, 0, st>>>(p);
+    }
+    return wb::launch_status();
 }
 
 int wb_atrous_scale_band(const void *in, void *out_c, void *out_w, int band_rows, int W, int global_H,

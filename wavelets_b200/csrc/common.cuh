@@ -51,6 +51,17 @@ __host__ __device__ __forceinline__ int reflect_any(long long i, int n) {
     return (int)(m < n ? m : period - 1 - m);
 }
 
+// Border rule of the reference's RECURSIVE algorithm (watroo/wavelets.py:330-406): at scale s the image is split into
+// the 2^s x 2^s decimated sub-arrays and each one is filtered with the undilated kernel and BORDER_REFLECT at ITS OWN
+// edges -- i.e. tap `off` of pixel i reflects inside the sub-lattice {o, o + d, o + 2d, ...} (o = i mod d) instead of
+// inside the full axis.  Differs from the standard algorithm within (taps/2) * 2^s samples of the borders.
+__host__ __device__ __forceinline__ int reflect_lattice(long long i, int off, int d, int n) {
+    const int o = (int)(i % d);
+    const int t = (int)(i / d);
+    const int n_sub = (n - o + d - 1) / d;
+    return o + reflect_any((long long)t + off, n_sub) * d;
+}
+
 template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }

@@ -35,6 +35,7 @@ struct ScaleParams {
     const double *noise_dev;   // device scalar per frame (from wb_abs_median), or nullptr
     double weight;             // recomposition weight of this plane
     int l2_hints;              // 1: L2 eviction-priority hints on loads / stores (see common.cuh)
+    int lattice;               // generic kernel only: reflect inside the 2^s sub-lattice (recursive algorithm's border rule)
     int suspend_ns;            // lean WOW kernel: suspend-time hint of the row-barrier waits (tuning, WB_MBAR_SUSPEND_NS)
     // --- peer-window mode (wb_atrous_scale_band_p2p): the rows of c_s live in the band buffers of ALL ranks, every
     // one mapped into this process (NVLink peer memory).  Rank k's buffer starts at peer_in[k] and its row 0 is global

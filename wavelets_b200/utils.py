@@ -40,14 +40,15 @@ def denoise(data, weights, scaling_function=B3spline, noise=None, bilateral=None
             anscombe=False):
     """Convenience denoiser (watroo/utils.py:83-102).  NB ``weights`` are the sigma thresholds of each scale and
     their count sets the number of scales; the result is the sum of the thresholded planes."""
-    img, was_numpy = to_device_image(data)
+    img, was_numpy = to_device_image(data, ndim_ok=(1, 2, 3))  # 1-D signals and 3-D volumes: plain cascade only
     if anscombe:
         img = generalized_anscombe(img)
     transform = AtrousTransform(scaling_function, bilateral=bilateral)
     coefficients = transform(img, len(weights))
     coefficients.noise = noise
     coefficients.denoise(weights, soft_threshold=soft_threshold)
-    out = synthesis(coefficients.data)
+    planes = coefficients.data
+    out = synthesis(planes if img.ndim == 2 else planes.reshape(planes.shape[0], 1, -1)).reshape(img.shape)
     if anscombe:
         out = generalized_anscombe(out, inverse=True)
     return _result(out, was_numpy)

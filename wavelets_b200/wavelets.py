@@ -348,18 +348,45 @@ class AtrousTransform:
         and 3-D volumes (2-D smooth of every slice, then the depth pass, watroo/wavelets.py:46-63) run the plain
         cascade through ``wb_atrous_axis``; their bilateral variants are not built.
 
-        ``recursive`` is accepted for signature compatibility and ignored: the reference's recursive variant is a
-        CPU-side optimisation of the same transform (it differs from the standard one only near the borders,
-        watroo/wavelets.py:394-395); the device kernels always implement the standard algorithm."""
+        ``recursive=True`` on a plain 2-D transform reproduces the RESULT of the reference's recursive algorithm
+        (watroo/wavelets.py:330-406; it differs from the standard one near the borders: symmetric pad by
+        ``(taps // 2) * 2**(level-1)``, then every scale reflects inside its decimated sub-arrays) through a parity
+        kernel (``wb_atrous_scale_lattice``), not its CPU-side recursion.  For the bilateral cascade and for 1-D / 3-D
+        inputs the flag is ignored and the standard algorithm runs."""
         img, _ = to_device_image(arr, ndim_ok=(1, 2, 3))
         scaling_function = self.scaling_function_class(img.ndim)
-        if img.ndim == 2:
+        if recursive and img.ndim == 2 and self.bilateral is None and int(level) >= 1:
+            planes = self._run_recursive(img, int(level), scaling_function)
+        elif img.ndim == 2:
             planes = self._run(img, int(level), scaling_function)
         else:
             if self.bilateral is not None:
                 raise NotImplementedError("wavelets_b200: the bilateral cascade is built for 2-D images only")
             planes = self._run_nd(img, int(level), scaling_function)
         return Coefficients(planes, scaling_function, self.bilateral)
+
+    def _run_recursive(self, img, level, scaling_function):
+        """Planes of ``atrous_recursive`` (watroo/wavelets.py:330-406) for a plain 2-D transform, level >= 1."""
+        lib = _lib.load(require_cuda=True)
+        n_taps = len(scaling_function.coefficients_1d)
+        hw = (n_taps // 2) * 2 ** (level - 1)
+        h, w = img.shape
+        # np.pad(arr, hw, mode='symmetric') (:394-395), any number of reflections
+        def sym(n):
+            i = torch.arange(-hw, n + hw, device=img.device)
+            m = torch.remainder(i, 2 * n)
+            return torch.where(m < n, m, 2 * n - 1 - m)
+        cur = img[sym(h)][:, sym(w)].contiguous()
+        hp, wp = cur.shape
+        full = torch.empty((level + 1, hp, wp), dtype=img.dtype, device=img.device)
+        code, taps = _lib.dtype_code(img.dtype), scaling_function.taps_code
+        with torch.cuda.device(img.device):
+            for s in range(level):
+                nxt = full[level] if s == level - 1 else torch.empty_like(cur)
+                _lib.check(lib.wb_atrous_scale_lattice(cur.data_ptr(), nxt.data_ptr(), full[s].data_ptr(), hp, wp, wp, wp,
+                                                       wp, s, taps, code, _lib.stream_ptr(img.device)))
+                cur = nxt
+        return full[:, hw:hw + h, hw:hw + w].contiguous()
 
     def _run_nd(self, arr, level, scaling_function):
         """Plain cascade of a 1-D signal or a 3-D volume: planes ``(level + 1, *arr.shape)``."""
