@@ -251,6 +251,14 @@ def test_noise_weights(sf):
     assert np.abs(out2 / table - 1).max() < 0.03, out2 / table
     out3 = _sf(sf)(2).compute_noise_weights(6, n_trials=3, seed=11)
     assert np.array_equal(out2, out3)
+    # 1-D signals and 3-D volumes (wavelets.py:225: side 11 * 2**n in every dimension) against their recorded tables;
+    # the 1-D fields are short (11 * 2**n samples), hence the many trials and the looser bound
+    w1 = _sf(sf)(1).compute_noise_weights(5, n_trials=400, seed=5)
+    assert w1.shape == (5,) and np.abs(w1 / _sf(sf)(1).sigma_e()[:5] - 1).max() < 0.08, w1
+    # (at side 88 the symmetric border weighs on scale 2: the oracle's own Monte-Carlo gives 0.935 x the table entry)
+    w3 = _sf(sf)(3).compute_noise_weights(3, n_trials=2, seed=7)
+    assert w3.shape == (3,) and np.abs(w3 / _sf(sf)(3).sigma_e()[:3] - 1).max() < 0.10, w3
+    assert np.abs(w3[:2] / _sf(sf)(3).sigma_e()[:2] - 1).max() < 0.03, w3
 
 
 @pytest.mark.parametrize("dt,bilateral", [(np.float32, None), (np.float32, 1), (np.float64, None)])

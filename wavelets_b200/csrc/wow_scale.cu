@@ -7,15 +7,18 @@
 // the 5*sizeof(T) of K1 followed by K3.
 //
 // Same chain walk as K1 (see atrous_scale.cu): the local power uses the SAME dilation as the smooth, so it only couples
-// rows of the same chain.  A thread block walks a chain segment once, with two specialised halves that form a
-// pipeline through shared memory (each half owns every column vector of the row, NG vectors per thread):
-//   SMOOTH warps (first half):  wait for input row j (TMA, mbarrier) -> row pass -> column pass (running partial
-//       sums in registers) -> c_{s+1} row (128-bit store, only rows of the segment) -> w_s = raw - c_{s+1} into the
-//       shared-memory w ring -> arrive "w row full"; release input row j-C.  Lane 0 of warp 0 is also the TMA loader.
-//   POWER warps (second half):  wait "w row full" -> row pass over the squares -> column pass -> P; epilogue with the
-//       raw w_s of the centre row (same ring) -> streaming 128-bit store of w'_s; release w row t-C.
-// All hand-offs are mbarriers with one arrival per warp, so warps drift freely (no block-wide barrier in the loop), and
-// with one ring of partial sums per thread both halves fit in 64 registers: 1024 threads = 32 warps per SM.
+// rows of the same chain.  A thread block (512 threads, every one a consumer, NG = 2 column vectors per thread; thread
+// 0 also issues the TMA row loads) walks a chain segment once; per step j
+//   A  input row j lands (TMA, mbarrier) -> row pass -> running column sums in registers -> c_{s+1} of row j-C:
+//      128-bit store (rows of the segment only); w_s = raw - c_{s+1} goes to a shared-memory ring (other threads need
+//      it for the x taps of the power filter); one mbarrier arrival per warp;
+//   B  (one step later) wait on that mbarrier -- a SPLIT-PHASE barrier: warps drift by a step instead of marching in
+//      lock-step -> row pass over the squares of the w row -> second set of running sums -> P; epilogue with the raw
+//      w_s of the centre row (same ring) -> streaming 128-bit store of w'_s.  The same barrier completion tells thread
+//      0 which input slot is free for the next TMA load.
+// Two kernels implement it: wow_rows_kernel (any dtype / width up to one 16 KiB row; keeps a separate w^2 ring and a
+// third phase C) and wow_rows_lean_kernel (fp32 rows wider than 2048 columns: unrolled ring, immediate addressing,
+// packed fp32x2, squares on the fly -- see the comment above it).
 // Rows outside the image are symmetric reflections: the loader fetches the reflected rows; because the symmetric
 // extension commutes with the symmetric smooth, c_{s+1} / w_s evaluated at such a virtual row equal their reflected
 // values (up to the rounding of a reversed summation order), which is what the power filter needs at the border.

@@ -548,20 +548,25 @@ def randn_field(shape, seed, offset=0, device=None):
 
 def noise_weights(scaling_function, n_scales, n_trials=100, bilateral=None, fields=None, seed=None):
     """compute_noise_weights (watroo/wavelets.py:221-229) on the device; see AbstractScalingFunction."""
-    if scaling_function.n_dim != 2:
-        raise NotImplementedError("wavelets_b200 covers the 2-D path only")
+    nd = scaling_function.n_dim
+    if nd != 2 and bilateral is not None:
+        raise NotImplementedError("wavelets_b200: the bilateral cascade is built for 2-D images only")
     transform = AtrousTransform(scaling_function.__class__, bilateral=bilateral)
     side = len(scaling_function.sigma_e_1d) * 2 ** n_scales
     if seed is None:
         seed = int(np.random.SeedSequence().entropy % (2 ** 63))
     total = torch.zeros(n_scales, dtype=torch.float64, device=_device())
     it = iter(fields) if fields is not None else None
-    quads = (side * side + 3) // 4
+    quads = (side ** nd + 3) // 4
     for trial in range(n_trials):
         if it is not None:
-            field, _ = to_device_image(next(it))
+            field, _ = to_device_image(next(it), ndim_ok=(nd,))
         else:
-            field = randn_field((side, side), seed, offset=trial * quads)
-        planes = transform._run(field, n_scales, scaling_function)
-        total += plane_moments(planes[:-1])[:, 2]
+            field = randn_field((side,) * nd, seed, offset=trial * quads)
+        if nd == 2:
+            planes = transform._run(field, n_scales, scaling_function)
+            total += plane_moments(planes[:-1])[:, 2]
+        else:  # 1-D signals / 3-D volumes: one "frame" of side**nd samples per plane
+            planes = transform._run_nd(field, n_scales, scaling_function)
+            total += plane_moments(planes[:-1].reshape(n_scales, 1, -1))[:, 2]
     return (total / n_trials).cpu().numpy()
