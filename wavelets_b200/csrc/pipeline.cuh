@@ -36,7 +36,6 @@ struct ScaleParams {
     double weight;             // recomposition weight of this plane
     int l2_hints;              // 1: L2 eviction-priority hints on loads / stores (see common.cuh)
     int lattice;               // generic kernel only: reflect inside the 2^s sub-lattice (recursive algorithm's border rule)
-    int suspend_ns;            // lean WOW kernel: suspend-time hint of the row-barrier waits (tuning, WB_MBAR_SUSPEND_NS)
     // --- peer-window mode (wb_atrous_scale_band_p2p): the rows of c_s live in the band buffers of ALL ranks, every
     // one mapped into this process (NVLink peer memory).  Rank k's buffer starts at peer_in[k] and its row 0 is global
     // row peer_y0[k]; peer_y0[n_peers] = Hg.  n_peers == 0: a single window `in` (everything above).
@@ -321,8 +320,7 @@ template <int OFF> __device__ __forceinline__ P4 lds_p4_imm(uint32_t a) {
 template <int OFF> __device__ __forceinline__ void sts_p4_imm(uint32_t a, const P4 &v) {
     asm volatile("st.shared.v2.b64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "l"(v.lo), "l"(v.hi) : "memory");
 }
-template <int OFF> __device__ __forceinline__ void mbar_wait_imm(uint32_t bar0, uint32_t parity,
-                                                                 uint32_t suspend_ns = kMbarSuspendHintNs) {
+template <int OFF> __device__ __forceinline__ void mbar_wait_imm(uint32_t bar0, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -331,7 +329,7 @@ template <int OFF> __device__ __forceinline__ void mbar_wait_imm(uint32_t bar0, 
         "@p bra WB_LDONE_%=;\n"
         "bra WB_LWAIT_%=;\n"
         "WB_LDONE_%=:\n"
-        "}\n" ::"r"(bar0), "n"(OFF), "r"(parity), "r"(suspend_ns)
+        "}\n" ::"r"(bar0), "n"(OFF), "r"(parity), "r"(kMbarSuspendHintNs)
         : "memory");
 }
 template <int OFF> __device__ __forceinline__ void mbar_arrive_imm(uint32_t bar0) {

@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
         }
         if (j > 2 * C) {
             constexpr int SP = (I - 1 - 2 * C + 16) & (kWRing - 1);  // w row j-1-2C (all threads' columns)
-            mbar_wait_imm<8 * SP>(wbar0, ((uint32_t)(j - 1 - 2 * C) >> 2) & 1u, (uint32_t)p.suspend_ns);
+            mbar_wait_imm<8 * SP>(wbar0, ((uint32_t)(j - 1 - 2 * C) >> 2) & 1u);
             if (tid == 0) {
                 // every warp is past part A of step j-1: input rows <= j-1-C are free
                 while (next_load < n_load && next_load - kInRing <= j - 1 - C) issue_load();
@@ -551,14 +551,7 @@ static int fill_wow_params(ScaleParams &p, const void *in, void *out_c, void *ou
         }
         p.l2_hints = l2_hints_enabled() ? v : 0;
     }
-    {
-        static int ns = -1;
-        if (ns < 0) {
-            const char *e = getenv("WB_MBAR_SUSPEND_NS");
-            ns = e ? atoi(e) : (int)kMbarSuspendHintNs;
-        }
-        p.suspend_ns = ns;
-    }
+
     return WB_OK;
 }
 
