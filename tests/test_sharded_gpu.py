@@ -18,7 +18,14 @@ def test_band_window_equals_rows_of_full_transform(dt):
     kernel, and must reproduce the unsharded cascade bit for bit (incl. bands whose halo exceeds their height)."""
     import wavelets_b200 as wb
     from wavelets_b200.sharded import _cuda_band_scale, band_range, halo_rows
-    h, w, level, world = 384, 512, 6, 3
+    # 512 columns: generic row-pipeline kernel; 2048 columns: the lean fp32 kernel (rows wider than 1024)
+    for h, w, level, world in ((384, 512, 6, 3), (192, 2048, 5, 2)):
+        _band_window_case(dt, h, w, level, world)
+
+
+def _band_window_case(dt, h, w, level, world):
+    import wavelets_b200 as wb
+    from wavelets_b200.sharded import _cuda_band_scale, band_range, halo_rows
     gen = torch.Generator(device="cuda").manual_seed(1)
     img = torch.randn((h, w), generator=gen, device="cuda", dtype=torch.float32).to(dt)
     for sf in (wb.B3spline, wb.Triangle):
@@ -45,7 +52,7 @@ def test_band_window_equals_rows_of_full_transform(dt):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.float64])
-@pytest.mark.parametrize("shape,world", [((384, 512), 3), ((200, 264), 5), ((96, 130), 2)])
+@pytest.mark.parametrize("shape,world", [((384, 512), 3), ((200, 264), 5), ((96, 130), 2), ((160, 2048), 3)])
 def test_peer_window_scale_equals_rows_of_full_transform(dt, shape, world):
     """wb_atrous_scale_band_p2p with the ranks' band buffers as separate allocations of ONE device (the address
     arithmetic is the same as with NVLink-mapped peers): every band of every scale must equal the unsharded cascade
