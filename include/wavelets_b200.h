@@ -111,6 +111,17 @@ int wb_atrous_scale_lattice(const void *in, void *out_c, void *out_w, int H, int
                             long long out_c_pitch, long long out_w_pitch, int scale, int taps, int dtype, void *stream);
 
 /*
+ * wb_wow_whiten_scale on ONE ROW BAND of a taller image (row-band sharded WOW, no reference equivalent): same window
+ * conventions as wb_atrous_scale_band -- `w_raw` holds the band's raw detail rows plus the halo rows of the
+ * neighbours (c * 2^scale above and below, filled by the caller), reflections about global_H.  `noise_dev`, when
+ * given, points to ONE device scalar (frame 0).
+ */
+int wb_wow_whiten_scale_band(const void *w_raw, void *out, int band_rows, int W, int global_H, long long band_y0,
+                             long long in_row_offset, long long in_pitch, long long out_row_offset, long long out_pitch,
+                             int scale, int taps, int dtype, int sig_mode, double sigma, double sigma_e,
+                             double noise_host, const double *noise_dev, double weight, void *stream);
+
+/*
  * Row-band scale with the halo rows read IN PLACE from the neighbours' band buffers over NVLink (no halo copy, no
  * padded buffer, no reference equivalent).  The running smooth plane c_s of a global_H-row image is distributed over
  * n_peers ranks: rank k owns global rows [peer_y0[k], peer_y0[k+1]) (peer_y0 has n_peers + 1 entries, peer_y0[0] = 0,

@@ -101,3 +101,82 @@ def test_banded_cascade_over_gloo(tmp_path, world, height, width, level, sf):
     assert got.shape == want.shape
     for p in range(level + 1):
         assert orc.emax(got[p], want[p]) < 1e-13, (p, orc.emax(got[p], want[p]))
+
+
+class _OracleWowBackend:
+    """Per-band arithmetic of BandedWow with the oracle's formulas (float64) -- the CUDA kernels' stand-in on CPU."""
+
+    scale = staticmethod(_oracle_band_scale)
+
+    @staticmethod
+    def whiten(ext_w, pad, out, rows, width, height, y0, scale, taps_code, sig_mode, sigma, sigma_e, noise, weight):
+        from scipy import special
+        name = "b3spline" if taps_code == 5 else "triangle"
+        taps = orc.TAPS[name]
+        c, d = len(taps) // 2, 2 ** scale
+        a = ext_w.numpy()
+        xs = np.arange(width)
+        gy = np.arange(y0, y0 + rows)
+        power = np.zeros((rows, width))
+        for i, ti in enumerate(taps):
+            src = a[orc.reflect_index(gy + (i - c) * d, height) - y0 + pad] ** 2
+            rowf = np.zeros((rows, width))
+            for j, tj in enumerate(taps):
+                rowf += tj * src[:, orc.reflect_index(xs + (j - c) * d, width)]
+            power += ti * rowf
+        assert np.isfinite(power).all(), "a halo row of w_s that was never exchanged has been read"
+        power[power <= 0] = 1e-15
+        w = a[pad:pad + rows].copy()
+        if sig_mode == 1:
+            w *= special.erf(np.abs(w / (sigma * noise * sigma_e)))
+        elif sig_mode == 2:
+            w *= np.abs(w) > sigma * noise * sigma_e
+        out[:] = torch.from_numpy(w * (weight / np.sqrt(power)))
+
+    @staticmethod
+    def moments(plane):
+        p = plane.numpy()
+        return torch.tensor([p.size, p.mean(), p.var()], dtype=torch.float64)
+
+    @staticmethod
+    def synthesis(planes):
+        return planes.sum(dim=0)
+
+
+def _wow_worker(rank, world, port, height, width, kw, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import wavelets_b200 as wb
+        from wavelets_b200.sharded import BandedWow
+        img = orc.solar_like(height, seed=4, flux=0.05, dtype=np.float64, m=width)
+        y0, y1 = band_range(height, rank, world)
+        recon, planes = BandedWow(wb.B3spline, backend=_OracleWowBackend, poison=True)(
+            torch.from_numpy(img[y0:y1].copy()), height, **kw)
+        np.save(os.path.join(result_dir, f"recon{rank}.npy"), recon.numpy())
+        np.save(os.path.join(result_dir, f"planes{rank}.npy"), planes.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,height,width,kw", [
+    (2, 64, 48, dict()),
+    (3, 72, 64, dict(n_scales=3, weights=[1.5, 1.0, 0.5], denoise_coefficients=[4, 2], noise=1.7)),
+    (3, 48, 40, dict(denoise_coefficients=[3], noise=2.0, soft_threshold=False)),
+])
+def test_banded_wow_over_gloo(tmp_path, world, height, width, kw):
+    """Row-band WOW over gloo (two halo exchanges per scale + the all-gather of the residual moments) reproduces the
+    unsharded oracle wow(): recon and every whitened plane."""
+    mp.spawn(_wow_worker, args=(world, _free_port(), height, width, kw, str(tmp_path)), nprocs=world, join=True)
+    img = orc.solar_like(height, seed=4, flux=0.05, dtype=np.float64, m=width)
+    recon, planes, _ = orc.wow(img, "b3spline", backend="numpy", **kw)
+    got_p = np.concatenate([np.load(tmp_path / f"planes{r}.npy") for r in range(world)], axis=1)
+    got_r = np.concatenate([np.load(tmp_path / f"recon{r}.npy") for r in range(world)], axis=0)
+    assert got_p.shape == planes.shape
+    for p in range(planes.shape[0]):
+        assert orc.emax(got_p[p], planes[p]) < 1e-11, (p, orc.emax(got_p[p], planes[p]))
+    assert orc.emax(got_r, recon) < 1e-11
+    with pytest.raises(NotImplementedError):
+        from wavelets_b200.sharded import BandedWow
+        BandedWow()(torch.zeros((8, 64)), 8, denoise_coefficients=[3])

@@ -81,6 +81,36 @@ def test_peer_window_scale_equals_rows_of_full_transform(dt, shape, world):
                 assert torch.equal(out_c, c[s + 1][y0s[rank]:y0s[rank + 1]]), (sf.__name__, rank, s)
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_band_whitening_equals_rows_of_unsharded_whitening(dt):
+    """wb_wow_whiten_scale_band on every band of every scale (halo rows of the raw w_s copied in by hand) equals the
+    rows of wb_wow_whiten_scale on the whole plane bit for bit, for the three significance modes."""
+    import wavelets_b200 as wb
+    from wavelets_b200 import _lib, utils
+    from wavelets_b200.sharded import _CudaWowBackend, band_range, halo_rows
+    lib = _lib.load(require_cuda=True)
+    for h, w, world in ((200, 264, 3), (128, 2048, 2)):
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        img = torch.randn((h, w), generator=gen, device="cuda", dtype=torch.float32).to(dt) * 3
+        sf = wb.B3spline(2)
+        raw = wb.AtrousTransform(wb.B3spline)(img, 5).data
+        for s in range(5):
+            for mode, noise in ((0, 0.0), (1, 0.9), (2, 1.3)):
+                ref = torch.empty_like(raw[s])
+                utils._whiten_scale(lib, raw[s].contiguous(), ref, s, sf, mode, 2.5, 0.3,
+                                    utils._Noise(host=noise) if mode else utils._Noise(), 1.25)
+                halo = halo_rows(s, 5)
+                for rank in range(world):
+                    y0, y1 = band_range(h, rank, world)
+                    rows = y1 - y0
+                    ext = torch.full((rows + 2 * halo, w), float("nan"), dtype=dt, device="cuda")
+                    g0, g1 = max(0, y0 - halo), min(h, y1 + halo)
+                    ext[halo + (g0 - y0): halo + (g1 - y0)] = raw[s][g0:g1]
+                    out = torch.empty((rows, w), dtype=dt, device="cuda")
+                    _CudaWowBackend.whiten(ext, halo, out, rows, w, h, y0, s, sf.taps_code, mode, 2.5, 0.3, noise, 1.25)
+                    assert torch.equal(out, ref[y0:y1]), (h, w, s, mode, rank)
+
+
 def test_peer_window_rejects_bad_arguments():
     from wavelets_b200.sharded import band_scale_p2p
     a = torch.zeros((8, 64), device="cuda")
@@ -101,3 +131,4 @@ def test_banded_two_ranks_nccl():
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
     assert '"bit_identical": true' in proc.stdout
     assert "p2p   banded == unsharded on all ranks: True" in proc.stdout  # in-kernel NVLink halo reads
+    assert "banded wow == unsharded two-pass wow on all ranks: True" in proc.stdout

@@ -85,6 +85,30 @@ def main():
                 del full, img
             del band
             torch.cuda.empty_cache()
+    # ---- WOW on bands (two halo exchanges per scale + all-gather of the residual moments) vs the unsharded two-pass wow
+    if not args.no_check and not args.quick:
+        from wavelets_b200 import utils
+        from wavelets_b200.sharded import BandedWow
+        for dt in (torch.float32, torch.float64):
+            gen = torch.Generator(device=dev).manual_seed(11)
+            img = (torch.randn((h, w), generator=gen, device=dev, dtype=torch.float32) * 5 + 40).to(dt)
+            kw = dict(n_scales=min(args.levels, 6), weights=[1.5, 1.2], denoise_coefficients=[4, 2], noise=1.5)
+            recon_b, planes_b = BandedWow(wb.B3spline, poison=True)(img[y0:y1].contiguous(), h, **kw)
+            utils.FUSED_WOW = False
+            try:
+                recon, co = wb.wow(img, **kw)
+            finally:
+                utils.FUSED_WOW = True
+            L = planes_b.shape[0] - 1
+            same = torch.equal(planes_b[:L], co.data[:L, y0:y1])
+            tol = 1e-5 if dt == torch.float32 else 1e-12
+            close = ((recon_b - recon[y0:y1]).abs().max() <= tol * recon.abs().max()) and \
+                    ((planes_b[L] - co.data[L, y0:y1]).abs().max() <= tol * co.data[L].abs().max())
+            flag = torch.tensor([1 if (same and bool(close)) else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = ok and bool(flag.item())
+            if rank == 0:
+                print(f"{str(dt):14s} banded wow == unsharded two-pass wow on all ranks: {bool(flag.item())}", flush=True)
     if rank == 0:
         line = json.dumps({"check": "banded_vs_unsharded", "n_gpus": world, "side": [h, w], "levels": args.levels,
                            "bit_identical": ok if not args.no_check else None, "timing": results})

@@ -638,6 +638,28 @@ int wb_wow_whiten_scale(const void *w_raw, void *out, int batch, int H, int W, l
     return wb::dispatch_typed<wb::OP_WHITEN>(p, batch, scale, taps, dtype, (cudaStream_t)stream);
 }
 
+int wb_wow_whiten_scale_band(const void *w_raw, void *out, int band_rows, int W, int global_H, long long band_y0,
+                             long long in_row_offset, long long in_pitch, long long out_row_offset, long long out_pitch,
+                             int scale, int taps, int dtype, int sig_mode, double sigma, double sigma_e,
+                             double noise_host, const double *noise_dev, double weight, void *stream) {
+    int rc = wb::check_common(1, band_rows, W, taps, dtype);
+    if (rc) return rc;
+    if (scale < 0 || scale > 30) return WB_EINVAL_SCALE;
+    if (!w_raw || !out || w_raw == out) return WB_EINVAL_POINTER;
+    if (global_H < band_rows || band_y0 < 0 || band_y0 + band_rows > global_H || in_pitch < W || out_pitch < W ||
+        sig_mode < 0 || sig_mode > 2)
+        return WB_EINVAL_ARG;
+    wb::ScaleParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = w_raw; p.out_c = nullptr; p.out_w = out;
+    p.H = band_rows; p.W = W; p.d = 1 << scale; p.Hg = global_H;
+    p.gwy0 = band_y0; p.row_off_in = in_row_offset; p.row_off_w = out_row_offset;
+    p.in_pitch = in_pitch; p.w_pitch = out_pitch;
+    p.sig_mode = sig_mode; p.sigma = sigma; p.sigma_e = sigma_e;
+    p.noise_host = noise_host; p.noise_dev = noise_dev; p.weight = weight;
+    return wb::dispatch_typed<wb::OP_WHITEN>(p, 1, scale, taps, dtype, (cudaStream_t)stream);
+}
+
 int wb_atrous_transform(const void *in, void *planes, void *scratch, int batch, int H, int W, long long in_pitch,
                         long long in_bstride, int levels, int taps, int dtype, void *stream) {
     int rc = wb::check_common(batch, H, W, taps, dtype);

@@ -26,7 +26,7 @@ from . import _lib
 from .scaling import B3spline
 
 __all__ = ["frame_shard", "band_range", "halo_rows", "exchange_plan", "exchange_halos", "BandedTransform",
-           "band_scale_p2p", "PeerBandBuffers"]
+           "band_scale_p2p", "PeerBandBuffers", "BandedWow"]
 
 
 def frame_shard(n_frames: int, rank: int, world: int) -> range:
@@ -220,3 +220,105 @@ class BandedTransform:
             out_c, out_pad = (planes[level], 0) if last else (nxt, pad)
             self.scale_fn(cur, pad, out_c, out_pad, planes[s], rows, width, global_height, y0, s, sf.taps_code)
         return planes
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# WOW of ONE image sharded by row bands ("WOW on bands additionally needs tiny all-reduces")
+# ---------------------------------------------------------------------------------------------------------------
+class _CudaWowBackend:
+    """Per-band arithmetic of BandedWow on the device (the gloo tests substitute an oracle backend)."""
+
+    scale = staticmethod(_cuda_band_scale)
+
+    @staticmethod
+    def whiten(ext_w, pad, out, rows, width, height, y0, scale, taps_code, sig_mode, sigma, sigma_e, noise, weight):
+        lib = _lib.load(require_cuda=True)
+        with torch.cuda.device(ext_w.device):
+            _lib.check(lib.wb_wow_whiten_scale_band(ext_w.data_ptr(), out.data_ptr(), rows, width, height, y0, pad,
+                                                    ext_w.stride(0), 0, out.stride(0), scale, taps_code,
+                                                    _lib.dtype_code(ext_w.dtype), sig_mode, float(sigma), float(sigma_e),
+                                                    float(noise), None, float(weight), _lib.stream_ptr(ext_w.device)))
+
+    @staticmethod
+    def moments(plane):
+        """(count, mean, population variance) of this rank's rows, float64 tensor on the plane's device."""
+        from .wavelets import plane_moments
+        m = plane_moments(plane)[0]
+        return torch.stack([torch.tensor(float(plane.numel()), dtype=torch.float64, device=plane.device), m[0], m[1]])
+
+    @staticmethod
+    def synthesis(planes):
+        from .wavelets import synthesis
+        return synthesis(planes)
+
+
+class BandedWow:
+    """``wow(image)`` (watroo/utils.py:105-219, plain cascade, whitening on) of ONE image sharded by row bands.
+
+    Per scale: halo exchange of ``c_s`` -> band scale kernel (``c_{s+1}``, raw ``w_s``) -> halo exchange of the raw
+    ``w_s`` (the local power is a second dilated filter) -> band whitening kernel.  The residual plane needs the
+    population std of the WHOLE plane: every rank contributes (count, mean, variance) of its rows, combined after one
+    all-gather of three doubles.  The synthesis sum is local.  Thresholds (``denoise_coefficients``) need the noise as an
+    argument: the MAD estimate of the reference is an exact median over the whole plane, whose distributed form is not
+    built.  Returns ``(recon_band, planes_band)``; the planes equal the two-pass single-device route bit for bit, the
+    residual plane up to the rounding of the combined std."""
+
+    def __init__(self, scaling_function_class=B3spline, group=None, backend=None, poison=False):
+        self.scaling_function_class = scaling_function_class
+        self.group = group
+        self.backend = backend or _CudaWowBackend
+        self.poison = poison
+
+    def __call__(self, band, global_height, n_scales=None, weights=(), denoise_coefficients=(), noise=None,
+                 soft_threshold=True):
+        from .utils import _wow_plan
+        sf = self.scaling_function_class(2)
+        n_taps = len(sf.coefficients_1d)
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        y0, y1 = band_range(global_height, rank, world)
+        rows, width = band.shape
+        assert rows == y1 - y0, f"rank {rank}: band has {rows} rows, expected {y1 - y0}"
+        level, _, wts, dns = _wow_plan((global_height, width), self.scaling_function_class, n_scales, list(weights),
+                                       list(denoise_coefficients), None)
+        if any(d != 0 for d in dns[:level]) and noise is None:
+            raise NotImplementedError("BandedWow: pass noise= (the distributed exact MAD estimate is not built)")
+        sigma_e = sf.sigma_e()
+        be = self.backend
+        planes = torch.empty((level + 1, rows, width), dtype=band.dtype, device=band.device)
+        pad = min(halo_rows(max(level - 1, 0), n_taps), global_height) if world > 1 else 0
+        fill = float("nan") if self.poison else 0.0
+        ext = [torch.full((rows + 2 * pad, width), fill, dtype=band.dtype, device=band.device) for _ in range(2)]
+        wext = torch.full((rows + 2 * pad, width), fill, dtype=band.dtype, device=band.device)
+        ext[0][pad:pad + rows].copy_(band)
+        if level == 0:
+            planes[0].copy_(band)
+        for s in range(level):
+            cur, nxt = ext[s & 1], ext[(s + 1) & 1]
+            halo = min(halo_rows(s, n_taps), pad)
+            if world > 1:
+                exchange_halos(cur, pad, global_height, halo, self.group)
+            last = s == level - 1
+            out_c, out_pad = (planes[level], 0) if last else (nxt, pad)
+            be.scale(cur, pad, out_c, out_pad, wext[pad:pad + rows], rows, width, global_height, y0, s, sf.taps_code)
+            if world > 1:
+                exchange_halos(wext, pad, global_height, halo, self.group)
+            d = dns[s]
+            mode = (1 if soft_threshold else 2) if d != 0 else 0
+            be.whiten(wext, pad, planes[s], rows, width, global_height, y0, s, sf.taps_code, mode, d,
+                      sigma_e[s] if d != 0 else 1.0, noise if d != 0 else 0.0, wts[s])
+        # residual plane: c_L *= wt_L / std(c_L) over the WHOLE plane (utils.py:185-189, :203)
+        mine = be.moments(planes[level])
+        if world > 1:
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine, group=self.group)
+        else:
+            parts = [mine]
+        stat = torch.stack(parts).to(torch.float64)
+        n_tot = stat[:, 0].sum()
+        mean = (stat[:, 0] * stat[:, 1]).sum() / n_tot
+        var = (stat[:, 0] * (stat[:, 2] + (stat[:, 1] - mean) ** 2)).sum() / n_tot  # no E[x^2] - mean^2 cancellation
+        sd = torch.sqrt(torch.clamp(var, min=0)).to(band.dtype)
+        sd = torch.where(sd <= 0, torch.full_like(sd, 1e-15), sd)
+        planes[level].mul_((torch.tensor(wts[level], dtype=band.dtype, device=sd.device) / sd).to(planes.device))
+        return be.synthesis(planes), planes
