@@ -164,6 +164,7 @@ def _wow_worker(rank, world, port, height, width, kw, result_dir):
     (2, 64, 48, dict()),
     (3, 72, 64, dict(n_scales=3, weights=[1.5, 1.0, 0.5], denoise_coefficients=[4, 2], noise=1.7)),
     (3, 48, 40, dict(denoise_coefficients=[3], noise=2.0, soft_threshold=False)),
+    (3, 60, 52, dict(denoise_coefficients=[4, 2])),   # noise=None: distributed exact MAD estimate of the raw w_0
 ])
 def test_banded_wow_over_gloo(tmp_path, world, height, width, kw):
     """Row-band WOW over gloo (two halo exchanges per scale + the all-gather of the residual moments) reproduces the
@@ -177,6 +178,46 @@ def test_banded_wow_over_gloo(tmp_path, world, height, width, kw):
     for p in range(planes.shape[0]):
         assert orc.emax(got_p[p], planes[p]) < 1e-11, (p, orc.emax(got_p[p], planes[p]))
     assert orc.emax(got_r, recon) < 1e-11
-    with pytest.raises(NotImplementedError):
-        from wavelets_b200.sharded import BandedWow
-        BandedWow()(torch.zeros((8, 64)), 8, denoise_coefficients=[3])
+
+
+def _median_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from wavelets_b200.sharded import distributed_abs_median
+        out = {}
+        for name, full in _median_cases().items():
+            y0, y1 = band_range(full.shape[0], rank, world)
+            out[name] = distributed_abs_median(torch.from_numpy(full[y0:y1].copy())).numpy()
+        if rank == 0:
+            np.savez(os.path.join(result_dir, "med.npz"), **out)
+    finally:
+        dist.destroy_process_group()
+
+
+def _median_cases():
+    rng = np.random.default_rng(3)
+    cases = {
+        "odd32": rng.standard_normal((31, 33)).astype(np.float32),          # odd count
+        "even32": rng.standard_normal((30, 34)).astype(np.float32) * 1e-3,  # even count: mean of the two middle values
+        "even64": rng.standard_normal((24, 50)) * 1e5,
+        "ties32": np.round(rng.standard_normal((40, 40)) * 2).astype(np.float32),  # heavy ties, many exact zeros
+        "const64": np.full((9, 9), -2.5),
+    }
+    cases["half_zero32"] = np.concatenate([np.zeros((20, 16), np.float32), cases["odd32"][:20, :16]])
+    return cases
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_distributed_abs_median_is_exact(tmp_path, world):
+    """The radix select over the ranks returns np.median(np.abs(x)) bit for bit (odd / even counts, ties, zeros)."""
+    if world == 1:
+        from wavelets_b200.sharded import distributed_abs_median
+        got = {k: distributed_abs_median(torch.from_numpy(v)).numpy() for k, v in _median_cases().items()}
+    else:
+        mp.spawn(_median_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+        got = dict(np.load(tmp_path / "med.npz"))
+    for name, full in _median_cases().items():
+        want = np.median(np.abs(full))
+        assert got[name].dtype == full.dtype and got[name] == want, (name, got[name], want)

@@ -92,7 +92,10 @@ def main():
         for dt in (torch.float32, torch.float64):
             gen = torch.Generator(device=dev).manual_seed(11)
             img = (torch.randn((h, w), generator=gen, device=dev, dtype=torch.float32) * 5 + 40).to(dt)
-            kw = dict(n_scales=min(args.levels, 6), weights=[1.5, 1.2], denoise_coefficients=[4, 2], noise=1.5)
+            # noise given for float32; float64 estimates it (distributed exact MAD of the raw w_0)
+            kw = dict(n_scales=min(args.levels, 6), weights=[1.5, 1.2], denoise_coefficients=[4, 2])
+            if dt == torch.float32:
+                kw["noise"] = 1.5
             recon_b, planes_b = BandedWow(wb.B3spline, poison=True)(img[y0:y1].contiguous(), h, **kw)
             utils.FUSED_WOW = False
             try:

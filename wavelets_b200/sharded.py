@@ -26,7 +26,7 @@ from . import _lib
 from .scaling import B3spline
 
 __all__ = ["frame_shard", "band_range", "halo_rows", "exchange_plan", "exchange_halos", "BandedTransform",
-           "band_scale_p2p", "PeerBandBuffers", "BandedWow"]
+           "band_scale_p2p", "PeerBandBuffers", "BandedWow", "distributed_abs_median"]
 
 
 def frame_shard(n_frames: int, rank: int, world: int) -> range:
@@ -252,15 +252,65 @@ class _CudaWowBackend:
         return synthesis(planes)
 
 
+def distributed_abs_median(x: torch.Tensor, group=None) -> torch.Tensor:
+    """Exact ``np.median(np.abs(X))`` of a tensor X whose elements are spread over the ranks of ``group`` (this rank
+    holds ``x``), as a 0-dim tensor of x's dtype -- bit-identical to NumPy, including the mean of the two middle values
+    for an even count.
+
+    Order statistics of |x| are order statistics of the IEEE bit patterns of |x| read as integers, so this is a
+    radix select on those integers, 11 bits per pass from the top: every rank histograms the digit of the keys that
+    match the prefix found so far, one all-reduce of 2048 counts per pass locates the bin that holds the wanted rank
+    (3 passes for float32, 6 for float64; twice that when the two middle ranks of an even count part ways).  Plumbing
+    only (torch ops + ``all_reduce``): the MAD estimate is computed once per image."""
+    if x.dtype == torch.float32:
+        keys, bits = x.detach().abs().contiguous().view(torch.int32).reshape(-1).to(torch.int64), 31
+    elif x.dtype == torch.float64:
+        keys, bits = x.detach().abs().contiguous().view(torch.int64).reshape(-1), 63
+    else:
+        raise TypeError(f"distributed_abs_median: float32 or float64, got {x.dtype}")
+    distributed = dist.is_initialized() and dist.get_world_size(group) > 1
+    n = torch.tensor([keys.numel()], dtype=torch.int64, device=x.device)
+    if distributed:
+        dist.all_reduce(n, group=group)
+    n = int(n.item())
+    if n == 0:
+        return torch.full((), float("nan"), dtype=x.dtype, device=x.device)
+
+    def select(k):
+        prefix, below, remaining = 0, 0, bits
+        while remaining > 0:
+            b = min(11, remaining)
+            shift = remaining - b
+            sel = keys if remaining == bits else keys[(keys >> remaining) == prefix]
+            digit = (sel >> shift) & ((1 << b) - 1)
+            hist = torch.bincount(digit, minlength=1 << b)
+            if distributed:
+                dist.all_reduce(hist, group=group)
+            cum = torch.cumsum(hist, 0)
+            bin_ = int(torch.searchsorted(cum, torch.tensor(k - below, dtype=torch.int64, device=cum.device),
+                                          right=True).item())
+            below += int(cum[bin_ - 1].item()) if bin_ > 0 else 0
+            prefix = (prefix << b) | bin_
+            remaining = shift
+        return prefix
+
+    k_lo, k_hi = (n - 1) // 2, n // 2
+    key_lo = select(k_lo)
+    key_hi = key_lo if k_hi == k_lo else select(k_hi)
+    pair = torch.tensor([key_lo, key_hi], dtype=torch.int64, device=x.device)
+    vals = pair.to(torch.int32).view(torch.float32) if x.dtype == torch.float32 else pair.view(torch.float64)
+    return (vals[0] + vals[1]) / 2
+
+
 class BandedWow:
     """``wow(image)`` (watroo/utils.py:105-219, plain cascade, whitening on) of ONE image sharded by row bands.
 
     Per scale: halo exchange of ``c_s`` -> band scale kernel (``c_{s+1}``, raw ``w_s``) -> halo exchange of the raw
     ``w_s`` (the local power is a second dilated filter) -> band whitening kernel.  The residual plane needs the
     population std of the WHOLE plane: every rank contributes (count, mean, variance) of its rows, combined after one
-    all-gather of three doubles.  The synthesis sum is local.  Thresholds (``denoise_coefficients``) need the noise as an
-    argument: the MAD estimate of the reference is an exact median over the whole plane, whose distributed form is not
-    built.  Returns ``(recon_band, planes_band)``; the planes equal the two-pass single-device route bit for bit, the
+    all-gather of three doubles.  The synthesis sum is local.  When thresholds (``denoise_coefficients``) are requested
+    without ``noise``, the MAD estimate is the exact median of |w_0| over the whole image (``distributed_abs_median``:
+    a radix select with one 2048-bin all-reduce per pass).  Returns ``(recon_band, planes_band)``; the planes equal the two-pass single-device route bit for bit, the
     residual plane up to the rounding of the combined std."""
 
     def __init__(self, scaling_function_class=B3spline, group=None, backend=None, poison=False):
@@ -281,8 +331,6 @@ class BandedWow:
         assert rows == y1 - y0, f"rank {rank}: band has {rows} rows, expected {y1 - y0}"
         level, _, wts, dns = _wow_plan((global_height, width), self.scaling_function_class, n_scales, list(weights),
                                        list(denoise_coefficients), None)
-        if any(d != 0 for d in dns[:level]) and noise is None:
-            raise NotImplementedError("BandedWow: pass noise= (the distributed exact MAD estimate is not built)")
         sigma_e = sf.sigma_e()
         be = self.backend
         planes = torch.empty((level + 1, rows, width), dtype=band.dtype, device=band.device)
@@ -301,6 +349,11 @@ class BandedWow:
             last = s == level - 1
             out_c, out_pad = (planes[level], 0) if last else (nxt, pad)
             be.scale(cur, pad, out_c, out_pad, wext[pad:pad + rows], rows, width, global_height, y0, s, sf.taps_code)
+            if s == 0 and noise is None and any(d != 0 for d in dns[:level]):
+                # MAD estimate from the raw w_0 of the WHOLE image (watroo/wavelets.py:126-127, :131-132), NumPy >= 2
+                # promotion: '/ 0.6745' in the plane dtype, '/ sigma_e[0]' in float64
+                med = distributed_abs_median(wext[pad:pad + rows], self.group)
+                noise = float((med / torch.tensor(0.6745, dtype=med.dtype)).item()) / float(sigma_e[0])
             if world > 1:
                 exchange_halos(wext, pad, global_height, halo, self.group)
             d = dns[s]
