@@ -41,7 +41,8 @@ except Exception:  # pragma: no cover
 __all__ = [
     "TAPS", "SIGMA_E_2D", "SIGMA_E_2D_BILATERAL", "reflect_index", "smooth", "local_variance", "bilateral_smooth",
     "atrous_transform", "get_noise", "significance", "denoise_planes", "denoise", "wow", "compute_noise_weights",
-    "default_backend", "wow_default_scales", "solar_like", "emax",
+    "default_backend", "wow_default_scales", "solar_like", "emax", "SIGMA_E_1D", "SIGMA_E_3D", "mirror_index",
+    "smooth_nd", "atrous_transform_recursive", "filter2d_reflect", "enhance", "richardson_lucy",
 ]
 
 # ---------------------------------------------------------------------------------------------------------------
