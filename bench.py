@@ -36,10 +36,31 @@ WORKLOAD = "cfg2: B3spline 2-D a trous, 4096x4096 fp32, 10 scales (BASELINE.json
 
 
 def measured_peaks():
+    """HBM roofline denominator: the driver-written MEASURED_PEAKS.json (the SUSTAINED figure when the file tells burst
+    and sustained apart -- K1 is timed inside a long step), else the fallback of B200_PROFILING.md."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
-        with open(path) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json (of measured)"
+        try:
+            with open(path) as fh:
+                d = json.load(fh)
+
+            def num(v):
+                if isinstance(v, (int, float)) and v > 0:
+                    return float(v)
+                if isinstance(v, dict):
+                    for k in ("sustained", "sustained_gbs", "gbs", "value", "burst"):
+                        if k in v and isinstance(v[k], (int, float)) and v[k] > 0:
+                            return float(v[k])
+                return None
+
+            for key in ("hbm_gbs_sustained", "hbm_sustained_gbs", "hbm_gbs"):
+                if key in d and num(d[key]):
+                    return num(d[key]), f"MEASURED_PEAKS.json[{key}] (of measured)"
+            for key, v in d.items():
+                if "hbm" in key.lower() and "burst" not in key.lower() and num(v):
+                    return num(v), f"MEASURED_PEAKS.json[{key}] (of measured)"
+        except (OSError, ValueError):
+            pass
     return 6650.0, "B200_PROFILING.md fallback (of fallback)"
 
 
