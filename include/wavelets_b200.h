@@ -232,14 +232,6 @@ int wb_residual_rescale(void *c, long long n, int batch, long long bstride, int 
                         double weight, void *stream);
 
 /*
- * wb_residual_rescale of the LAST plane fused with wb_synthesis (the tail of wow(), watroo/utils.py:185-189, :203, :205):
- * plane nplanes-1 is rescaled in place by dtype(weight / std) and the planes are summed in plane order, in one pass.
- */
-int wb_synthesis_rescale(void *planes, int nplanes, long long plane_stride, long long n, int batch, long long in_bstride,
-                         void *out, long long out_bstride, int dtype, const double *moments, double weight,
-                         void *stream);
-
-/*
  * One dilated filter pass along ONE axis of a C-contiguous (n_outer, n_axis, n_inner) array: what the 1-D and 3-D
  * branches of `convolution` need beyond the 2-D kernels (watroo/wavelets.py:46-69):
  *   - 1-D signal of n samples: n_outer = 1, n_axis = n, n_inner = 1, border = WB_BORDER_MIRROR

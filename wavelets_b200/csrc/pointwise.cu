@@ -91,58 +91,6 @@ __global__ void __launch_bounds__(256) residual_rescale_kernel(T *c, long long n
 }
 
 // out = ((p_0 + p_1) + p_2) + ... in plane order and in the plane dtype, as np.sum(axis=0) does.
-// Residual rescale + synthesis in one pass (the tail of wow(): watroo/utils.py:185-189, :203, :205): the last plane is
-// multiplied by dtype(weight / std) -- std = moments[frame][2] rounded to the plane dtype, non-positive -> 1e-15 --
-// written back (coefficients.data holds the whitened planes) and summed with the others in plane order.  Saves one
-// read of the plane and one launch against wb_residual_rescale followed by wb_synthesis; same roundings.
-template <typename T>
-__global__ void __launch_bounds__(256) synthesis_rescale_kernel(T *planes, int nplanes, long long plane_stride,
-                                                                long long n, long long in_bstride, T *out,
-                                                                long long out_bstride, const double *moments,
-                                                                double weight) {
-    const int frame = blockIdx.y;
-    T *pf = planes + (long long)frame * in_bstride;
-    T *last = pf + (long long)(nplanes - 1) * plane_stride;
-    T *of = out + (long long)frame * out_bstride;
-    T sd = (T)moments[frame * 3 + 2];
-    if (sd <= T(0)) sd = T(1e-15);
-    const T ratio = (T)weight / sd;
-    constexpr int V = VecOf<T>::V;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nth = (long long)gridDim.x * blockDim.x;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(pf) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(of) & 15u) == 0) &&
-                        (plane_stride % V == 0);
-    const long long nvec = vec_ok ? n / V : 0;
-    for (long long i = tid; i < nvec; i += nth) {
-        Pack<T, V> acc;
-#pragma unroll
-        for (int e = 0; e < V; ++e) acc.v[e] = T(0);
-        for (int k = 0; k < nplanes; ++k) {
-            Pack<T, V> p = ld_vec(pf + (long long)k * plane_stride + i * V);
-            if (k == nplanes - 1) {
-#pragma unroll
-                for (int e = 0; e < V; ++e) p.v[e] *= ratio;
-                st_vec(last + i * V, p);
-            }
-#pragma unroll
-            for (int e = 0; e < V; ++e) acc.v[e] = (k == 0) ? p.v[e] : acc.v[e] + p.v[e];
-        }
-        st_vec(of + i * V, acc);
-    }
-    for (long long i = nvec * V + tid; i < n; i += nth) {
-        T acc = T(0);
-        for (int k = 0; k < nplanes; ++k) {
-            T v = pf[(long long)k * plane_stride + i];
-            if (k == nplanes - 1) {
-                v *= ratio;
-                last[i] = v;
-            }
-            acc = (k == 0) ? v : acc + v;
-        }
-        of[i] = acc;
-    }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256) synthesis_kernel(const T *planes, int nplanes, long long plane_stride,
                                                         long long n, int batch, long long in_bstride, T *out,
@@ -421,26 +369,6 @@ int wb_filter2d(const void *in, void *out, int H, int W, long long in_pitch, lon
         wb::filter2d_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double *>(in),
                                                          reinterpret_cast<double *>(out), H, W, in_pitch, out_pitch,
                                                          reinterpret_cast<const double *>(kernel), kh, kw, flip);
-    return wb::launch_status();
-}
-
-int wb_synthesis_rescale(void *planes, int nplanes, long long plane_stride, long long n, int batch, long long in_bstride,
-                         void *out, long long out_bstride, int dtype, const double *moments, double weight,
-                         void *stream) {
-    if (dtype != WB_F32 && dtype != WB_F64) return WB_EINVAL_DTYPE;
-    if (n < 1 || nplanes < 1 || batch < 1 || batch > 65535) return WB_EINVAL_SHAPE;
-    if (!planes || !out || !moments) return WB_EINVAL_POINTER;
-    cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(wb::grid_for(n / 4 + 1), (unsigned)batch);
-    if (dtype == WB_F32)
-        wb::synthesis_rescale_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<float *>(planes), nplanes, plane_stride,
-                                                                  n, in_bstride, reinterpret_cast<float *>(out),
-                                                                  out_bstride, moments, weight);
-    else
-        wb::synthesis_rescale_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<double *>(planes), nplanes,
-                                                                   plane_stride, n, in_bstride,
-                                                                   reinterpret_cast<double *>(out), out_bstride, moments,
-                                                                   weight);
     return wb::launch_status();
 }
 

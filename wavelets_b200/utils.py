@@ -186,15 +186,12 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
     # residual plane: c_L *= wt_L / std(c_L)  (watroo/utils.py:185-189, :203)
     last = planes[:, L]
     if whitening:
-        # rescale of the residual plane fused with the synthesis sum (one pass over the planes)
+        # (a fused rescale + synthesis pass measured slower: the separate rescale finds c_L still in L2)
         mom = plane_moments(last)
-        recon = torch.empty((b, h, w), dtype=dt, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.wb_synthesis_rescale(planes.data_ptr(), L + 1, h * w, h * w, b, (L + 1) * h * w,
-                                                recon.data_ptr(), h * w, _lib.dtype_code(dt), mom.data_ptr(),
-                                                float(wts[L]), _lib.stream_ptr(dev)))
-        return recon, planes, nz
-    if wts[L] != 1:
+            _lib.check(lib.wb_residual_rescale(last.data_ptr(), h * w, b, (L + 1) * h * w, _lib.dtype_code(dt),
+                                               mom.data_ptr(), float(wts[L]), _lib.stream_ptr(dev)))
+    elif wts[L] != 1:
         last.mul_(wts[L])
     recon = synthesis(planes)
     return recon, planes, nz
