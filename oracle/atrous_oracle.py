@@ -347,13 +347,26 @@ def denoise_planes(planes: np.ndarray, name: str, sigma, weights=None, noise=Non
     return noise
 
 
+def generalized_anscombe(signal: np.ndarray, alpha=1, g=0, sigma=0, inverse: bool = False) -> np.ndarray:
+    """Variance-stabilising transform of Poisson-Gaussian data and its algebraic inverse (wavelets.py:14-21)."""
+    if inverse:
+        return ((alpha * signal / 2) ** 2 + alpha * g - sigma ** 2 - 3 * alpha / 8) / alpha
+    dum = alpha * signal + 3 * alpha ** 2 / 8 + sigma ** 2 - alpha * g
+    dum[dum <= 0] = 0
+    return 2 * np.sqrt(dum) / alpha
+
+
 def denoise(data: np.ndarray, weights, name: str = "b3spline", noise=None, bilateral=None,
-            soft_threshold: bool = True, backend: str | None = None) -> np.ndarray:
-    """utils.denoise (utils.py:83-102) without the Anscombe option: ``weights`` are the sigma thresholds and their
-    count is the number of scales; result = sum of the planes in plane order (np.sum(axis=0))."""
+            soft_threshold: bool = True, backend: str | None = None, anscombe: bool = False) -> np.ndarray:
+    """utils.denoise (utils.py:83-102): ``weights`` are the sigma thresholds and their count is the number of
+    scales; result = sum of the planes in plane order (np.sum(axis=0)); ``anscombe`` wraps the whole thing in the
+    generalized Anscombe transform and its inverse (utils.py:93-94, :99-100)."""
+    if anscombe:
+        data = generalized_anscombe(data)
     planes = atrous_transform(data, len(weights), name, bilateral=bilateral, backend=backend)
     denoise_planes(planes, name, weights, noise=noise, bilateral=bilateral, soft_threshold=soft_threshold)
-    return np.sum(planes, axis=0)
+    out = np.sum(planes, axis=0)
+    return generalized_anscombe(out, inverse=True) if anscombe else out
 
 
 # ---------------------------------------------------------------------------------------------------------------

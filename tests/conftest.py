@@ -14,6 +14,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Tests marked `gpu` are skipped (not failed) where there is no CUDA device or the CUDA library is not built."""
+    reason = None
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            reason = "no CUDA device"
+    except Exception as exc:  # pragma: no cover
+        reason = f"torch unavailable: {exc}"
+    if reason is None and not os.path.exists(os.path.join(ROOT, "wavelets_b200", "libwavelets_b200.so")):
+        reason = "wavelets_b200/libwavelets_b200.so is not built"
+    if reason is None:
+        return
+    skip = pytest.mark.skip(reason=reason)
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 

@@ -111,6 +111,68 @@ def main_callers():
     save("richardson_lucy", **out)
 
 
+
+def wide_columns(w):
+    """Column subset stored by the wide fixtures: 4 columns either side of every 512-column strip boundary of the
+    CUDA kernels, the first and last 8 columns, and every 64th column in between."""
+    cols = set(range(0, 8)) | set(range(w - 8, w)) | set(range(0, w, 64))
+    for b in range(512, w, 512):
+        cols |= set(range(b - 4, b + 4))
+    return np.array(sorted(c for c in cols if 0 <= c < w), dtype=np.int64)
+
+
+def main_wide():
+    """Frames at the widths the benchmark runs (>= 1024 columns, several 512-column strips): plain and bilateral
+    transform, wow default / bilateral + denoise.  Inputs are regenerated from the seed by the tests (checked against
+    the stored sum and a few rows); outputs are stored on `wide_columns` only to keep the fixtures small."""
+    for dt in ("float32", "float64"):
+        out = {}
+        for tag, (h, w, seed, flux) in (("a", (96, 4096, 12, 0.05)), ("b", (72, 1536, 13, 1.0))):
+            img = solar_like(h, seed=seed, flux=flux, dtype=dt, m=w)
+            cols = wide_columns(w)
+            out[f"{tag}_shape"] = np.array([h, w, seed], dtype=np.int64)
+            out[f"{tag}_flux"] = np.float64(flux)
+            out[f"{tag}_cols"] = cols
+            out[f"{tag}_in_sum"] = np.float64(img.astype(np.float64).sum())
+            out[f"{tag}_in_rows"] = img[:2].copy()
+            out[f"{tag}_plain"] = AtrousTransform(B3spline)(img.copy(), 5).data[:, :, cols]
+            out[f"{tag}_bil"] = AtrousTransform(B3spline, bilateral=1)(img.copy(), 5).data[:, :, cols]
+            out[f"{tag}_tri_bil"] = AtrousTransform(Triangle, bilateral=[1.5, 1], bilateral_scaling=True)(img.copy(), 6).data[:, :, cols]
+            for key, kw in (("default", {}), ("den", dict(denoise_coefficients=[5, 2])),
+                            ("bil_den", dict(bilateral=1, denoise_coefficients=[5, 2]))):
+                recon, co = wow(img.copy(), **kw)
+                out[f"{tag}_{key}_recon"] = recon[:, cols]
+                out[f"{tag}_{key}_planes"] = co.data[:, :, cols]
+                out[f"{tag}_{key}_noise"] = np.float64(np.nan if co.noise is None else co.noise)
+        save(f"wide_{dt}", **out)
+
+
+def main_f2():
+    """compute_noise_weights(bilateral=...) on stored noise fields and denoise(anscombe=True)."""
+    import watroo.wavelets as ww
+    ww.tqdm = lambda it: it  # silence the progress bar
+    out = {}
+    side = 11 * 2 ** 3
+    for sf in SF:
+        np.random.seed(8)
+        state = np.random.get_state()
+        out[f"{sf}_fields"] = np.stack([np.random.normal(size=(side, side)).astype(np.float32) for _ in range(2)])
+        np.random.set_state(state)
+        out[f"{sf}_nw_bil1"] = SF[sf](2).compute_noise_weights(3, n_trials=2, bilateral=1)
+        np.random.set_state(state)
+        out[f"{sf}_nw_bil2"] = SF[sf](2).compute_noise_weights(3, n_trials=2, bilateral=2.5)
+    for dt in ("float32", "float64"):
+        img = solar_like(96, seed=15, flux=0.05, dtype=dt, m=128)
+        out[f"ans_in_{dt}"] = img
+        out[f"ans_soft_{dt}"] = denoise(img.copy(), [4, 2, 1], B3spline, anscombe=True)
+        out[f"ans_tri_hard_{dt}"] = denoise(img.copy(), [3, 2], Triangle, anscombe=True, soft_threshold=False, noise=1.0)
+        out[f"ans_bil_{dt}"] = denoise(img.copy(), [3, 2], B3spline, anscombe=True, bilateral=1)
+        from watroo.wavelets import generalized_anscombe
+        out[f"ans_fwd_{dt}"] = generalized_anscombe(img.copy(), alpha=2.0, g=1.5, sigma=0.7)
+        out[f"ans_inv_{dt}"] = generalized_anscombe(out[f"ans_fwd_{dt}"].copy(), alpha=2.0, g=1.5, sigma=0.7, inverse=True)
+    save("f2_noise_weights_anscombe", **out)
+
+
 def main():
     assert watroo.__version__ == "0.0.4", watroo.__version__
     if "--callers" in sys.argv:
@@ -118,12 +180,20 @@ def main():
         return main_callers()
     if "--recursive" in sys.argv:
         return main_recursive()
+    if "--wide" in sys.argv:  # benchmark-width fixtures (round 2; the others are unchanged)
+        warnings.simplefilter("ignore")
+        return main_wide()
+    if "--f2" in sys.argv:
+        warnings.simplefilter("ignore")
+        return main_f2()
     warnings.simplefilter("ignore")
     if "--nd" in sys.argv:  # only the 1-D / 3-D fixtures (added later; the others are unchanged)
         return main_nd()
     main_nd()
     main_callers()
     main_recursive()
+    main_wide()
+    main_f2()
 
     # ---- plain transform: wavelets.py:408-444 via :307 ------------------------------------------------------
     cases = [((64, 64), 4), ((37, 53), 4), ((6, 7), 3), ((96, 64), 6), ((24, 256), 5)]

@@ -315,3 +315,55 @@ def test_transform_recursive_golden(sf):
             assert err <= max(TOL[dt] * np.abs(ref[p]).max(), floor), (k, p, err)
         std = orc.atrous_transform(img, level, sf)
         assert max(orc.emax(std[p], ref[p]) for p in range(level + 1)) > 1e-2  # the two algorithms really differ
+
+
+def test_oracle_f2_noise_weights_bilateral_and_anscombe():
+    """SURVEY 8(f) rank 2 against the real reference (tests/golden/make_golden.py --f2): compute_noise_weights with a
+    bilateral cascade on stored noise fields, denoise(anscombe=True), generalized_anscombe and its inverse."""
+    g = load_golden("f2_noise_weights_anscombe")
+    for sf in ("b3spline", "triangle"):
+        for key, bil in (("nw_bil1", 1), ("nw_bil2", 2.5)):
+            out = orc.compute_noise_weights(sf, 3, n_trials=2, bilateral=bil, fields=g[f"{sf}_fields"], backend="cv2")
+            assert np.abs(out / g[f"{sf}_{key}"] - 1).max() < 2e-5, (sf, key, out, g[f"{sf}_{key}"])
+    for dt in ("float32", "float64"):
+        img = g[f"ans_in_{dt}"]
+        tol = 2e-5 if dt == "float32" else 1e-12
+        assert orc.emax(orc.denoise(img.copy(), [4, 2, 1], "b3spline", anscombe=True, backend="cv2"), g[f"ans_soft_{dt}"]) < tol
+        assert orc.emax(orc.denoise(img.copy(), [3, 2], "b3spline", anscombe=True, bilateral=1, backend="cv2"),
+                        g[f"ans_bil_{dt}"]) < (1e-4 if dt == "float32" else 1e-11)
+        hard = orc.denoise(img.copy(), [3, 2], "triangle", anscombe=True, soft_threshold=False, noise=1.0, backend="cv2")
+        assert (np.abs(hard - g[f"ans_tri_hard_{dt}"]) > 1e-5 * np.abs(hard).max()).mean() < 1e-3
+        fwd = orc.generalized_anscombe(img.copy(), alpha=2.0, g=1.5, sigma=0.7)
+        assert np.array_equal(fwd, g[f"ans_fwd_{dt}"])
+        assert np.array_equal(orc.generalized_anscombe(fwd.copy(), alpha=2.0, g=1.5, sigma=0.7, inverse=True), g[f"ans_inv_{dt}"])
+
+
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+def test_oracle_wide_golden(dt):
+    """The oracle against the real reference at benchmark widths (96x4096, 72x1536; make_golden.py --wide): the cv2
+    backend is bit-identical on the plain path, within summation-order rounding on the bilateral / WOW paths, and the
+    separable numpy backend (what the GPU tests use) agrees with it."""
+    g = load_golden(f"wide_{dt}")
+    npdt = np.dtype(dt).type
+    for tag in ("a", "b"):
+        h, w, seed = (int(v) for v in g[f"{tag}_shape"])
+        img = orc.solar_like(h, seed=seed, flux=float(g[f"{tag}_flux"]), dtype=npdt, m=w)
+        assert img.astype(np.float64).sum() == float(g[f"{tag}_in_sum"]) and np.array_equal(img[:2], g[f"{tag}_in_rows"])
+        cols = g[f"{tag}_cols"]
+        plain = orc.atrous_transform(img, 5, "b3spline", backend="cv2")[:, :, cols]
+        assert np.array_equal(plain, g[f"{tag}_plain"])
+        sep = orc.atrous_transform(img.astype(np.float64), 5, "b3spline", backend="numpy")[:, :, cols]
+        for p in range(6):
+            assert orc.emax(sep[p], g[f"{tag}_plain"][p]) < (1e-5 if dt == "float32" else 1e-13), (tag, p)
+        if dt == "float64":
+            bil = orc.atrous_transform(img, 5, "b3spline", bilateral=1, backend="cv2")[:, :, cols]
+            for p in range(6):
+                assert orc.emax(bil[p], g[f"{tag}_bil"][p]) < 1e-12, (tag, p)
+            for key, kw in (("default", {}), ("bil_den", dict(bilateral=1, denoise_coefficients=[5, 2]))):
+                recon, planes, noise = orc.wow(img.copy(), backend="cv2", **kw)
+                # bilateral WOW: the 24-term weighted sum is accumulated in a different order than the reference's
+                # in-place loop -- measured 1.1e-12 (96x4096, flux 0.05) and 1.2e-11 (72x1536, flux 1: S[x^2] - S[x]^2
+                # cancels ~8 digits of float64 on counts of 1e4), which is the floor any "1e-12" bilateral claim has
+                assert orc.emax(recon[:, cols], g[f"{tag}_{key}_recon"]) < (1e-10 if kw else 1e-12), (tag, key)
+                if noise is not None:
+                    assert abs(noise - float(g[f"{tag}_{key}_noise"])) <= 1e-13 * noise

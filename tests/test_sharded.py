@@ -165,6 +165,8 @@ def _wow_worker(rank, world, port, height, width, kw, result_dir):
     (3, 72, 64, dict(n_scales=3, weights=[1.5, 1.0, 0.5], denoise_coefficients=[4, 2], noise=1.7)),
     (3, 48, 40, dict(denoise_coefficients=[3], noise=2.0, soft_threshold=False)),
     (3, 60, 52, dict(denoise_coefficients=[4, 2])),   # noise=None: distributed exact MAD estimate of the raw w_0
+    (2, 60, 52, dict(denoise_coefficients=[0, 3])),   # first threshold at scale 1: MAD of the WHITENED plane 0
+    (3, 64, 64, dict(denoise_coefficients=[0, 0, 2], soft_threshold=False)),
 ])
 def test_banded_wow_over_gloo(tmp_path, world, height, width, kw):
     """Row-band WOW over gloo (two halo exchanges per scale + the all-gather of the residual moments) reproduces the

@@ -24,7 +24,12 @@ def assert_planes_close(new, ref, dtype, scale_mag, what=""):
     assert new.shape == ref.shape and new.dtype == ref.dtype, (new.shape, ref.shape, new.dtype, ref.dtype)
     for p in range(len(ref)):
         err = np.abs(new[p].astype(np.float64) - ref[p]).max()
-        assert err <= max(tol * np.abs(ref[p]).max(), floor), (what, p, err, np.abs(ref[p]).max())
+        mag = np.abs(ref[p]).max()
+        assert err <= max(tol * mag, floor), (what, p, err, mag)
+        if err > tol * mag:  # only the data-rounding floor admits this plane: say so in the parity report
+            from tests.test_wide_parity_gpu import report
+            report(f"floor-limited plane: {what} plane {p} {np.dtype(dtype).name}: E_max {err / mag:.2e} "
+                   f"(|plane| {mag:.2e}, |image| {scale_mag:.2e})")
 
 
 @pytest.mark.parametrize("dt", ["float32", "float64"])
@@ -182,7 +187,8 @@ def test_strided_rows_and_level_edge_cases():
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_full_size_properties(dt):
-    """BASELINE cfg2 size (4096x4096, B3spline, 10 scales): size-independent properties + sampled oracle rows."""
+    """BASELINE cfg2 size (4096x4096, B3spline, 10 scales): size-independent properties + EVERY pixel of every plane
+    against the separable float64 oracle (the lean K1 kernel is the one behind the headline number)."""
     import wavelets_b200 as wb
     n, level = 4096, 10
     gen = torch.Generator(device="cuda").manual_seed(0)
@@ -202,12 +208,12 @@ def test_full_size_properties(dt):
     stds = planes[:-1].to(torch.float64).std(dim=(1, 2), unbiased=False).cpu().numpy()
     table = wb.B3spline(2).sigma_e()[:level]
     assert np.abs(stds[:6] / table[:6] - 1).max() < 0.02, stds / table
-    # exact check of a band of rows/cols against the oracle evaluated on the needed sub-lattice only
+    # all rows and columns of every plane against the oracle's separable float64 sum
     host = img.cpu().numpy().astype(np.float64)
     c = host
     taps = orc.TAPS["b3spline"]
-    ys = np.array([0, 1, 2, 3, 1000, 2047, 2048, 4093, 4094, 4095])
     xs = np.arange(n)
+    worst = 0.0
     for s in range(level):
         d = 2 ** s
         rows = np.zeros_like(c)
@@ -217,11 +223,15 @@ def test_full_size_properties(dt):
         for i, t in enumerate(taps):
             nxt += t * rows[orc.reflect_index(np.arange(n) + (i - 2) * d, n), :]
         w = c - nxt
-        got = planes[s][ys].cpu().numpy().astype(np.float64)
+        got = planes[s].cpu().numpy().astype(np.float64)
         tol = 1e-5 if dt == np.float32 else 1e-12
-        floor = 4 * np.finfo(dt).eps * np.abs(host).max()
-        assert np.abs(got - w[ys]).max() <= max(tol * np.abs(w).max(), floor), (s, np.abs(got - w[ys]).max())
+        err = np.abs(got - w).max() / np.abs(w).max()
+        worst = max(worst, err)
+        assert err <= tol, (s, err)
         c = nxt
+    err = np.abs(planes[level].cpu().numpy().astype(np.float64) - c).max() / np.abs(c).max()
+    assert err <= (1e-5 if dt == np.float32 else 1e-12), err
+    print(f"\nfull-size K1 parity {np.dtype(dt).name}: worst E_max over {level} detail planes {worst:.2e}, residual {err:.2e}")
 
 
 def test_stream_of_host_frames_matches_per_frame_calls():

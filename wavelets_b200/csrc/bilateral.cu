@@ -18,7 +18,8 @@ namespace wb {
 
 struct BilateralParams {
     ScaleParams sp;
-    double var_factor;  // sigma_b[s]^2 * (s + 1 if bilateral_scaling else 1)
+    double var_factor;    // sigma_b[s]^2 * (s + 1 if bilateral_scaling else 1)
+    float var_factor_f;   // the same, rounded once on the host (no F2F in the fp32 step loop)
 };
 
 __device__ __forceinline__ float exp2_fast(float x) {
@@ -507,6 +508,253 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
     else run(IC<0>{});
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 fast path, round 2: the same arithmetic with the 5x5 tap VALUES of the pixel pair held in a REGISTER sliding
+// window (bilateral_window_kernel).  ncu on bilateral_pairs_kernel: 457 warp instructions per warp-row of which 255 are
+// FP / MUFU -- the rest is re-loading all 25 tap pairs for every output row (30 LDS.64 with one address add each), the
+// row-statistics ring in shared memory and its indexing.  Here a staged row is read ONCE per thread, when it arrives
+// (TAPS LDS.64), into the window X[row slot][tap]; its row statistics (a, b) stay in registers too.  The step loop is
+// unrolled by TAPS so that the rotating row slot is a compile-time index: no register moves, no shared-memory ring
+// beyond the TMA staging slots (released right after the loads), ~250 warp instructions per warp-row of which 48 are
+// the MUFU ex2 that bound the kernel (2 per packed tap: 24 * 4096^2 exponentials per plane = 87 us of MUFU pipe).
+// Operation order and roundings are those of bilateral_pairs_kernel: the planes are bit-identical (WB_K2_WINDOW=0
+// selects the old kernel; tests/test_wide_parity_gpu.py compares the two).
+// ---------------------------------------------------------------------------------------------------------------
+// PW (producer warp): 8 consumer warps + a ninth warp whose lane 0 streams the rows (288 threads; ptxas then budgets 96
+// registers per thread and spills a little).  !PW: 256 threads, all consumers; thread 0 tops the ring up at the start
+// of each of its steps with a NON-blocking probe of the slot's `empty` barrier (and keeps probing while warp 0 waits
+// for a row, so a late reader can never dead-lock the block) -- 128 registers per thread at two blocks per SM.
+template <int TAPS, int DMODE, bool PW>
+__global__ void __launch_bounds__(PW ? 288 : 256, 2) bilateral_window_kernel(const BilateralParams bp) {
+    const ScaleParams &p = bp.sp;
+    pdl_launch_dependents();
+    constexpr int C = TAPS / 2;
+    constexpr int NL = PairPlan<TAPS, DMODE>::NL;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *rows = reinterpret_cast<float *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)p.slots * p.row_stride * sizeof(float));
+    uint64_t *empty = full + p.slots;
+
+    const int nt = PW ? blockDim.x - 32 : blockDim.x;  // consumer threads
+    const int nwc = nt >> 5;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    int bx = blockIdx.x;
+    const int strip = bx % p.n_strips;
+    bx /= p.n_strips;
+    const int r = bx % p.d;
+    const int g = bx / p.d;
+    const int frame = blockIdx.y;
+
+    const int n_chain = (r < p.H) ? (p.H - r + p.d - 1) / p.d : 0;
+    const int i0 = g * p.seg;
+    const int n_out = min(p.seg, n_chain - i0);
+    if (n_out <= 0) return;
+    const int n_load = n_out + 2 * C;
+
+    const int x0 = strip * p.wt;
+    const int lo = max(0, x0 - p.halo_al);
+    const int hi = min(p.W, x0 + p.wt + p.halo_al);
+    const uint32_t row_bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(float);
+    const uint32_t RB = (uint32_t)p.row_stride * (uint32_t)sizeof(float);
+
+    if (tid == 0) {
+        for (int s = 0; s < p.slots; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nwc);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_wait();  // everything below touches global memory written or read by the previous launch
+
+    // loader state (one thread): the next chain row to request, its ring slot and its position in the 2 Hg-periodic
+    // symmetric extension of the (global) image, walked incrementally
+    const float *src = reinterpret_cast<const float *>(p.in) + (long long)frame * p.in_bstride + lo;
+    const uint64_t pol_in = policy_evict_first();  // c_s is dead once this launch has read it
+    int next_load = 0, lslot = 0;
+    uint32_t lround = 0;
+    const long long period = 2LL * p.Hg;
+    const long long d_mod = (long long)p.d % period;
+    long long m_pos = 0;
+    if (tid == (PW ? nt : 0)) {
+        m_pos = (p.gwy0 + r + (long long)(i0 - C) * p.d) % period;
+        if (m_pos < 0) m_pos += period;
+    }
+    auto issue_load = [&]() {
+        const long long y = (m_pos < p.Hg ? m_pos : period - 1 - m_pos) - p.gwy0 + p.row_off_in;
+        mbar_arrive_expect_tx(&full[lslot], row_bytes);
+        if (p.l2_hints) tma_load_1d_hint(rows + (size_t)lslot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[lslot], pol_in);
+        else tma_load_1d(rows + (size_t)lslot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[lslot]);
+        ++next_load;
+        if (++lslot == p.slots) { lslot = 0; ++lround; }
+        m_pos += d_mod;
+        if (m_pos >= period) m_pos -= period;
+    };
+    // request every row whose slot is free, never blocking
+    auto top_up = [&]() {
+        while (next_load < n_load) {
+            if (lround > 0 && !mbar_test(&empty[lslot], (lround - 1) & 1)) break;
+            issue_load();
+        }
+    };
+
+    if constexpr (PW) {
+        if (warp == nwc) {
+            if (lane == 0) {
+                while (next_load < n_load) {
+                    // the producer runs rows ahead of the consumers: poll rarely, its spinning would take issue slots
+                    // from the warps doing the arithmetic
+                    if (lround > 0)
+                        while (!mbar_test(&empty[lslot], (lround - 1) & 1)) __nanosleep(1000);
+                    issue_load();
+                }
+            }
+            return;
+        }
+    } else {
+        if (tid == 0) top_up();
+    }
+
+    float *out_c = reinterpret_cast<float *>(p.out_c);
+    float *out_w = reinterpret_cast<float *>(p.out_w);
+
+    int xg = x0 + tid * 2;
+    const bool act = xg < p.W && xg < x0 + p.wt;
+    if (!act) xg = x0;  // idle threads shadow the first pair of the strip; their stores are masked
+    uint32_t colb[NL];
+    unsigned rev = 0;
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+        const int pcol = xg + (k - NL / 2) * (DMODE == 0 ? p.d : 2);  // even; one reflection at most
+        const bool left = pcol < 0, right = pcol >= p.W;
+        const int q = left ? (-2 - pcol) : (right ? (2 * p.W - 2 - pcol) : pcol);
+        colb[k] = smem_u32(rows) + (uint32_t)(q - lo) * 4u;  // absolute address of the tap in ring slot 0
+        if (left || right) rev |= 1u << k;
+    }
+    const float var_factor = bp.var_factor_f;
+    const uint64_t pol_keep = p.l2_hints ? policy_evict_last() : 0ull;  // c_{s+1}: the next scale reads it back
+    const float kc = Taps<float, TAPS>::h(C) * Taps<float, TAPS>::h(C);
+
+    // per-thread output pointers of the first output row; one add per row afterwards
+    const long long orow0 = (long long)r + (long long)i0 * p.d;
+    float *c_dst = out_c ? out_c + (long long)frame * p.c_bstride + orow0 * p.c_pitch + xg : nullptr;
+    float *w_dst = out_w ? out_w + (long long)frame * p.w_bstride + orow0 * p.w_pitch + xg : nullptr;
+    const long long c_step = (long long)p.d * p.c_pitch, w_step = (long long)p.d * p.w_pitch;
+
+    auto run = [&](auto mirror) {
+        constexpr bool MIRROR = decltype(mirror)::value != 0;
+        u64 X[TAPS][TAPS];       // X[row slot][tap]: tap pairs of the last TAPS chain rows (row j lives in slot j % TAPS)
+        u64 SA[TAPS], SB[TAPS];  // row statistics (a, b) of those rows, see row_stats
+        int slot = 0;
+        uint32_t parity = 0;
+        // Step j = TAPS u + I: chain row j lands -> its tap pairs and statistics enter slot I; from j = 2C on, the
+        // output row j - C (centre slot (I - C) mod TAPS) is produced from the window.
+        auto step = [&](auto ic, const int j) {
+            constexpr int I = decltype(ic)::value;
+            if (j >= n_load) return;
+            if constexpr (PW) {
+                mbar_wait(&full[slot], parity);
+            } else {
+                if (warp == 0) {
+                    if (lane == 0) top_up();
+                    while (!mbar_test(&full[slot], parity)) {
+                        if (lane == 0) top_up();
+                    }
+                } else {
+                    mbar_wait(&full[slot], parity);
+                }
+            }
+            pair_taps<TAPS, DMODE, MIRROR>((uint32_t)slot * RB, colb, rev, X[I]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);  // the staged row is read exactly once per thread
+            if (++slot == p.slots) { slot = 0; parity ^= 1; }
+            {
+                const P4 st = row_stats<TAPS>(X[I]);
+                SA[I] = st.lo;
+                SB[I] = st.hi;
+            }
+            if (j < 2 * C) return;
+            constexpr int RC = (I + TAPS - C) % TAPS;  // slot of the centre row
+            const u64 xc = X[RC][C];
+            // window moments from the row statistics (law of total variance, differences only), rows top to bottom
+            u64 s1 = 0ull, s2 = 0ull;
+#pragma unroll
+            for (int i = 0; i < TAPS; ++i) {
+                const int rs = (I + 1 + i) % TAPS;  // compile-time after unrolling
+                const float hi_ = Taps<float, TAPS>::h(i);
+                if (i == C) {
+                    s1 = fma2(pk2(-hi_, -hi_), SA[rs], s1);
+                    s2 = fma2(pk2(hi_, hi_), SB[rs], s2);
+                } else {
+                    const u64 dc = sub2(xc, X[rs][C]);
+                    const u64 t = fma2(pk2(-2.0f, -2.0f), SA[rs], dc);
+                    const u64 u = fma2(dc, t, SB[rs]);
+                    s1 = fma2(pk2(hi_, hi_), sub2(dc, SA[rs]), s1);
+                    s2 = fma2(pk2(hi_, hi_), u, s2);
+                }
+            }
+            // var = S[x^2] - S[x]^2 in centred form; V = max(var, 1e-20) * var_factor (kept a normal number: a tiny
+            // var_factor must not turn 1 / V into inf and the weight of an equal neighbour into 0 * inf);
+            // exponent scale -log2(e) / (2 V)
+            float v0, v1;
+            up2(sub2(s2, mul2(s1, s1)), v0, v1);
+            v0 = (v0 <= 0.0f) ? 1e-20f : v0;
+            v1 = (v1 <= 0.0f) ? 1e-20f : v1;
+            const u64 nhi = pk2(-0.72134752044448170f * rcp_fast(fmaxf(v0 * var_factor, 1e-37f)),
+                                -0.72134752044448170f * rcp_fast(fmaxf(v1 * var_factor, 1e-37f)));
+            u64 num = 0ull, den = pk2(kc, kc);
+#pragma unroll
+            for (int i = 0; i < TAPS; ++i) {
+                const int rs = (I + 1 + i) % TAPS;
+#pragma unroll
+                for (int k = 0; k < TAPS; ++k) {
+                    if (i == C && k == C) continue;
+                    const float lk = TapLog2<TAPS>::l(i) + TapLog2<TAPS>::l(k);
+                    const u64 dd = sub2(xc, X[rs][k]);
+                    float a0, a1;
+                    up2(fma2(mul2(dd, dd), nhi, pk2(lk, lk)), a0, a1);
+                    const u64 gw = pk2(exp2_fast(a0), exp2_fast(a1));
+                    den = add2(den, gw);
+                    num = fma2(gw, dd, num);
+                }
+            }
+            float n0, n1, d0, d1, x0v, x1v;
+            up2(num, n0, n1);
+            up2(den, d0, d1);
+            up2(xc, x0v, x1v);
+            const float c0 = x0v - n0 * rcp_fast(d0), c1 = x1v - n1 * rcp_fast(d1);
+            if (act) {
+                if (c_dst) {
+                    if (pol_keep)
+                        asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(c_dst), "f"(c0), "f"(c1), "l"(pol_keep) : "memory");
+                    else
+                        *reinterpret_cast<float2 *>(c_dst) = make_float2(c0, c1);
+                }
+                if (w_dst) __stcs(reinterpret_cast<float2 *>(w_dst), make_float2(x0v - c0, x1v - c1));
+            }
+            if (c_dst) c_dst += c_step;
+            if (w_dst) w_dst += w_step;
+        };
+#pragma unroll 1
+        for (int jb = 0; jb < n_load; jb += TAPS) {
+            step(IC<0>{}, jb + 0);
+            step(IC<1>{}, jb + 1);
+            step(IC<2>{}, jb + 2);
+            if constexpr (TAPS == 5) {
+                step(IC<3>{}, jb + 3);
+                step(IC<4>{}, jb + 4);
+            }
+        }
+    };
+    // warps that own no reflected column (all but the first / last strip's edge warps) run the variant without the
+    // mirror selects; the choice is warp-uniform, so no thread diverges inside the step
+    if (__any_sync(0xffffffffu, rev != 0)) run(IC<1>{});
+    else run(IC<0>{});
+}
+
 template <typename T, int TAPS>
 __global__ void __launch_bounds__(256) bilateral_generic_kernel(const BilateralParams bp) {
     const ScaleParams &p = bp.sp;
@@ -601,8 +849,36 @@ static bool plan_bilateral(ScaleParams &p, int taps, int esize, int batch) {
     return true;
 }
 
+// WB_K2_WINDOW in the environment: 0 selects the round-1 kernel (bilateral_pairs_kernel), 1 the register-window kernel
+// with a producer warp, 2 (default) the register-window kernel whose thread 0 streams the rows -- for A/B measurements
+// and the bit-identity test.
+static int k2_window_mode() {
+    const char *e = getenv("WB_K2_WINDOW");  // read on every call: the bit-identity test flips it inside one process
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+}
+
+template <int TAPS, int DMODE, bool PW>
+static int launch_bilateral_window(const BilateralParams &bp, int batch, cudaStream_t st) {
+    auto kern = bilateral_window_kernel<TAPS, DMODE, PW>;
+    const ScaleParams &p = bp.sp;
+    const size_t smem = (size_t)p.slots * p.row_stride * sizeof(float) + 16 * (size_t)p.slots;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
+    return launch_pdl<BilateralParams>(kern, grid, dim3(PW ? 256 + 32 : 256), smem, st, bp);
+}
+
 template <int TAPS, int DMODE>
 static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStream_t st) {
+    const int wm = k2_window_mode();
+    if (wm == 1) return launch_bilateral_window<TAPS, DMODE, true>(bp, batch, st);
+    if (wm == 2) return launch_bilateral_window<TAPS, DMODE, false>(bp, batch, st);
     auto kern = bilateral_pairs_kernel<TAPS, DMODE>;
     const ScaleParams &p = bp.sp;
     const size_t smem = (size_t)p.slots * p.row_stride * sizeof(float) + 16 * (size_t)p.slots + kPairStats * (size_t)p.slots;
@@ -695,6 +971,7 @@ int wb_atrous_scale_bilateral(const void *in, void *out_c, void *out_w, int batc
     p.c_pitch = out_c_pitch; p.c_bstride = out_c_bstride;
     p.w_pitch = out_w_pitch; p.w_bstride = out_w_bstride;
     bp.var_factor = var_factor;
+    bp.var_factor_f = (float)var_factor;
     p.l2_hints = wb::l2_hints_enabled();
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == WB_F32)

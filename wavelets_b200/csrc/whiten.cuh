@@ -36,7 +36,9 @@ template <typename T> struct WhitenEpilogue {
         if constexpr (sizeof(T) == 4) {
             thr_cmp = __double2float_rd(t);
             thr = (T)t;
-            inv_thr = (T)(1.0 / t);
+            // a denormal threshold must not turn 1 / thr into inf (0 * inf would poison pixels where w == 0, for which the
+            // reference's erf(|w / thr|) is 0): clamp to the largest finite float
+            inv_thr = (T)fmin(1.0 / t, 3.4028234663852886e38);
         } else {
             thr_cmp = t;
             thr = t;

@@ -349,14 +349,16 @@ class BandedWow:
             last = s == level - 1
             out_c, out_pad = (planes[level], 0) if last else (nxt, pad)
             be.scale(cur, pad, out_c, out_pad, wext[pad:pad + rows], rows, width, global_height, y0, s, sf.taps_code)
-            if s == 0 and noise is None and any(d != 0 for d in dns[:level]):
-                # MAD estimate from the raw w_0 of the WHOLE image (watroo/wavelets.py:126-127, :131-132), NumPy >= 2
-                # promotion: '/ 0.6745' in the plane dtype, '/ sigma_e[0]' in float64
-                med = distributed_abs_median(wext[pad:pad + rows], self.group)
+            d = dns[s]
+            if d != 0 and noise is None:
+                # MAD estimate over the WHOLE image, lazily at the first scale that thresholds (watroo/wavelets.py:126-127,
+                # :131-132): from the raw w_0 when that is scale 0, else from plane 0 as it stands by then -- already
+                # whitened (the quirk the reference's 'tri' golden with [0, 3] pins; wow()/_wow_stack do the same).
+                # NumPy >= 2 promotion: '/ 0.6745' in the plane dtype, '/ sigma_e[0]' in float64.
+                med = distributed_abs_median(wext[pad:pad + rows] if s == 0 else planes[0], self.group)
                 noise = float((med / torch.tensor(0.6745, dtype=med.dtype)).item()) / float(sigma_e[0])
             if world > 1:
                 exchange_halos(wext, pad, global_height, halo, self.group)
-            d = dns[s]
             mode = (1 if soft_threshold else 2) if d != 0 else 0
             be.whiten(wext, pad, planes[s], rows, width, global_height, y0, s, sf.taps_code, mode, d,
                       sigma_e[s] if d != 0 else 1.0, noise if d != 0 else 0.0, wts[s])

@@ -107,10 +107,44 @@ def atrous_scale(src, scale, scaling_function, out_c=None, out_w=None, var_facto
 
 
 def convolution(arr, scaling_function, s=0, output=None):
-    """Device counterpart of the reference's exported ``convolution`` (watroo/wavelets.py:35-45, 2-D branch):
-    the dilated smooth ``S_s[arr]`` with the symmetric border.  Returns a device tensor."""
-    img, _ = to_device_image(arr)
-    out, _ = atrous_scale(img, s, scaling_function, out_c=output, out_w=False)
+    """Device counterpart of the reference's exported ``convolution`` (watroo/wavelets.py:35-45): the dilated smooth
+    ``S_s[arr]`` with the reference's border (2-D / 3-D: symmetric, 1-D: whole-sample mirror).
+
+    NumPy in -> NumPy out, torch tensor in -> device tensor out.  ``output`` (the reference's in-place argument) may be a
+    device tensor (written directly when 2-D) or an ndarray (filled from the device result); it is returned."""
+    img, was_numpy = to_device_image(arr, ndim_ok=(1, 2, 3))
+    if isinstance(output, np.ndarray):
+        if output.shape != tuple(img.shape):
+            raise ValueError(f"output has shape {output.shape}, expected {tuple(img.shape)}")
+        output[...] = convolution(img, scaling_function, s).cpu().numpy()
+        return output
+    if output is not None and not isinstance(output, torch.Tensor):
+        raise TypeError("output must be a NumPy array or a torch tensor")
+    if img.ndim == 2:
+        out, _ = atrous_scale(img, s, scaling_function, out_c=output, out_w=False)
+    else:
+        out = _smooth_nd(img.contiguous(), int(s), scaling_function)
+        if output is not None:
+            output.copy_(out)
+            out = output
+    return out.cpu().numpy() if (was_numpy and output is None) else out
+
+
+def _smooth_nd(arr, s, scaling_function):
+    """S_s of a contiguous 1-D signal (mirror border, watroo/wavelets.py:64-69) or 3-D volume (2-D smooth of every
+    slice, then the depth pass, :46-63) -- one scale of AtrousTransform._run_nd without the detail plane."""
+    lib = _lib.load(require_cuda=True)
+    code, taps = _lib.dtype_code(arr.dtype), scaling_function.taps_code
+    out = torch.empty_like(arr)
+    with torch.cuda.device(arr.device):
+        if arr.ndim == 1:
+            _lib.check(lib.wb_atrous_axis(arr.data_ptr(), arr.data_ptr(), out.data_ptr(), 0, 1, arr.shape[0], 1, s, taps,
+                                          code, _lib.WB_BORDER_MIRROR, _lib.stream_ptr(arr.device)))
+        else:
+            depth, h, w = arr.shape
+            tmp, _ = atrous_scale(arr, s, scaling_function, out_w=False)  # every [i] slice, one launch
+            _lib.check(lib.wb_atrous_axis(tmp.data_ptr(), arr.data_ptr(), out.data_ptr(), 0, 1, depth, h * w, s, taps,
+                                          code, _lib.WB_BORDER_SYMMETRIC, _lib.stream_ptr(arr.device)))
     return out
 
 
