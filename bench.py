@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the à trous hot path on B200 (see DESIGN.md section "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload transform|wow]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-wow] [--no-extras]
 
 Workload at N=1 (BASELINE.json configs[1]): B3spline 2-D à trous transform of one 4096x4096 fp32 frame over 10
 scales.  One "step" = one full transform (10 per-scale launches) of a device-resident frame; `value` is
@@ -33,6 +33,10 @@ SF_NAME = "b3spline"
 METRIC = "atrous_transform_throughput"
 UNIT = "Mpixel*scales/s"
 WORKLOAD = "cfg2: B3spline 2-D a trous, 4096x4096 fp32, 10 scales (BASELINE.json configs[1])"
+# The SAME dict in both arms' lines (the driver compares them key by key); per-arm details go to "detail".
+CONFIG = {"workload": WORKLOAD, "scaling_function": "b3spline", "side": N_SIDE, "scales": LEVELS, "frames_per_rank": 1,
+          "sharding": "one frame per rank, no collective",
+          "l2": "working set 14 planes x 64 MiB = 896 MiB per step >> 126 MB L2 (no flush needed)"}
 
 
 def measured_peaks():
@@ -161,24 +165,28 @@ def run_reference(args):
     t0 = time.perf_counter()
     orc.atrous_transform(img, LEVELS, SF_NAME, backend=backend)  # warm-up (one frame, whatever W: ~6 s each)
     t_frame = time.perf_counter() - t0
-    steps = max(1, min(args.steps, int(100.0 / max(t_frame, 1e-3))))
+    # K steps are honoured exactly while they fit in ~4 minutes of CPU work (K <= ~40 at 5.7 s per frame); beyond that
+    # every step is accounted at the mean time of a bounded sample of full frames (stated in `sample`).
+    timed = max(1, min(args.steps, int(240.0 / max(t_frame, 1e-3))))
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(timed):
         orc.atrous_transform(img, LEVELS, SF_NAME, backend=backend)
     dt = time.perf_counter() - t0
-    value = side * side * LEVELS * steps / dt / 1e6
+    value = side * side * LEVELS * timed / dt / 1e6
     threads = 1
     if backend == "cv2":
         import cv2
         threads = cv2.getNumThreads()
-    sample = (f"{steps} full {side}x{side} fp32 frames x {LEVELS} scales timed ({args.steps} steps requested, capped to "
-              f"~100 s of CPU work; 1 warm-up frame), oracle port backend={backend}")
+    sample = (f"{timed} full {side}x{side} fp32 frames x {LEVELS} scales timed"
+              + ("" if timed == args.steps else f" (bounded sample: {args.steps} steps requested, each accounted at the mean)")
+              + f", 1 warm-up frame, oracle port backend={backend} = the reference's own cv2.filter2D calls")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "steps_requested": args.steps, "warmup": 1, "ms_per_step": dt / steps * 1e3,
+        "steps": args.steps, "steps_timed": timed, "warmup": args.warmup, "ms_per_step": dt / timed * 1e3,
         "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": dict(CONFIG),
+        "detail": {"sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -212,6 +220,7 @@ def time_wow(wb, img, reps, peak, **kw):
     for _ in range(3):
         _, co = wb.wow(img, **kw)
     levels = len(co) - 1
+    del co
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -225,12 +234,169 @@ def time_wow(wb, img, reps, peak, **kw):
             "achieved_gbs": algo / ms / 1e6, "frac_of_hbm_peak": algo / ms / 1e6 / peak}
 
 
+def pin_to_gpu_numa_node(index, uuid=None):
+    """Bind this process to the CPUs NVML reports as local to the GPU BEFORE any pinned allocation: first-touch then
+    places the pinned buffers on the GPU's own NUMA node (8 ranks otherwise share one node's memory controller and
+    PCIe root for their host copies).  Returns the number of CPUs bound, or None when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def copy_ceiling(dev, h2d_bytes, d2h_bytes, barrier, reps=4):
+    """What plain pinned copies of one step's bytes reach on this box with every rank copying at once (H2D and D2H on
+    two streams, device time): the ceiling of the e2e number at this N."""
+    import torch
+    hin = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    hout = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    din = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    dout = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    cur = torch.cuda.current_stream(dev)
+
+    def once():
+        s1.wait_stream(cur)
+        s2.wait_stream(cur)
+        with torch.cuda.stream(s1):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+
+    once()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    for _ in range(reps):
+        once()
+    e1.record(cur)
+    barrier()
+    return e0.elapsed_time(e1) / reps
+
+
+def multi_gpu_extras(args, wb, dist, dev, rank, world, peak):
+    """The modes with more than one frame per job (N > 1 only): cfg4 (frames sharded, no collective) and cfg5 (ONE image
+    in N row bands, per-scale halo transfer over NVLink).  Every number: device events, max over ranks."""
+    import torch
+    from wavelets_b200.sharded import BandedTransform, band_range, halo_rows
+    out = {}
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_ms(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- cfg4: batch of 4096^2 frames, B3spline 8 scales + WOW, frames dealt to the ranks (weak scaling) -------------
+    nb, L4, reps4 = 16, 8, 4
+    frame = solar_like_device(N_SIDE, torch.float32, dev, seed=3 + rank)
+    stack = frame.unsqueeze(0).repeat(nb, 1, 1)
+    stack += torch.sqrt(stack.clamp(min=1)) * 0.1 * torch.randn(stack.shape, device=dev)
+    for _ in range(2):
+        wb.wow_batch(stack, n_scales=L4)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps4):
+        wb.wow_batch(stack, n_scales=L4)
+    e1.record()
+    barrier()
+    ms = max_ms(e0.elapsed_time(e1))
+    algo4 = (5 * L4 + 3) * 4 * N_SIDE * N_SIDE
+    fps = world * nb * reps4 / (ms / 1e3)
+    out["wow_batch_cfg4"] = {
+        "frames_per_s": fps, "frames_per_s_per_gpu": fps / world, "ms_per_frame_per_gpu": ms / (nb * reps4), "scales": L4,
+        "frames_per_rank": nb * reps4, "frames_per_launch": nb, "sharding": "frames dealt to the ranks, no collective",
+        "algorithmic_bytes_per_frame": algo4, "frac_of_hbm_peak": algo4 * fps / world / 1e9 / peak,
+        "call": f"wow_batch({nb} x 4096x4096 fp32 solar-like, n_scales=8) per rank, BASELINE.json configs[3]"}
+    del stack, frame
+    torch.cuda.empty_cache()
+
+    # ---- cfg5: ONE 32768^2 image, B3spline 12 scales, N row bands ------------------------------------------------------
+    def run_banded(side, levels, reps, check):
+        y0, y1 = band_range(side, rank, world)
+        res = {}
+        gen = torch.Generator(device=dev).manual_seed(99)
+        full = None
+        if check:
+            img = torch.randn((side, side), generator=gen, device=dev, dtype=torch.float32)
+            band = img[y0:y1].contiguous()
+            full = wb.AtrousTransform(wb.B3spline)(img, levels).data[:, y0:y1].clone()
+            del img
+        else:
+            gen.manual_seed(99 + rank)
+            band = torch.randn((y1 - y0, side), generator=gen, device=dev, dtype=torch.float32)
+        for mode in ("push", "nccl"):
+            bt = BandedTransform(wb.B3spline, push=(mode == "push"))
+            planes = bt(band, levels, side)
+            if full is not None:
+                flag = torch.tensor([1 if torch.equal(planes, full) else 0], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                res[f"bit_identical_{mode}"] = bool(flag.item())
+            del planes
+            bt(band, levels, side)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                bt(band, levels, side)
+            e1.record()
+            barrier()
+            ms = max_ms(e0.elapsed_time(e1) / reps)
+            res[mode] = {"ms": ms, "mpx_scales_per_s": side * side * levels / ms / 1e3}
+        del band, full
+        torch.cuda.empty_cache()
+        return res
+
+    side5, L5 = 32768, 12
+    chk = run_banded(16384, 11, 3, True)      # fits one GPU: every rank also runs the unsharded cascade and compares
+    big = run_banded(side5, L5, 3, False)
+    rows = side5 // world
+    halo_bytes = [2 * min(halo_rows(s, 5), rows) * side5 * 4 for s in range(L5)]  # ingress per interior rank per scale
+    best = min(("push", "nccl"), key=lambda m: big[m]["ms"])
+    hbm_ms = L5 * 3 * 4 * rows * side5 / (peak * 1e9) * 1e3
+    link_ms = sum(halo_bytes) / 770e9 * 1e3
+    out["banded"] = {
+        "call": f"BandedTransform(B3spline)(band, 12, 32768): one 32768x32768 fp32 image in {world} row bands, "
+                "BASELINE.json configs[4]",
+        "ms": big[best]["ms"], "mpx_scales_per_s": big[best]["mpx_scales_per_s"], "transport": best,
+        "ms_by_transport": {m: big[m]["ms"] for m in big},
+        "transports": {"push": "halo rows of the next scale stored into the neighbours' buffers by the scale kernel "
+                               "(posted NVLink writes from wb_atrous_scale_band_push), one device barrier per scale",
+                       "nccl": "per-scale ncclSend/ncclRecv halo exchange, then the band kernel"},
+        "halo_bytes_in_per_scale_interior_rank": halo_bytes, "halo_bytes_in_total": sum(halo_bytes),
+        "floor_ms": {"hbm_3T_per_scale": hbm_ms, "nvlink_770GBs": link_ms,
+                     "note": "transfers of scale s+1 cannot start before scale s is computed: the floor with in-kernel "
+                             "overlap is the sum over scales of max(hbm, link), not max of the sums"},
+        "bit_identical": bool(chk.get("bit_identical_push", False) and chk.get("bit_identical_nccl", False)),
+        "bit_identical_check": {"image": "16384x16384 fp32, 11 scales, banded vs unsharded on every rank",
+                                **{k: v for k, v in chk.items() if k.startswith("bit_identical")},
+                                "ms": {m: chk[m]["ms"] for m in ("push", "nccl")}},
+    }
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-
-    import wavelets_b200 as wb
-    from wavelets_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -239,6 +405,12 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device: wavelets_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = pin_to_gpu_numa_node(local_rank, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
+
+    import wavelets_b200 as wb
+    from wavelets_b200 import _lib
+
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load(require_cuda=True)
@@ -262,12 +434,12 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local_rank, uuid=getattr(torch.cuda.get_device_properties(dev), "uuid", None))
-    for _ in range(max(3, args.warmup)):
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
         step()
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # keep the GPU busy long enough for the clock sampler to see clocks under load, without changing K
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
@@ -307,83 +479,142 @@ def run_ours(args):
     f1.record(stream)
     barrier()
     e2e_ms = f0.elapsed_time(f1)
+    # what plain pinned copies of the same bytes reach with every rank copying at once (the ceiling of e2e at this N)
+    ceil_ms = copy_ceiling(dev, h * w * 4, (LEVELS + 1) * h * w * 4, barrier)
 
-    times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
+    # the call users make: wow(host frame) -> host reconstruction (64 MiB in, 64 MiB out per frame), 3-stream pipeline
+    wow_out = torch.empty((h, w), dtype=torch.float32).pin_memory()
+    wow_frames = host_in.abs().mul_(50).unsqueeze(0).expand(e2e_steps, h, w)
+    wow_view = wow_out.unsqueeze(0).expand(e2e_steps, h, w)
+    wb.wow_stream(wow_frames[:2], out=wow_view[:2])
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    wb.wow_stream(wow_frames, out=wow_view)
+    g1.record(stream)
+    barrier()
+    e2e_wow_ms = g0.elapsed_time(g1)
+
+    times = torch.tensor([elapsed_ms, e2e_ms, ceil_ms, e2e_wow_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms = times.tolist()
+    elapsed_ms, e2e_ms, ceil_ms, e2e_wow_ms = times.tolist()
 
     units_per_step = h * w * LEVELS / 1e6  # Mpixel*scales
     value = units_per_step * args.steps * world / (elapsed_ms / 1e3)
     e2e_value = units_per_step * e2e_steps * world / (e2e_ms / 1e3)
+    peak, peak_src = measured_peaks()
 
-    # ---- WOW frames/s (BASELINE.json configs[2]), device-resident, rank 0 reports its own GPU ---------------------
-    wow_keys = {}
-    if rank == 0 and not args.no_wow:
-        peak_w, _ = measured_peaks()
-        solar = solar_like_device(N_SIDE, torch.float32, dev)
-        wow_keys["wow"] = time_wow(wb, solar, 30, peak_w)
-        wow_keys["wow_bilateral"] = time_wow(wb, solar, 15, peak_w, bilateral=1, denoise_coefficients=[5, 2])
-        wow_keys["wow"]["call"] = "wow(4096x4096 fp32 solar-like)"
-        wow_keys["wow_bilateral"]["call"] = "wow(4096x4096 fp32 solar-like, bilateral=1, denoise_coefficients=[5, 2])"
-        wow_keys["wow_bilateral"]["bound"] = "instruction issue and FMA/MUFU pipes (24 exp + ~160 fp32 ops per pixel per scale), not HBM"
-        # BASELINE.json configs[3] flavour: a stack of frames, one launch per scale for the whole stack (wow_batch)
-        nb = 8
-        stack = solar.unsqueeze(0).repeat(nb, 1, 1)
-        stack += torch.sqrt(stack.clamp(min=1)) * 0.1 * torch.randn(stack.shape, device=dev)
-        for _ in range(2):
-            _, pl, _ = wb.wow_batch(stack)
-        levels_b = pl.shape[1] - 1
-        del pl
-        torch.cuda.synchronize(dev)
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for _ in range(5):
-            wb.wow_batch(stack)
-        b1.record()
-        torch.cuda.synchronize(dev)
-        ms_b = b0.elapsed_time(b1) / 5 / nb
-        algo_b = (5 * levels_b + 3) * 4 * h * w
-        wow_keys["wow_batch"] = {"frames_per_s": 1e3 / ms_b, "ms_per_frame": ms_b, "scales": levels_b,
-                                 "frames_per_launch": nb, "algorithmic_bytes_per_frame": algo_b,
-                                 "achieved_gbs": algo_b / ms_b / 1e6, "frac_of_hbm_peak": algo_b / ms_b / 1e6 / peak_w,
-                                 "call": "wow_batch(8 x 4096x4096 fp32 solar-like)"}
-        del stack
-    if world > 1:
-        dist.barrier()
-
+    line = None
     if rank == 0:
-        peak, peak_src = measured_peaks()
         launch_ms = elapsed_ms / (args.steps * LEVELS)
         algo_bytes = 3 * 4 * h * w  # read c_s, write c_{s+1}, write w_s
         achieved = algo_bytes / (launch_ms / 1e3) / 1e9
-        # the CPU baseline is timed on rank 0 at N = 1 only (the contract); multi-GPU lines carry null
-        cpu_base = None
-        if world == 1:
-            cpu_val, cpu_s, backend, threads = cpu_reference_rate(N_SIDE, LEVELS)
-            cpu_base = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"one full {N_SIDE}x{N_SIDE} fp32 frame, {LEVELS} scales, {cpu_s:.2f} s, "
-                                  f"oracle port backend={backend} ({os.cpu_count()} host cpus)"}
+        step_bytes = h * w * 4 + (LEVELS + 1) * h * w * 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "warmup": warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_rank": 1, "sharding": "one frame per rank, no collective",
-                       "l2": "working set 14 planes x 64 MiB = 896 MiB per step >> 126 MB L2 (no flush needed)",
-                       "e2e_steps": e2e_steps, "kernel": "atrous_rows_lean_kernel<5> (TMA row pipeline, packed fp32x2, PDL)"},
+            "config": dict(CONFIG),
+            "detail": {"kernel": "atrous_rows_lean_kernel<5> (TMA row pipeline, packed fp32x2, PDL)",
+                       "e2e_steps": e2e_steps, "numa_cpus_bound": numa_cpus},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": launch_ms},
-            "cpu_baseline": cpu_base,
+            "cpu_baseline": None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h * w * 4,
-                    "d2h_bytes_per_step": (LEVELS + 1) * h * w * 4, "ms_per_step": e2e_ms / e2e_steps},
+                    "d2h_bytes_per_step": (LEVELS + 1) * h * w * 4, "ms_per_step": e2e_ms / e2e_steps,
+                    "api": "AtrousTransform.stream(pinned host frames) -> pinned host planes",
+                    "gbs_per_gpu": step_bytes / (e2e_ms / e2e_steps) / 1e6,
+                    "plain_copy_ms_per_step": ceil_ms, "plain_copy_gbs_per_gpu": step_bytes / ceil_ms / 1e6,
+                    "frac_of_plain_copy": ceil_ms / (e2e_ms / e2e_steps)},
+            "e2e_wow": {"frames_per_s": world * e2e_steps / (e2e_wow_ms / 1e3), "ms_per_frame": e2e_wow_ms / e2e_steps,
+                        "h2d_bytes_per_step": h * w * 4, "d2h_bytes_per_step": h * w * 4,
+                        "api": "wow_stream(pinned host frames) -> pinned host reconstructions (wow() per frame)"},
             "gpu_launches": args.steps * LEVELS,
             "clocks": clocks,
         }
-        line.update(wow_keys)
-        print(json.dumps(line), flush=True)
+
+    # Everything below only ADDS keys.  A watchdog prints the line as it stands if an extra stalls (a collective that
+    # never completes must not cost the headline number).
+    done = threading.Event()
+
+    def emit(extra_error=None):
+        if done.is_set():
+            return
+        done.set()
+        if rank == 0:
+            if extra_error:
+                line["extras_error"] = extra_error
+            print(json.dumps(line), flush=True)
+
+    def watchdog():
+        if not done.wait(args.extras_timeout):
+            emit(f"extras did not finish within {args.extras_timeout} s")
+            os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+    err = None
+    try:
+        # ---- WOW frames/s (BASELINE.json configs[2]), device-resident, rank 0 reports its own GPU ------------------
+        if rank == 0 and not args.no_wow:
+            solar = solar_like_device(N_SIDE, torch.float32, dev)
+            line["wow"] = time_wow(wb, solar, 30, peak)
+            line["wow_bilateral"] = time_wow(wb, solar, 15, peak, bilateral=1, denoise_coefficients=[5, 2])
+            line["wow"]["call"] = "wow(4096x4096 fp32 solar-like)"
+            line["wow_bilateral"]["call"] = "wow(4096x4096 fp32 solar-like, bilateral=1, denoise_coefficients=[5, 2])"
+            line["wow_bilateral"]["bound"] = ("MUFU pipe: 24 exponentials per pixel per scale = 87 us per 4096^2 scale at "
+                                              "16 MUFU/clk/SM, against 31 us of HBM time")
+            solar64 = solar.to(torch.float64)
+            line["wow_f64"] = time_wow(wb, solar64, 10, peak)
+            line["wow_bilateral_f64"] = time_wow(wb, solar64, 4, peak, bilateral=1, denoise_coefficients=[5, 2])
+            line["wow_f64"]["call"] = "wow(4096x4096 fp64 solar-like)"
+            line["wow_bilateral_f64"]["call"] = "wow(4096x4096 fp64 solar-like, bilateral=1, denoise_coefficients=[5, 2])"
+            del solar64
+            # BASELINE.json configs[3] flavour: a stack of frames, one launch per scale for the whole stack (wow_batch)
+            nb = 8
+            stack = solar.unsqueeze(0).repeat(nb, 1, 1)
+            stack += torch.sqrt(stack.clamp(min=1)) * 0.1 * torch.randn(stack.shape, device=dev)
+            for _ in range(2):
+                _, pl, _ = wb.wow_batch(stack)
+            levels_b = pl.shape[1] - 1
+            del pl
+            torch.cuda.synchronize(dev)
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(5):
+                wb.wow_batch(stack)
+            b1.record()
+            torch.cuda.synchronize(dev)
+            ms_b = b0.elapsed_time(b1) / 5 / nb
+            algo_b = (5 * levels_b + 3) * 4 * h * w
+            line["wow_batch"] = {"frames_per_s": 1e3 / ms_b, "ms_per_frame": ms_b, "scales": levels_b,
+                                 "frames_per_launch": nb, "algorithmic_bytes_per_frame": algo_b,
+                                 "achieved_gbs": algo_b / ms_b / 1e6, "frac_of_hbm_peak": algo_b / ms_b / 1e6 / peak,
+                                 "call": "wow_batch(8 x 4096x4096 fp32 solar-like)"}
+            del stack, solar
+            torch.cuda.empty_cache()
+        if world > 1 and not args.no_extras:
+            del planes, scratch, img
+            torch.cuda.empty_cache()
+            extras = multi_gpu_extras(args, wb, dist, dev, rank, world, peak)
+            if rank == 0:
+                line.update(extras)
+        # the CPU baseline is timed on rank 0 at N = 1 only (the contract); multi-GPU lines carry null
+        if rank == 0 and world == 1:
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline may use every host core again
+            cpu_val, cpu_s, backend, threads = cpu_reference_rate(N_SIDE, LEVELS)
+            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"one full {N_SIDE}x{N_SIDE} fp32 frame, {LEVELS} scales, {cpu_s:.2f} s, "
+                                              f"oracle port backend={backend} ({os.cpu_count()} host cpus)"}
+    except Exception as exc:  # an extra must never cost the headline line
+        err = f"{type(exc).__name__}: {exc}"[:400]
+    emit(err)
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 def main():
@@ -393,6 +624,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-wow", action="store_true", help="skip the extra WOW frames/s measurements")
+    ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the cfg4 / cfg5 (banded) keys")
+    ap.add_argument("--extras-timeout", type=float, default=300.0,
+                    help="seconds after which the line is printed without the extra keys that have not finished")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -122,6 +122,23 @@ int wb_wow_whiten_scale_band(const void *w_raw, void *out, int band_rows, int W,
                              double noise_host, const double *noise_dev, double weight, void *stream);
 
 /*
+ * wb_atrous_scale_band that also PUSHES the next scale's halo rows to the neighbouring bands (no reference equivalent;
+ * multi-GPU row bands): output rows [0, push_up_rows) of c_{s+1} are stored a second time at
+ * push_up + i * out_c_pitch and output rows [band_rows - push_dn_rows, band_rows) at push_dn + i * out_c_pitch, where
+ * push_up / push_dn are the addresses -- valid ON THIS DEVICE: peer-mapped memory over NVLink (CUDA IPC / symmetric
+ * memory) -- of the place this band's output row 0 has in the upper / lower neighbour's padded c buffer (its halo
+ * zone).  Pass NULL / 0 rows at the global top / bottom.  The remote stores are posted writes that overlap with this
+ * launch's own streaming; the next scale then reads local memory only (plain wb_atrous_scale_band semantics for
+ * everything else).  The caller orders the ranks with one device-side barrier per scale: a neighbour's buffer may be
+ * written only after that neighbour has finished the scale that read it, and read only after this launch has completed.
+ */
+int wb_atrous_scale_band_push(const void *in, void *out_c, void *out_w, int band_rows, int W, int global_H,
+                              long long band_y0, long long in_row_offset, long long in_pitch, long long out_c_row_offset,
+                              long long out_c_pitch, long long out_w_row_offset, long long out_w_pitch, void *push_up,
+                              int push_up_rows, void *push_dn, int push_dn_rows, int scale, int taps, int dtype,
+                              void *stream);
+
+/*
  * Row-band scale with the halo rows read IN PLACE from the neighbours' band buffers over NVLink (no halo copy, no
  * padded buffer, no reference equivalent).  The running smooth plane c_s of a global_H-row image is distributed over
  * n_peers ranks: rank k owns global rows [peer_y0[k], peer_y0[k+1]) (peer_y0 has n_peers + 1 entries, peer_y0[0] = 0,

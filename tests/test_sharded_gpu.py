@@ -82,6 +82,52 @@ def test_peer_window_scale_equals_rows_of_full_transform(dt, shape, world):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+@pytest.mark.parametrize("shape,level,world", [((384, 512), 6, 3), ((256, 2048), 6, 2), ((200, 130), 5, 3),
+                                               ((1024, 4096), 8, 4)])
+def test_halo_push_scale_equals_rows_of_full_transform(dt, shape, level, world):
+    """wb_atrous_scale_band_push with every rank's padded buffers as separate allocations of ONE device (the address
+    arithmetic is the same as with NVLink-mapped peers; launching the ranks one after the other stands for the
+    per-scale barrier): each scale kernel stores the next scale's halo rows into the neighbours' buffers, no other
+    exchange happens, and every band of every plane equals the unsharded cascade bit for bit.  Buffers start
+    NaN-filled, so a halo row that was never pushed would show up."""
+    import wavelets_b200 as wb
+    from wavelets_b200.sharded import band_range, band_scale_push, halo_rows, push_plan
+    h, w = shape
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    img = torch.randn((h, w), generator=gen, device="cuda", dtype=torch.float32).to(dt)
+    for sf in (wb.B3spline, wb.Triangle):
+        taps = len(sf.coefficients_1d)
+        pad = halo_rows(level - 1, taps)
+        bands = [band_range(h, k, world) for k in range(world)]
+        if pad > min(b - a for a, b in bands):
+            continue  # multi-hop halos are outside the push mode (BandedTransform falls back to the exchange)
+        full = wb.AtrousTransform(sf)(img, level).data
+        ext = [torch.full((2, (b - a) + 2 * pad, w), float("nan"), dtype=dt, device="cuda") for a, b in bands]
+        planes = [torch.empty((level + 1, b - a, w), dtype=dt, device="cuda") for a, b in bands]
+        h0 = halo_rows(0, taps)
+        for k, (a, b) in enumerate(bands):
+            ext[k][0, pad:pad + (b - a)] = img[a:b]
+            if a > 0:
+                ext[k][0, pad - h0:pad] = img[a - h0:a]
+            if b < h:
+                ext[k][0, pad + (b - a):pad + (b - a) + h0] = img[b:b + h0]
+        row_bytes = w * img.element_size()
+        for s in range(level):
+            last = s == level - 1
+            for k, (a, b) in enumerate(bands):
+                rows = b - a
+                if last:
+                    band_scale_push(ext[k][s & 1], pad, planes[k][level], 0, planes[k][s], rows, w, h, a, s, sf.taps_code)
+                else:
+                    up, n_up, dn, n_dn = push_plan(h, world, k, halo_rows(s + 1, taps), pad, row_bytes,
+                                                   [e[(s + 1) & 1].data_ptr() for e in ext])
+                    band_scale_push(ext[k][s & 1], pad, ext[k][(s + 1) & 1], pad, planes[k][s], rows, w, h, a, s,
+                                    sf.taps_code, up, n_up, dn, n_dn)
+        for k, (a, b) in enumerate(bands):
+            assert torch.equal(planes[k], full[:, a:b]), (sf.__name__, k)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
 def test_band_whitening_equals_rows_of_unsharded_whitening(dt):
     """wb_wow_whiten_scale_band on every band of every scale (halo rows of the raw w_s copied in by hand) equals the
     rows of wb_wow_whiten_scale on the whole plane bit for bit, for the three significance modes."""
@@ -131,4 +177,5 @@ def test_banded_two_ranks_nccl():
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
     assert '"bit_identical": true' in proc.stdout
     assert "p2p   banded == unsharded on all ranks: True" in proc.stdout  # in-kernel NVLink halo reads
+    assert "push  banded == unsharded on all ranks: True" in proc.stdout  # in-kernel NVLink halo writes
     assert "banded wow == unsharded two-pass wow on all ranks: True" in proc.stdout

@@ -3,7 +3,7 @@
     python tools/bench_k2.py [--side 4096] [--reps 20] [--out gpurun_out/bench_k2.json]
 
 WB_K2_WINDOW = 0: round-1 kernel (bilateral_pairs_kernel, tap pairs re-loaded per output row), 1: register-window kernel
-with a producer warp, 2: register-window kernel whose thread 0 streams the rows (default).  Also checks that the three
+(default), 3: low-register streaming kernel (four blocks per SM).  Also checks that the three
 produce bit-identical planes."""
 import argparse
 import json
@@ -22,7 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--side", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--modes", default="0,1,2")
+    ap.add_argument("--modes", default="0,1,3")
     ap.add_argument("--out", default="gpurun_out/bench_k2.json")
     args = ap.parse_args()
     n = args.side

@@ -26,7 +26,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-check", action="store_true", help="skip the unsharded comparison (image too large for one GPU)")
     ap.add_argument("--quick", action="store_true", help="B3spline fp32 only")
-    ap.add_argument("--modes", default="nccl,p2p", help="halo transport: nccl (send/recv exchange), p2p (in-kernel peer reads)")
+    ap.add_argument("--modes", default="nccl,p2p,push",
+                    help="halo transport: nccl (send/recv exchange), p2p (in-kernel peer reads), push (in-kernel peer writes)")
     ap.add_argument("--out", default="", help="also write the JSON summary to this file (rank 0)")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -53,7 +54,7 @@ def main():
                 band = img[y0:y1].contiguous()
             full = None if args.no_check else wb.AtrousTransform(sf)(img, args.levels).data
             for mode in modes:
-                bt = BandedTransform(sf, poison=True, p2p=(mode == "p2p"))
+                bt = BandedTransform(sf, poison=True, p2p=(mode == "p2p"), push=(mode == "push"))
                 planes = bt(band, args.levels, h)
                 torch.cuda.synchronize()
                 if full is not None:
@@ -66,7 +67,7 @@ def main():
                               f"{bool(flag.item())}", flush=True)
                 del planes
                 # timing of the sharded cascade (device time, max over ranks)
-                bt = BandedTransform(sf, p2p=(mode == "p2p"))
+                bt = BandedTransform(sf, p2p=(mode == "p2p"), push=(mode == "push"))
                 for _ in range(2):
                     bt(band, args.levels, h)
                 dist.barrier(); torch.cuda.synchronize()

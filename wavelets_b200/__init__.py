@@ -7,8 +7,8 @@ kernels of ``libwavelets_b200.so`` (C ABI: include/wavelets_b200.h).  There is n
 """
 from .scaling import AbstractScalingFunction, B3spline, Triangle  # noqa: F401
 from .wavelets import AtrousTransform, Coefficients, atrous_scale, convolution  # noqa: F401
-from .utils import denoise, enhance, generalized_anscombe, richardson_lucy, wow, wow_batch  # noqa: F401
+from .utils import denoise, enhance, generalized_anscombe, richardson_lucy, wow, wow_batch, wow_stream  # noqa: F401
 
 __version__ = "0.1.0"
 __all__ = ["AtrousTransform", "B3spline", "Triangle", "Coefficients", "generalized_anscombe", "convolution",
-           "denoise", "wow", "wow_batch", "atrous_scale", "enhance", "richardson_lucy"]
+           "denoise", "wow", "wow_batch", "wow_stream", "atrous_scale", "enhance", "richardson_lucy"]

@@ -97,9 +97,12 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
     T *w_ptr = reinterpret_cast<T *>(p.out_w);
     // first output row of this block; the pointers advance by one chain step (d rows) per output row
     const long long orow = (long long)r + (long long)i0 * p.d;
+    const T *c_base = c_ptr ? c_ptr + (long long)frame * p.c_bstride + p.row_off_c * p.c_pitch : nullptr;  // output row 0
     if (c_ptr) c_ptr += (long long)frame * p.c_bstride + (orow + p.row_off_c) * p.c_pitch;
     if (w_ptr) w_ptr += (long long)frame * p.w_bstride + (orow + p.row_off_w) * p.w_pitch;
     const long long c_step = (long long)p.d * p.c_pitch, w_step = (long long)p.d * p.w_pitch;
+    const bool pushing = (p.push_up != nullptr) | (p.push_dn != nullptr);
+    int out_row = (int)orow;  // band row of the next output
 
     WhitenEpilogue<T> epi;
     if constexpr (OP == OP_WHITEN) epi.init(p, frame);
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
                     if (c_ptr && act[q]) {
                         if (hints) st_vec_hint(c_ptr + xg[q], cv[q], pol_keep);
                         else st_vec(c_ptr + xg[q], cv[q]);
+                        if (pushing) push_store(p, c_ptr + xg[q], c_base, out_row, cv[q]);
                     }
                     if (w_ptr) {
                         Pack<T, V> raw = lds_vec<T>(crow_addr + xb[q]);
@@ -168,6 +172,7 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
             }
             if (c_ptr) c_ptr += c_step;
             if (w_ptr) w_ptr += w_step;
+            out_row += p.d;
         }
         if (j >= C) {
             // the raw row j-C is not needed any more: hand its slot back to the producer
@@ -286,10 +291,13 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
     T *c_ptr = reinterpret_cast<T *>(p.out_c);
     T *w_ptr = reinterpret_cast<T *>(p.out_w);
     const long long orow = (long long)r + (long long)i0 * p.d;  // first output row of this block
+    const T *c_base = c_ptr ? c_ptr + (long long)frame * p.c_bstride + p.row_off_c * p.c_pitch : nullptr;  // output row 0
     if (c_ptr) c_ptr += (long long)frame * p.c_bstride + (orow + p.row_off_c) * p.c_pitch + xg0;
     if (w_ptr) w_ptr += (long long)frame * p.w_bstride + (orow + p.row_off_w) * p.w_pitch + xg0;
     const long long c_step = (long long)p.d * p.c_pitch, w_step = (long long)p.d * p.w_pitch;
     const bool has_c = c_ptr != nullptr, has_w = w_ptr != nullptr;
+    const bool pushing = (p.push_up != nullptr) | (p.push_dn != nullptr);
+    int out_row = (int)orow;  // band row of the next output
 
     // Step j = 8 u + I: input row j lands -> row pass -> column feed -> c row j-C; w = raw centre row - c; release the
     // centre row's slot.
@@ -312,6 +320,7 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
                 if (has_c && act[q]) {
                     if (HINTS) stg_p4_hint(c_ptr + q * q_off, cv[q], pol_keep);
                     else stg_p4(c_ptr + q * q_off, cv[q]);
+                    if (pushing) push_store(p, c_ptr + q * q_off, c_base, out_row, cv[q]);
                 }
                 if (has_w) {
                     P4 raw = lds_p4_imm<SC * RB>(own[q]);
@@ -322,6 +331,7 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
             }
             if (has_c) c_ptr += c_step;
             if (has_w) w_ptr += w_step;
+            out_row += p.d;
         }
         if (j >= C) {
             // the raw row j-C is not needed any more: hand its slot back to the producer
@@ -381,7 +391,11 @@ __global__ void __launch_bounds__(256) atrous_generic_kernel(const ScaleParams p
         }
         const T raw = (input_row<T>(p, p.gwy0 + y) + foff)[x];
         if constexpr (OP == OP_TRANSFORM) {
-            if (out_c) out_c[(long long)frame * p.c_bstride + ((long long)y + p.row_off_c) * p.c_pitch + x] = acc;
+            if (out_c) {
+                T *dst = out_c + (long long)frame * p.c_bstride + ((long long)y + p.row_off_c) * p.c_pitch + x;
+                *dst = acc;
+                push_store(p, dst, out_c + (long long)frame * p.c_bstride + p.row_off_c * p.c_pitch, y, acc);
+            }
             if (out_w) out_w[(long long)frame * p.w_bstride + ((long long)y + p.row_off_w) * p.w_pitch + x] = raw - acc;
         } else {
             out_w[(long long)frame * p.w_bstride + ((long long)y + p.row_off_w) * p.w_pitch + x] = epi.apply(raw, acc);
@@ -578,6 +592,34 @@ int wb_atrous_scale_band(const void *in, void *out_c, void *out_w, int band_rows
     p.H = band_rows; p.W = W; p.d = 1 << scale; p.Hg = global_H;
     p.gwy0 = band_y0; p.row_off_in = in_row_offset; p.row_off_c = out_c_row_offset; p.row_off_w = out_w_row_offset;
     p.in_pitch = in_pitch; p.c_pitch = out_c_pitch; p.w_pitch = out_w_pitch;
+    return wb::dispatch_typed<wb::OP_TRANSFORM>(p, 1, scale, taps, dtype, (cudaStream_t)stream);
+}
+
+int wb_atrous_scale_band_push(const void *in, void *out_c, void *out_w, int band_rows, int W, int global_H,
+                              long long band_y0, long long in_row_offset, long long in_pitch, long long out_c_row_offset,
+                              long long out_c_pitch, long long out_w_row_offset, long long out_w_pitch, void *push_up,
+                              int push_up_rows, void *push_dn, int push_dn_rows, int scale, int taps, int dtype,
+                              void *stream) {
+    int rc = wb::check_common(1, band_rows, W, taps, dtype);
+    if (rc) return rc;
+    if (scale < 0 || scale > 30) return WB_EINVAL_SCALE;
+    if (!in || !out_c || in == out_c || in == out_w) return WB_EINVAL_POINTER;
+    if (global_H < band_rows || band_y0 < 0 || band_y0 + band_rows > global_H || in_pitch < W || out_c_pitch < W ||
+        (out_w && out_w_pitch < W) || push_up_rows < 0 || push_dn_rows < 0)
+        return WB_EINVAL_ARG;
+    if ((push_up && (push_up == out_c || push_up == in)) || (push_dn && (push_dn == out_c || push_dn == in)))
+        return WB_EINVAL_POINTER;
+    wb::ScaleParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = in; p.out_c = out_c; p.out_w = out_w;
+    p.H = band_rows; p.W = W; p.d = 1 << scale; p.Hg = global_H;
+    p.gwy0 = band_y0; p.row_off_in = in_row_offset; p.row_off_c = out_c_row_offset; p.row_off_w = out_w_row_offset;
+    p.in_pitch = in_pitch; p.c_pitch = out_c_pitch; p.w_pitch = out_w_pitch;
+    p.push_up = push_up_rows > 0 ? push_up : nullptr;
+    p.push_dn = push_dn_rows > 0 ? push_dn : nullptr;
+    p.push_up_rows = push_up_rows < band_rows ? push_up_rows : band_rows;
+    p.push_dn_from = push_dn_rows < band_rows ? band_rows - push_dn_rows : 0;
+    p.l2_hints = wb::l2_hints_enabled();
     return wb::dispatch_typed<wb::OP_TRANSFORM>(p, 1, scale, taps, dtype, (cudaStream_t)stream);
 }
 

@@ -520,12 +520,12 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
 // Operation order and roundings are those of bilateral_pairs_kernel: the planes are bit-identical (WB_K2_WINDOW=0
 // selects the old kernel; tests/test_wide_parity_gpu.py compares the two).
 // ---------------------------------------------------------------------------------------------------------------
-// PW (producer warp): 8 consumer warps + a ninth warp whose lane 0 streams the rows (288 threads; ptxas then budgets 96
-// registers per thread and spills a little).  !PW: 256 threads, all consumers; thread 0 tops the ring up at the start
-// of each of its steps with a NON-blocking probe of the slot's `empty` barrier (and keeps probing while warp 0 waits
-// for a row, so a late reader can never dead-lock the block) -- 128 registers per thread at two blocks per SM.
-template <int TAPS, int DMODE, bool PW>
-__global__ void __launch_bounds__(PW ? 288 : 256, 2) bilateral_window_kernel(const BilateralParams bp) {
+// 8 consumer warps + a ninth warp whose lane 0 streams the rows.  Two blocks per SM at the 96 registers ptxas budgets
+// for this block size (a few spilled values in the prologue; __maxnreg__(112) removes them but the register file then
+// holds ONE block per SM: 204 instead of 150 us).  Measured and not kept: 256-thread blocks whose thread 0 tops the ring
+// up with non-blocking probes (213 us: instruction-cache misses and a lagging warp 0).
+template <int TAPS, int DMODE>
+__global__ void __maxnreg__(104) bilateral_window_kernel(const BilateralParams bp) {
     const ScaleParams &p = bp.sp;
     pdl_launch_dependents();
     constexpr int C = TAPS / 2;
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(PW ? 288 : 256, 2) bilateral_window_kernel(con
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)p.slots * p.row_stride * sizeof(float));
     uint64_t *empty = full + p.slots;
 
-    const int nt = PW ? blockDim.x - 32 : blockDim.x;  // consumer threads
+    const int nt = blockDim.x - 32;  // consumer threads; the last warp is the TMA producer
     const int nwc = nt >> 5;
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(PW ? 288 : 256, 2) bilateral_window_kernel(con
     const long long period = 2LL * p.Hg;
     const long long d_mod = (long long)p.d % period;
     long long m_pos = 0;
-    if (tid == (PW ? nt : 0)) {
+    if (tid == nt) {
         m_pos = (p.gwy0 + r + (long long)(i0 - C) * p.d) % period;
         if (m_pos < 0) m_pos += period;
     }
@@ -593,29 +593,17 @@ __global__ void __launch_bounds__(PW ? 288 : 256, 2) bilateral_window_kernel(con
         m_pos += d_mod;
         if (m_pos >= period) m_pos -= period;
     };
-    // request every row whose slot is free, never blocking
-    auto top_up = [&]() {
-        while (next_load < n_load) {
-            if (lround > 0 && !mbar_test(&empty[lslot], (lround - 1) & 1)) break;
-            issue_load();
-        }
-    };
-
-    if constexpr (PW) {
-        if (warp == nwc) {
-            if (lane == 0) {
-                while (next_load < n_load) {
-                    // the producer runs rows ahead of the consumers: poll rarely, its spinning would take issue slots
-                    // from the warps doing the arithmetic
-                    if (lround > 0)
-                        while (!mbar_test(&empty[lslot], (lround - 1) & 1)) __nanosleep(1000);
-                    issue_load();
-                }
+    if (warp == nwc) {
+        if (lane == 0) {
+            while (next_load < n_load) {
+                // the producer runs rows ahead of the consumers: poll rarely, its spinning would take issue slots
+                // from the warps doing the arithmetic
+                if (lround > 0)
+                    while (!mbar_test(&empty[lslot], (lround - 1) & 1)) __nanosleep(1000);
+                issue_load();
             }
-            return;
         }
-    } else {
-        if (tid == 0) top_up();
+        return;
     }
 
     float *out_c = reinterpret_cast<float *>(p.out_c);
@@ -655,18 +643,7 @@ __global__ void __launch_bounds__(PW ? 288 : 256, 2) bilateral_window_kernel(con
         auto step = [&](auto ic, const int j) {
             constexpr int I = decltype(ic)::value;
             if (j >= n_load) return;
-            if constexpr (PW) {
-                mbar_wait(&full[slot], parity);
-            } else {
-                if (warp == 0) {
-                    if (lane == 0) top_up();
-                    while (!mbar_test(&full[slot], parity)) {
-                        if (lane == 0) top_up();
-                    }
-                } else {
-                    mbar_wait(&full[slot], parity);
-                }
-            }
+            mbar_wait(&full[slot], parity);
             pair_taps<TAPS, DMODE, MIRROR>((uint32_t)slot * RB, colb, rev, X[I]);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);  // the staged row is read exactly once per thread
@@ -751,6 +728,197 @@ __global__ void __launch_bounds__(PW ? 288 : 256, 2) bilateral_window_kernel(con
     };
     // warps that own no reflected column (all but the first / last strip's edge warps) run the variant without the
     // mirror selects; the choice is warp-uniform, so no thread diverges inside the step
+    if (__any_sync(0xffffffffu, rev != 0)) run(IC<1>{});
+    else run(IC<0>{});
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32, thread-level parallelism instead of registers (bilateral_stream_kernel).  ncu on the register-window kernel:
+// only 16 consumer warps fit per SM (112 registers), ptxas places every MUFU pair right in front of its consumer, and
+// the MUFU pipe that bounds the kernel idles 35 % of the time (stalls: wait, short scoreboard, MIO queue).  Here nothing
+// lives in registers across output rows: the taps are re-read from the staged rows (LDS.64), the differences are
+// formed where they are used, the row statistics sit in the per-thread shared-memory ring of the round-1 kernel -- 56
+// registers, FOUR blocks per SM (32 consumer warps), so that some warp always has exponentials to issue.
+// Same operations in the same order as bilateral_pairs_kernel: bit-identical planes.
+// ---------------------------------------------------------------------------------------------------------------
+template <int TAPS, int DMODE>
+__global__ void __maxnreg__(56) bilateral_stream_kernel(const BilateralParams bp) {
+    const ScaleParams &p = bp.sp;
+    pdl_launch_dependents();
+    constexpr int C = TAPS / 2;
+    constexpr int NL = PairPlan<TAPS, DMODE>::NL;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *rows = reinterpret_cast<float *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)p.slots * p.row_stride * sizeof(float));
+    uint64_t *empty = full + p.slots;
+    const uint32_t stats_base = smem_u32(empty + p.slots);  // slots x 256 threads x 16 bytes of row statistics
+
+    const int nt = blockDim.x - 32;  // 8 consumer warps; the last warp is the TMA producer
+    const int nwc = nt >> 5;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    int bx = blockIdx.x;
+    const int strip = bx % p.n_strips;
+    bx /= p.n_strips;
+    const int r = bx % p.d;
+    const int g = bx / p.d;
+    const int frame = blockIdx.y;
+
+    const int n_chain = (r < p.H) ? (p.H - r + p.d - 1) / p.d : 0;
+    const int i0 = g * p.seg;
+    const int n_out = min(p.seg, n_chain - i0);
+    if (n_out <= 0) return;
+    const int n_load = n_out + 2 * C;
+
+    const int x0 = strip * p.wt;
+    const int lo = max(0, x0 - p.halo_al);
+    const int hi = min(p.W, x0 + p.wt + p.halo_al);
+    const uint32_t row_bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(float);
+    const uint32_t RB = (uint32_t)p.row_stride * (uint32_t)sizeof(float);
+
+    if (tid == 0) {
+        for (int s = 0; s < p.slots; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nwc);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_wait();  // everything below touches global memory written or read by the previous launch
+
+    if (warp == nwc) {
+        if (lane == 0) {
+            const float *src = reinterpret_cast<const float *>(p.in) + (long long)frame * p.in_bstride + lo;
+            const uint64_t pol_in = policy_evict_first();  // c_s is dead once this launch has read it
+            int slot = 0;
+            uint32_t round = 0;
+            for (int j = 0; j < n_load; ++j) {
+                if (round > 0) {
+                    while (!mbar_test(&empty[slot], (round - 1) & 1)) __nanosleep(500);
+                }
+                const long long y = reflect_any(p.gwy0 + r + (long long)(i0 - C + j) * p.d, p.Hg) - p.gwy0 + p.row_off_in;
+                mbar_arrive_expect_tx(&full[slot], row_bytes);
+                if (p.l2_hints) tma_load_1d_hint(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[slot], pol_in);
+                else tma_load_1d(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes, &full[slot]);
+                if (++slot == p.slots) { slot = 0; ++round; }
+            }
+        }
+        return;
+    }
+
+    float *out_c = reinterpret_cast<float *>(p.out_c);
+    float *out_w = reinterpret_cast<float *>(p.out_w);
+
+    int xg = x0 + tid * 2;
+    const bool act = xg < p.W && xg < x0 + p.wt;
+    if (!act) xg = x0;  // idle threads shadow the first pair of the strip; their stores are masked
+    uint32_t colb[NL];
+    unsigned rev = 0;
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+        const int pcol = xg + (k - NL / 2) * (DMODE == 0 ? p.d : 2);  // even; one reflection at most
+        const bool left = pcol < 0, right = pcol >= p.W;
+        const int q = left ? (-2 - pcol) : (right ? (2 * p.W - 2 - pcol) : pcol);
+        colb[k] = smem_u32(rows) + (uint32_t)(q - lo) * 4u;  // absolute address of the tap in ring slot 0
+        if (left || right) rev |= 1u << k;
+    }
+    const uint32_t cb = smem_u32(rows) + (uint32_t)(xg - lo) * 4u;
+    const uint32_t stat_t = stats_base + (uint32_t)tid * 16u;  // this thread's entry in stats slot 0
+    const float var_factor = bp.var_factor_f;
+    const uint64_t pol_keep = p.l2_hints ? policy_evict_last() : 0ull;  // c_{s+1}: the next scale reads it back
+    const float kc = Taps<float, TAPS>::h(C) * Taps<float, TAPS>::h(C);
+
+    const long long orow0 = (long long)r + (long long)i0 * p.d;
+    float *c_dst = out_c ? out_c + (long long)frame * p.c_bstride + orow0 * p.c_pitch + xg : nullptr;
+    float *w_dst = out_w ? out_w + (long long)frame * p.w_bstride + orow0 * p.w_pitch + xg : nullptr;
+    const long long c_step = (long long)p.d * p.c_pitch, w_step = (long long)p.d * p.w_pitch;
+
+    auto run = [&](auto mirror) {
+        constexpr bool MIRROR = decltype(mirror)::value != 0;
+        int slot = 0, fslot = 0;  // slot of chain row j, slot of row j - 2C (first row of the window, next to be released)
+        uint32_t parity = 0;
+#pragma unroll 1
+        for (int j = 0; j < n_load; ++j) {
+            mbar_wait(&full[slot], parity);
+            {
+                // row statistics of the newest row, kept in the per-thread ring for the 2C later windows
+                u64 tv[TAPS];
+                pair_taps<TAPS, DMODE, MIRROR>((uint32_t)slot * RB, colb, rev, tv);
+                sts_p4(stat_t + (uint32_t)slot * (256u * 16u), row_stats<TAPS>(tv));
+            }
+            if (j >= 2 * C) {
+                int cs = fslot + C;
+                if (cs >= p.slots) cs -= p.slots;
+                const u64 xc = lds64(cb + (uint32_t)cs * RB);
+                // window moments from the row statistics (differences only), rows top to bottom
+                u64 s1 = 0ull, s2 = 0ull;
+                int ws = fslot;
+#pragma unroll
+                for (int i = 0; i < TAPS; ++i) {
+                    const float hi_ = Taps<float, TAPS>::h(i);
+                    const P4 st = lds_p4(stat_t + (uint32_t)ws * (256u * 16u));
+                    if (i == C) {
+                        s1 = fma2(pk2(-hi_, -hi_), st.lo, s1);
+                        s2 = fma2(pk2(hi_, hi_), st.hi, s2);
+                    } else {
+                        const u64 dc = sub2(xc, lds64(cb + (uint32_t)ws * RB));
+                        const u64 t = fma2(pk2(-2.0f, -2.0f), st.lo, dc);
+                        const u64 u = fma2(dc, t, st.hi);
+                        s1 = fma2(pk2(hi_, hi_), sub2(dc, st.lo), s1);
+                        s2 = fma2(pk2(hi_, hi_), u, s2);
+                    }
+                    if (++ws == p.slots) ws = 0;
+                }
+                float v0, v1;
+                up2(sub2(s2, mul2(s1, s1)), v0, v1);
+                v0 = (v0 <= 0.0f) ? 1e-20f : v0;
+                v1 = (v1 <= 0.0f) ? 1e-20f : v1;
+                const u64 nhi = pk2(-0.72134752044448170f * rcp_fast(fmaxf(v0 * var_factor, 1e-37f)),
+                                    -0.72134752044448170f * rcp_fast(fmaxf(v1 * var_factor, 1e-37f)));
+                u64 num = 0ull, den = pk2(kc, kc);
+                ws = fslot;
+#pragma unroll
+                for (int i = 0; i < TAPS; ++i) {
+                    u64 tv[TAPS];
+                    pair_taps<TAPS, DMODE, MIRROR>((uint32_t)ws * RB, colb, rev, tv);
+#pragma unroll
+                    for (int k = 0; k < TAPS; ++k) {
+                        if (i == C && k == C) continue;
+                        const float lk = TapLog2<TAPS>::l(i) + TapLog2<TAPS>::l(k);
+                        const u64 dd = sub2(xc, tv[k]);
+                        float a0, a1;
+                        up2(fma2(mul2(dd, dd), nhi, pk2(lk, lk)), a0, a1);
+                        const u64 gw = pk2(exp2_fast(a0), exp2_fast(a1));
+                        den = add2(den, gw);
+                        num = fma2(gw, dd, num);
+                    }
+                    if (++ws == p.slots) ws = 0;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[fslot]);  // the oldest window row is not needed any more
+                if (++fslot == p.slots) fslot = 0;
+                float n0, n1, d0, d1, x0v, x1v;
+                up2(num, n0, n1);
+                up2(den, d0, d1);
+                up2(xc, x0v, x1v);
+                const float c0 = x0v - n0 * rcp_fast(d0), c1 = x1v - n1 * rcp_fast(d1);
+                if (act) {
+                    if (c_dst) {
+                        if (pol_keep)
+                            asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(c_dst), "f"(c0), "f"(c1), "l"(pol_keep) : "memory");
+                        else
+                            *reinterpret_cast<float2 *>(c_dst) = make_float2(c0, c1);
+                    }
+                    if (w_dst) __stcs(reinterpret_cast<float2 *>(w_dst), make_float2(x0v - c0, x1v - c1));
+                }
+                if (c_dst) c_dst += c_step;
+                if (w_dst) w_dst += w_step;
+            }
+            if (++slot == p.slots) { slot = 0; parity ^= 1; }
+        }
+    };
     if (__any_sync(0xffffffffu, rev != 0)) run(IC<1>{});
     else run(IC<0>{});
 }
@@ -849,17 +1017,34 @@ static bool plan_bilateral(ScaleParams &p, int taps, int esize, int batch) {
     return true;
 }
 
-// WB_K2_WINDOW in the environment: 0 selects the round-1 kernel (bilateral_pairs_kernel), 1 the register-window kernel
-// with a producer warp, 2 (default) the register-window kernel whose thread 0 streams the rows -- for A/B measurements
-// and the bit-identity test.
+// WB_K2_WINDOW in the environment: 0 selects the round-1 kernel (bilateral_pairs_kernel), 1 (default) the
+// register-window kernel, 3 the low-register streaming kernel (four blocks per SM) -- for A/B measurements and the
+// bit-identity test.
 static int k2_window_mode() {
     const char *e = getenv("WB_K2_WINDOW");  // read on every call: the bit-identity test flips it inside one process
-    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+    return (e && (e[0] == '0' || e[0] == '3')) ? e[0] - '0' : 1;
 }
 
-template <int TAPS, int DMODE, bool PW>
+template <int TAPS, int DMODE>
+static int launch_bilateral_stream(const BilateralParams &bp, int batch, cudaStream_t st) {
+    auto kern = bilateral_stream_kernel<TAPS, DMODE>;
+    const ScaleParams &p = bp.sp;
+    const size_t smem = (size_t)p.slots * p.row_stride * sizeof(float) + 16 * (size_t)p.slots + kPairStats * (size_t)p.slots;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
+    return launch_pdl<BilateralParams>(kern, grid, dim3(256 + 32), smem, st, bp);
+}
+
+template <int TAPS, int DMODE>
 static int launch_bilateral_window(const BilateralParams &bp, int batch, cudaStream_t st) {
-    auto kern = bilateral_window_kernel<TAPS, DMODE, PW>;
+    auto kern = bilateral_window_kernel<TAPS, DMODE>;
     const ScaleParams &p = bp.sp;
     const size_t smem = (size_t)p.slots * p.row_stride * sizeof(float) + 16 * (size_t)p.slots;
     static bool configured[64] = {};
@@ -871,14 +1056,14 @@ static int launch_bilateral_window(const BilateralParams &bp, int batch, cudaStr
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
-    return launch_pdl<BilateralParams>(kern, grid, dim3(PW ? 256 + 32 : 256), smem, st, bp);
+    return launch_pdl<BilateralParams>(kern, grid, dim3(256 + 32), smem, st, bp);
 }
 
 template <int TAPS, int DMODE>
 static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStream_t st) {
     const int wm = k2_window_mode();
-    if (wm == 1) return launch_bilateral_window<TAPS, DMODE, true>(bp, batch, st);
-    if (wm == 2) return launch_bilateral_window<TAPS, DMODE, false>(bp, batch, st);
+    if (wm == 1) return launch_bilateral_window<TAPS, DMODE>(bp, batch, st);
+    if (wm == 3) return launch_bilateral_stream<TAPS, DMODE>(bp, batch, st);
     auto kern = bilateral_pairs_kernel<TAPS, DMODE>;
     const ScaleParams &p = bp.sp;
     const size_t smem = (size_t)p.slots * p.row_stride * sizeof(float) + 16 * (size_t)p.slots + kPairStats * (size_t)p.slots;
@@ -894,8 +1079,10 @@ static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStre
     return launch_pdl<BilateralParams>(kern, grid, dim3(256 + 32), smem, st, bp);
 }
 
+static int k2_window_mode();
+
 // Geometry for the fp32 pair kernel: 256 consumer threads x 2 pixels = 512-column strips.
-static bool plan_bilateral_pairs(ScaleParams &p, int taps, int batch) {
+static bool plan_bilateral_pairs(ScaleParams &p, int taps, int batch, int occ) {
     const int c = taps / 2;
     p.wt = 512;
     p.n_strips = (p.W + p.wt - 1) / p.wt;
@@ -905,14 +1092,15 @@ static bool plan_bilateral_pairs(ScaleParams &p, int taps, int batch) {
     p.row_stride = (int)rs;
     int slots = taps + 3;
     const int min_slots = taps + 1;
-    // two resident blocks per SM (register-limited anyway): keep a block under half of the shared memory if possible
-    while (slots > min_slots && (long long)slots * (p.row_stride * 4 + 16LL + kPairStats) > kMaxSmem / 2 - 1024) --slots;
+    // `occ` resident blocks per SM (register-limited: 2, or 4 for the streaming kernel): keep a block under that share
+    // of the shared memory if possible
+    while (slots > min_slots && (long long)slots * (p.row_stride * 4 + 16LL + kPairStats) > kMaxSmem / occ - 1024) --slots;
     if ((long long)slots * (p.row_stride * 4 + 16LL + kPairStats) > kMaxSmem) return false;
     p.slots = slots;
     const int n_max = (p.H + p.d - 1) / p.d;
     // Compute-bound kernel: about 4 waves of 2 resident blocks per SM; halo rows only cost L2 reads.
     const long long chains = (long long)p.n_strips * (p.d < p.H ? p.d : p.H) * batch;
-    const long long target = 4LL * 2LL * device_sm_count();
+    const long long target = 4LL * occ * device_sm_count();
     long long per_chain = (target + chains - 1) / chains;
     if (per_chain < 1) per_chain = 1;
     int seg = (int)((n_max + per_chain - 1) / per_chain);
@@ -929,7 +1117,8 @@ static int dispatch_bilateral(BilateralParams &bp, int batch, cudaStream_t st) {
     ScaleParams &p = bp.sp;
     if constexpr (sizeof(T) == 4) {
         // packed fp32x2 pair kernel: dilation 1 or even (every scale of a dyadic cascade)
-        if (fast_path_ok(p, TAPS, 4) && (p.d == 1 || p.d % 2 == 0) && plan_bilateral_pairs(p, TAPS, batch))
+        if (fast_path_ok(p, TAPS, 4) && (p.d == 1 || p.d % 2 == 0) &&
+            plan_bilateral_pairs(p, TAPS, batch, k2_window_mode() == 3 ? 4 : 2))
             return p.d == 1 ? launch_bilateral_pairs<TAPS, 1>(bp, batch, st) : launch_bilateral_pairs<TAPS, 0>(bp, batch, st);
     }
     if (fast_path_ok(p, TAPS, (int)sizeof(T)) && plan_bilateral(p, TAPS, (int)sizeof(T), batch)) {
@@ -971,6 +1160,7 @@ int wb_atrous_scale_bilateral(const void *in, void *out_c, void *out_w, int batc
     p.c_pitch = out_c_pitch; p.c_bstride = out_c_bstride;
     p.w_pitch = out_w_pitch; p.w_bstride = out_w_bstride;
     bp.var_factor = var_factor;
+    bp.var_factor_f = (float)var_factor;
     bp.var_factor_f = (float)var_factor;
     p.l2_hints = wb::l2_hints_enabled();
     cudaStream_t st = (cudaStream_t)stream;

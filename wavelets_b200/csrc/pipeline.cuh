@@ -42,7 +42,24 @@ struct ScaleParams {
     int n_peers;
     long long peer_y0[kMaxPeers + 1];
     const void *peer_in[kMaxPeers];
+    // --- halo push (wb_atrous_scale_band_push): the rows of c_{s+1} that fall into a neighbour's halo of the NEXT scale
+    // are stored a second time, straight into that neighbour's padded band buffer (posted writes over NVLink that overlap
+    // with this launch's own streaming) -- the next scale then reads local memory only.  push_up / push_dn: address, in
+    // the upper / lower neighbour's buffer, of this band's output row 0 (same pitch as out_c); output rows
+    // [0, push_up_rows) go up, rows [push_dn_from, H) go down.  nullptr: no neighbour on that side.
+    void *push_up, *push_dn;
+    int push_up_rows, push_dn_from;
 };
+
+// Second store of a c_{s+1} vector into the neighbours' halo zones (see ScaleParams::push_up).  `c_ptr` points at the
+// vector inside out_c (row `row` of the band), `base` at row 0 of out_c incl. its row offset.
+template <typename T, typename V>
+__device__ __forceinline__ void push_store(const ScaleParams &p, const T *c_ptr, const T *base, int row, const V &val) {
+    if (p.push_up && row < p.push_up_rows)
+        *reinterpret_cast<V *>(reinterpret_cast<T *>(p.push_up) + (c_ptr - base)) = val;
+    if (p.push_dn && row >= p.push_dn_from)
+        *reinterpret_cast<V *>(reinterpret_cast<T *>(p.push_dn) + (c_ptr - base)) = val;
+}
 
 // Address of global input row gy (already reflected into [0, Hg)) of this launch's frame-0 window.
 template <typename T>
@@ -440,6 +457,8 @@ inline bool fast_path_ok(const ScaleParams &p, int taps, int esize) {
     if (p.in_pitch % V || p.in_bstride % V || !aligned16(p.in)) return false;
     if (p.out_c && (p.c_pitch % V || p.c_bstride % V || !aligned16(p.out_c))) return false;
     if (p.out_w && (p.w_pitch % V || p.w_bstride % V || !aligned16(p.out_w))) return false;
+    // the vector path stores 16-byte vectors into the neighbours' buffers too (halo push)
+    if ((p.push_up && !aligned16(p.push_up)) || (p.push_dn && !aligned16(p.push_dn))) return false;
     return true;
 }
 

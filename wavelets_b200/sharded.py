@@ -26,7 +26,7 @@ from . import _lib
 from .scaling import B3spline
 
 __all__ = ["frame_shard", "band_range", "halo_rows", "exchange_plan", "exchange_halos", "BandedTransform",
-           "band_scale_p2p", "PeerBandBuffers", "BandedWow", "distributed_abs_median"]
+           "band_scale_p2p", "band_scale_push", "push_plan", "PeerBandBuffers", "BandedWow", "distributed_abs_median"]
 
 
 def frame_shard(n_frames: int, rank: int, world: int) -> range:
@@ -129,6 +129,40 @@ def band_scale_p2p(peer_ptrs, peer_y0, rank, out_c, out_w, width, pitch, scale, 
             _lib.stream_ptr(device)))
 
 
+def band_scale_push(ext_in, pad, out_c, out_pad, w_out, band_rows, width, height, y0, scale, taps_code,
+                    push_up_ptr=0, push_up_rows=0, push_dn_ptr=0, push_dn_rows=0):
+    """One scale of one band that also stores the next scale's halo rows into the neighbours' padded buffers:
+    wb_atrous_scale_band_push.  ``push_up_ptr`` / ``push_dn_ptr``: address (valid on this device) of the row that this
+    band's output row 0 occupies in the upper / lower neighbour's padded c buffer (0: no neighbour)."""
+    lib = _lib.load(require_cuda=True)
+    with torch.cuda.device(ext_in.device):
+        _lib.check(lib.wb_atrous_scale_band_push(
+            ext_in.data_ptr(), out_c.data_ptr(), w_out.data_ptr() if w_out is not None else None, band_rows, width,
+            height, y0, pad, ext_in.stride(0), out_pad, out_c.stride(0), 0,
+            w_out.stride(0) if w_out is not None else 0, push_up_ptr or None, int(push_up_rows), push_dn_ptr or None,
+            int(push_dn_rows), scale, taps_code, _lib.dtype_code(ext_in.dtype), _lib.stream_ptr(ext_in.device)))
+
+
+def push_plan(height: int, world: int, rank: int, halo_next: int, pad: int, row_bytes: int, base_ptrs):
+    """Where band ``rank`` pushes the halo rows of the NEXT scale (``halo_next`` rows beyond each band edge).
+
+    ``base_ptrs[k]``: address of row 0 of rank k's padded buffer (the half that receives c_{s+1}); row ``pad + i`` of a
+    buffer holds that rank's band row i.  Returns (push_up_ptr, push_up_rows, push_dn_ptr, push_dn_rows): my output row
+    0 sits ``rows_up`` rows below the upper neighbour's band start and ``rows_mine`` rows above the lower neighbour's."""
+    y0, y1 = band_range(height, rank, world)
+    rows = y1 - y0
+    up = dn = 0
+    n_up = n_dn = 0
+    if halo_next > 0 and rank > 0:
+        a, b = band_range(height, rank - 1, world)
+        n_up = min(halo_next, rows)
+        up = int(base_ptrs[rank - 1]) + (pad + (b - a)) * row_bytes
+    if halo_next > 0 and rank < world - 1:
+        n_dn = min(halo_next, rows)
+        dn = int(base_ptrs[rank + 1]) + (pad - rows) * row_bytes
+    return up, n_up, dn, n_dn
+
+
 _PEER_BUFFERS: dict = {}
 
 
@@ -140,10 +174,15 @@ class PeerBandBuffers:
     def __init__(self, rows_max: int, width: int, dtype: torch.dtype, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
-        self.buf = symm_mem.empty((2, rows_max, width), dtype=dtype, device=device)
+        self.shape = (2, rows_max, width)
+        self.buf = symm_mem.empty(self.shape, dtype=dtype, device=device)
         self.handle = symm_mem.rendezvous(self.buf, group)
         half = rows_max * width * self.buf.element_size()
         self._ptrs = [[int(base) + b * half for base in self.handle.buffer_ptrs] for b in range(2)]
+
+    def peer(self, k: int) -> torch.Tensor:
+        """Rank k's whole buffer ``(2, rows_max, width)`` as a tensor on THIS device (peer-mapped memory)."""
+        return self.handle.get_buffer(k, self.shape, self.buf.dtype)
 
     def ptrs(self, b: int):
         return self._ptrs[b]
@@ -160,12 +199,55 @@ class BandedTransform:
     CPU tensor with a custom ``scale_fn`` in the gloo tests).  Returns this rank's rows of the coefficient planes,
     shape ``(level + 1, band_rows, W)``.  ``scale_fn`` computes one scale of one band (default: the CUDA kernel)."""
 
-    def __init__(self, scaling_function_class=B3spline, group=None, scale_fn=None, poison=False, p2p=False):
+    def __init__(self, scaling_function_class=B3spline, group=None, scale_fn=None, poison=False, p2p=False, push=False):
         self.scaling_function_class = scaling_function_class
         self.group = group
         self.scale_fn = scale_fn or _cuda_band_scale
         self.poison = poison  # tests: NaN-fill the padded buffers so that any read of an unfilled halo row shows up
         self.p2p = p2p        # halo rows read in place from the neighbours' buffers (NVLink), no exchange
+        self.push = push      # halo rows of the next scale stored into the neighbours' buffers by the scale kernel
+
+    def _call_push(self, band, planes, level, global_height, sf, rank, world):
+        """Compute and communication in ONE kernel per scale, transfers as posted writes: the scale kernel stores the
+        rows of c_{s+1} that the neighbours need at scale s+1 straight into their padded buffers (symmetric memory over
+        NVLink) while it streams its own band; every scale then reads local memory only.  One device-side barrier per
+        scale orders the ranks (no host synchronisation).  Single-hop halos only (the caller checks)."""
+        rows, width = band.shape
+        n_taps = len(sf.coefficients_1d)
+        rows_max = band_range(global_height, 0, world)[1]
+        pad = halo_rows(level - 1, n_taps)
+        key = ("push", id(self.group), rows_max + 2 * pad, width, band.dtype, band.device.index)
+        peer = _PEER_BUFFERS.get(key)
+        if peer is None:
+            peer = _PEER_BUFFERS[key] = PeerBandBuffers(rows_max + 2 * pad, width, band.dtype, band.device, self.group)
+        if self.poison:
+            peer.buf.fill_(float("nan"))  # safe: the previous call ended with a barrier
+            peer.barrier()                # ... and no neighbour may write its scale-0 halo rows before the fill
+        row_bytes = width * band.element_size()
+        ext = peer.buf
+        ext[0, pad:pad + rows].copy_(band)
+        # halo of scale 0: my edge rows go to the neighbours by plain peer copies
+        h0 = halo_rows(0, n_taps)
+        if rank > 0:
+            a, b = band_range(global_height, rank - 1, world)
+            peer.peer(rank - 1)[0, pad + (b - a): pad + (b - a) + h0].copy_(band[:h0])
+        if rank < world - 1:
+            peer.peer(rank + 1)[0, pad - h0: pad].copy_(band[rows - h0:])
+        y0 = band_range(global_height, rank, world)[0]
+        for s in range(level):
+            # every rank has received its halo of c_s and has finished reading the half this scale overwrites
+            peer.barrier()
+            last = s == level - 1
+            cur = ext[s & 1]
+            if last:
+                band_scale_push(cur, pad, planes[level], 0, planes[s], rows, width, global_height, y0, s, sf.taps_code)
+            else:
+                up, n_up, dn, n_dn = push_plan(global_height, world, rank, halo_rows(s + 1, n_taps), pad, row_bytes,
+                                               peer.ptrs((s + 1) & 1))
+                band_scale_push(cur, pad, ext[(s + 1) & 1], pad, planes[s], rows, width, global_height, y0, s,
+                                sf.taps_code, up, n_up, dn, n_dn)
+        peer.barrier()  # nobody may refill the buffers (next call) while a neighbour still reads them
+        return planes
 
     def _call_p2p(self, band, planes, level, global_height, sf, rank, world):
         rows, width = band.shape
@@ -201,6 +283,11 @@ class BandedTransform:
         if level == 0:
             planes[0].copy_(band)
             return planes
+        if self.push and world > 1:
+            min_rows = min(band_range(global_height, k, world)[1] - band_range(global_height, k, world)[0]
+                           for k in range(world))
+            if halo_rows(level - 1, n_taps) <= min_rows:  # single-hop halos; otherwise the exchange below (multi-hop)
+                return self._call_push(band, planes, level, global_height, sf, rank, world)
         if self.p2p and world > 1:
             return self._call_p2p(band, planes, level, global_height, sf, rank, world)
         pad = halo_rows(level - 1, n_taps) if world > 1 else 0

@@ -17,7 +17,7 @@ from .scaling import B3spline
 from .wavelets import (AtrousTransform, Coefficients, _Noise, _frame_layout, abs_median_noise, atrous_scale,
                        bilateral_list, plane_moments, synthesis, to_device_image)
 
-__all__ = ["denoise", "wow", "wow_batch", "generalized_anscombe", "enhance", "richardson_lucy"]
+__all__ = ["denoise", "wow", "wow_batch", "wow_stream", "generalized_anscombe", "enhance", "richardson_lucy"]
 
 # Development switch (tests compare the fused one-pass WOW scales against the two-pass route bit for bit).
 FUSED_WOW = True
@@ -258,6 +258,70 @@ def wow_batch(frames, scaling_function=B3spline, n_scales=None, weights=[], whit
                                    whitening, soft_threshold, nz)
     noise_out = None if nz is None else (nz.dev if nz.dev is not None else nz.host)
     return recon, planes, noise_out
+
+
+def wow_stream(frames, out=None, depth=2, scaling_function=B3spline, **kwargs):
+    """NEW entry point (no reference equivalent): ``wow()`` of a sequence of HOST frames ``(N, H, W)`` into a host array
+    ``(N, H, W)`` of reconstructions, overlapping the host->device copy of frame n+1, the WOW of frame n and the
+    device->host copy of the reconstruction of frame n-1 on three CUDA streams (``depth`` device buffers in flight).
+
+    ``frames`` / ``out``: torch CPU tensors (pinned memory is used as is, pageable memory is staged through a pinned copy)
+    or NumPy arrays; ``kwargs`` are those of ``wow`` (scalar ``noise`` only).  Returns ``out`` (allocated pinned when None;
+    a NumPy view of it for NumPy input).  Per-frame results are identical to ``wow(frame, ...)[0]``."""
+    was_numpy = not isinstance(frames, torch.Tensor)
+    host = torch.from_numpy(np.ascontiguousarray(frames)) if was_numpy else frames
+    if host.ndim != 3:
+        raise ValueError("wow_stream() takes a stack of frames (N, H, W)")
+    if host.is_cuda:
+        raise ValueError("wow_stream() takes host frames; use wow_batch() for device-resident stacks")
+    if host.dtype not in (torch.float32, torch.float64):
+        host = host.to(torch.float64)  # the reference's recast rule for integer inputs
+    if not host.is_pinned():
+        host = host.contiguous().pin_memory()
+    n, h, w = host.shape
+    if out is None:
+        out = torch.empty((n, h, w), dtype=host.dtype).pin_memory()
+    out_t = torch.from_numpy(out) if isinstance(out, np.ndarray) else out
+    if tuple(out_t.shape) != (n, h, w) or out_t.dtype != host.dtype:
+        raise ValueError("out must be (N, H, W) of the frame dtype")
+    staged = None if out_t.is_pinned() else torch.empty(out_t.shape, dtype=out_t.dtype).pin_memory()
+    dst = out_t if staged is None else staged
+    _lib.load(require_cuda=True)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    depth = max(1, min(int(depth), n))
+    s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    caller = torch.cuda.current_stream(dev)
+    for st in (s_in, s_cmp, s_out):
+        st.wait_stream(caller)
+    d_in = [torch.empty((h, w), dtype=host.dtype, device=dev) for _ in range(depth)]
+    d_out = [None] * depth
+    ev_in = [torch.cuda.Event() for _ in range(depth)]
+    ev_cmp = [torch.cuda.Event() for _ in range(depth)]
+    ev_out = [torch.cuda.Event() for _ in range(depth)]
+    for i in range(n):
+        b = i % depth
+        with torch.cuda.stream(s_in):
+            if i >= depth:
+                s_in.wait_event(ev_cmp[b])       # the WOW that read d_in[b] is done
+            d_in[b].copy_(host[i], non_blocking=True)
+            ev_in[b].record(s_in)
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(ev_in[b])
+            if i >= depth:
+                s_cmp.wait_event(ev_out[b])      # the download of d_out[b] is done (its memory may be reused)
+            d_out[b], _ = wow(d_in[b], scaling_function=scaling_function, **kwargs)
+            ev_cmp[b].record(s_cmp)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_cmp[b])
+            dst[i].copy_(d_out[b], non_blocking=True)
+            d_out[b].record_stream(s_out)
+            ev_out[b].record(s_out)
+    for st in (s_in, s_cmp, s_out):
+        caller.wait_stream(st)
+    s_out.synchronize()  # the result lives in host memory: hand it back complete
+    if staged is not None:
+        out_t.copy_(staged)
+    return out if (isinstance(out, np.ndarray) or not was_numpy) else out_t.numpy()
 
 
 def _wow_coefficients(co, weights, whitening, denoise_coefficients, bilateral, soft_threshold, plan=None):
