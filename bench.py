@@ -484,7 +484,8 @@ def run_ours(args):
 
     # the call users make: wow(host frame) -> host reconstruction (64 MiB in, 64 MiB out per frame), 3-stream pipeline
     wow_out = torch.empty((h, w), dtype=torch.float32).pin_memory()
-    wow_frames = host_in.abs().mul_(50).unsqueeze(0).expand(e2e_steps, h, w)
+    wow_in = host_in.abs().mul_(50).pin_memory()
+    wow_frames = wow_in.unsqueeze(0).expand(e2e_steps, h, w)
     wow_view = wow_out.unsqueeze(0).expand(e2e_steps, h, w)
     wb.wow_stream(wow_frames[:2], out=wow_view[:2])
     barrier()

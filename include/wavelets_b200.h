@@ -263,6 +263,16 @@ int wb_atrous_axis(const void *in, const void *sub_from, void *out_c, void *out_
                    long long n_inner, int scale, int taps, int dtype, int border, void *stream);
 
 /*
+ * One scale of the BILATERAL cascade of a 1-D signal (ndim = 1, shape (1, 1, n2)) or a 3-D volume (ndim = 3, shape
+ * (n0, n1, n2), C-contiguous): replaces watroo/wavelets.py:433-442 for those inputs -- sdev_loc (:24-32) through the
+ * n-D branches of convolution (:46-69: 1-D whole-sample 'mirror' border, 3-D half-sample symmetric) and the
+ * dimension-generic atrous_convolution (:74-105: K^ndim - 1 range-weighted taps through np.pad 'symmetric').
+ * out_c = c_{s+1}, out_w = c_s - c_{s+1} (either may be NULL).  A parity path: one thread per sample.
+ */
+int wb_atrous_scale_bilateral_nd(const void *in, void *out_c, void *out_w, int ndim, long long n0, long long n1,
+                                 long long n2, int scale, int taps, int dtype, double var_factor, void *stream);
+
+/*
  * Dense 2-D correlation with a small arbitrary kernel and the symmetric border: the PSF filters of richardson_lucy
  * (watroo/utils.py:252-255 with the flipped PSF = convolution, :283-286 with the PSF as is = correlation; both
  * cv2.filter2D(..., (-1,-1), 0, cv2.BORDER_REFLECT)).  `kernel` is a DEVICE array of kh*kw coefficients of the image

@@ -78,6 +78,10 @@ SIGMA_E_1D = {
     "b3spline": np.array([0.72514976, 0.28538683, 0.17901161, 0.12222841, 0.08469601, 0.06027006, 0.04242257,
                           0.02919823, 0.01805671, 0.01383672, 0.00943623]),
 }
+SIGMA_E_3D_BILATERAL = {
+    "triangle": np.array([0.3828863, 0.36182913, 0.19520299, 0.08498861, 0.03363142]),
+    "b3spline": np.array([0.44111772, 0.3552894, 0.16137159, 0.05769064, 0.01932497]),
+}
 SIGMA_E_3D = {
     "triangle": np.array([0.89736751, 0.19514386, 0.06239262, 0.02311278, 0.00939645]),
     "b3spline": np.array([0.95633954, 0.12491933, 0.03933029, 0.01489642, 0.0064108]),
@@ -88,9 +92,9 @@ def sigma_e(name: str, bilateral=None, ndim: int = 2) -> np.ndarray:
     """wavelets.py:199-219: the table of the data's dimensionality; the bilateral table (restated for 2-D only) is
     selected whenever ``bilateral is not None``."""
     if bilateral is not None:
-        if ndim != 2:
-            raise ValueError("oracle: bilateral tables are restated for 2-D images only")
-        return SIGMA_E_2D_BILATERAL[name]
+        if ndim == 1:
+            raise AttributeError("sigma_e_1d_bilateral")  # the reference has no such table
+        return {2: SIGMA_E_2D_BILATERAL, 3: SIGMA_E_3D_BILATERAL}[ndim][name]
     return {1: SIGMA_E_1D, 2: SIGMA_E_2D, 3: SIGMA_E_3D}[ndim][name]
 
 
@@ -241,6 +245,8 @@ def bilateral_smooth(arr: np.ndarray, name: str, variance: np.ndarray, s: int) -
     out = (k_c x + sum_t g_t x_t) / (k_c + sum_t g_t),  g_t = k_t exp(-(x - x_t)^2 / V / 2) over the K^2-1
     off-centre taps, x_t read through the symmetric border, V taken at the output pixel.  All arithmetic in the
     image dtype (the kernel is cast with .astype(arr.dtype), wavelets.py:438)."""
+    if arr.ndim != 2:
+        return bilateral_smooth_nd(arr, name, variance, s)
     taps = TAPS[name]
     k2d = np.outer(taps, taps).astype(arr.dtype)
     n = len(taps)
@@ -259,6 +265,33 @@ def bilateral_smooth(arr: np.ndarray, name: str, variance: np.ndarray, s: int) -
             weight = k * np.exp(-((arr - shifted) ** 2) / variance / 2)
             norm += weight
             out += shifted * weight
+    out /= norm
+    return out
+
+
+def bilateral_smooth_nd(arr: np.ndarray, name: str, variance: np.ndarray, s: int) -> np.ndarray:
+    """atrous_convolution on a 1-D signal or a 3-D volume (wavelets.py:74-105 is dimension-generic): the kernel is the
+    n-fold tensor product of the taps, the border is np.pad 'symmetric' on every axis (also in 1-D, where the plain
+    smooth -- and hence the variance -- uses 'mirror')."""
+    taps = TAPS[name]
+    n = len(taps)
+    c = n // 2
+    d = 2 ** s
+    kern = taps
+    for _ in range(arr.ndim - 1):
+        kern = np.multiply.outer(kern, taps)
+    kern = kern.astype(arr.dtype)
+    padded = np.pad(arr, [(c * d, c * d)] * arr.ndim, mode="symmetric")
+    centre = (c,) * arr.ndim
+    out = kern[centre] * arr
+    norm = np.full_like(arr, kern[centre])
+    for index in np.ndindex(*kern.shape):
+        if index == centre:
+            continue
+        shifted = padded[tuple(slice(i * d, i * d + m) for i, m in zip(index, arr.shape))]
+        weight = kern[index] * np.exp(-((arr - shifted) ** 2) / variance / 2)
+        norm += weight
+        out += shifted * weight
     out /= norm
     return out
 
@@ -285,8 +318,6 @@ def atrous_transform(arr: np.ndarray, level: int, name: str = "b3spline", bilate
     Integer and big-endian inputs are recast to float64 (wavelets.py:297,319-320); the input is never modified."""
     if arr.ndim > 3:
         raise ValueError("Unsupported number of dimensions")  # wavelets.py:316-317
-    if arr.ndim != 2 and bilateral is not None:
-        raise ValueError("oracle: the bilateral cascade is restated for 2-D images only")
     if arr.dtype in _RECAST:
         arr = np.float64(arr)
     sb = _bilateral_list(bilateral, level)
@@ -393,7 +424,7 @@ def wow(data: np.ndarray, name: str = "b3spline", n_scales=None, weights=(), whi
         n_scales = max_scales if h < 1 else len(denoise_coefficients)  # utils.py:123-124
     elif n_scales > max_scales:
         n_scales = max_scales
-    table_len = len(sigma_e(name, bilateral))
+    table_len = len(sigma_e(name, bilateral, data.ndim))
     if len(denoise_coefficients) >= table_len:  # utils.py:135-138
         warnings.warn(f"Required number of scales lager then the maximum for scaling function. Using {table_len}.")
         n_scales = table_len

@@ -173,6 +173,48 @@ def main_f2():
     save("f2_noise_weights_anscombe", **out)
 
 
+def main_nd_bilateral():
+    """Bilateral cascade of 1-D signals and 3-D volumes (wavelets.py:433-442 on n-D input: variance through the n-D
+    branches of convolution, gather through the dimension-generic atrous_convolution), plus denoise of a volume (the
+    3-D bilateral sigma_e table exists; the reference has no 1-D one)."""
+    for dt in ("float32", "float64"):
+        out = {}
+        cases = [((200,), 4, "b3spline", dict(bilateral=1)), ((64,), 3, "triangle", dict(bilateral=[2, 1.5], bilateral_scaling=True)),
+                 ((10, 18, 22), 3, "b3spline", dict(bilateral=1)), ((6, 20, 12), 2, "triangle", dict(bilateral=1.5))]
+        for k, (shape, level, sf, kw) in enumerate(cases):
+            arr = (gaussian(shape, 60 + k, "float64") * 3 + 10 + 4 * np.sin(np.arange(shape[-1]) / 7.0)).astype(dt)
+            co = AtrousTransform(SF[sf], **kw)(arr.copy(), level)
+            out[f"in{k}"] = arr
+            out[f"out{k}"] = co.data.copy()
+            out[f"level{k}"] = np.int64(level)
+            if arr.ndim == 3:
+                out[f"noise{k}"] = np.float64(co.get_noise())
+                out[f"dn{k}"] = denoise(arr.copy(), [3, 2][:level], scaling_function=SF[sf], bilateral=kw["bilateral"])
+        save(f"transform_nd_bilateral_{dt}", n=np.int64(len(cases)), **out)
+
+
+WOW_ND_CASES = [((300,), {}), ((300,), dict(denoise_coefficients=[4, 2], weights=[1.5, 1.0, 0.5])),
+                ((257,), dict(scaling_function="triangle", h=0.3, preserve_variance=True, denoise_coefficients=[3], noise=1.2)),
+                ((24, 40, 44), {}), ((24, 40, 44), dict(denoise_coefficients=[4, 2], soft_threshold=False)),
+                ((24, 36, 40), dict(bilateral=1, denoise_coefficients=[3, 1], n_scales=2))]
+
+
+def main_wow_nd():
+    """wow() on 1-D signals and 3-D volumes (utils.py:121-219 is dimension-generic)."""
+    for dt in ("float32", "float64"):
+        out = {}
+        for k, (shape, kw) in enumerate(WOW_ND_CASES):
+            kw = dict(kw)
+            sf = SF[kw.pop("scaling_function", "b3spline")]
+            arr = (gaussian(shape, 80 + k, "float64") * 4 + 30 + 10 * np.sin(np.arange(shape[-1]) / 9.0)).astype(dt)
+            recon, co = wow(arr.copy(), scaling_function=sf, **kw)
+            out[f"in{k}"] = arr
+            out[f"recon{k}"] = recon
+            out[f"planes{k}"] = co.data.copy()
+            out[f"noise{k}"] = np.float64(np.nan if co.noise is None else co.noise)
+        save(f"wow_nd_{dt}", n=np.int64(len(WOW_ND_CASES)), **out)
+
+
 def main():
     assert watroo.__version__ == "0.0.4", watroo.__version__
     if "--callers" in sys.argv:
@@ -186,6 +228,12 @@ def main():
     if "--f2" in sys.argv:
         warnings.simplefilter("ignore")
         return main_f2()
+    if "--nd-bilateral" in sys.argv:
+        warnings.simplefilter("ignore")
+        return main_nd_bilateral()
+    if "--wow-nd" in sys.argv:
+        warnings.simplefilter("ignore")
+        return main_wow_nd()
     warnings.simplefilter("ignore")
     if "--nd" in sys.argv:  # only the 1-D / 3-D fixtures (added later; the others are unchanged)
         return main_nd()
@@ -194,6 +242,8 @@ def main():
     main_recursive()
     main_wide()
     main_f2()
+    main_nd_bilateral()
+    main_wow_nd()
 
     # ---- plain transform: wavelets.py:408-444 via :307 ------------------------------------------------------
     cases = [((64, 64), 4), ((37, 53), 4), ((6, 7), 3), ((96, 64), 6), ((24, 256), 5)]

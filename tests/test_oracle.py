@@ -367,3 +367,50 @@ def test_oracle_wide_golden(dt):
                 assert orc.emax(recon[:, cols], g[f"{tag}_{key}_recon"]) < (1e-10 if kw else 1e-12), (tag, key)
                 if noise is not None:
                     assert abs(noise - float(g[f"{tag}_{key}_noise"])) <= 1e-13 * noise
+
+
+ND_BILATERAL_CASES = [("b3spline", dict(bilateral=1)), ("triangle", dict(bilateral=[2, 1.5], bilateral_scaling=True)),
+                      ("b3spline", dict(bilateral=1)), ("triangle", dict(bilateral=1.5))]
+
+
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+def test_oracle_nd_bilateral_golden(dt):
+    """Bilateral cascade of 1-D signals and 3-D volumes against the real reference (make_golden.py --nd-bilateral)."""
+    g = load_golden(f"transform_nd_bilateral_{dt}")
+    for k, (sf, kw) in enumerate(ND_BILATERAL_CASES):
+        arr, level = g[f"in{k}"], int(g[f"level{k}"])
+        out = orc.atrous_transform(arr, level, sf, backend="cv2" if arr.ndim == 3 else None, **kw)
+        for p in range(level + 1):
+            # fp32: the reference's variance S[x^2] - S[x]^2 cancels in float32 and the shim's exp is NumPy's
+            assert orc.emax(out[p], g[f"out{k}"][p]) < (5e-5 if dt == "float32" else 1e-12), (k, p)
+        if arr.ndim == 3:
+            assert abs(orc.get_noise(out, sf, kw["bilateral"]) / float(g[f"noise{k}"]) - 1) < (5e-6 if dt == "float32" else 1e-13)
+            dn = orc.denoise(arr.copy(), [3, 2][:level], sf, bilateral=kw["bilateral"], backend="cv2")
+            assert orc.emax(dn, g[f"dn{k}"]) < (5e-6 if dt == "float32" else 1e-13)
+    with pytest.raises(AttributeError):  # the reference has no sigma_e_1d_bilateral table
+        orc.sigma_e("b3spline", bilateral=1, ndim=1)
+
+
+WOW_ND_CASES = [{}, dict(denoise_coefficients=[4, 2], weights=[1.5, 1.0, 0.5]),
+                dict(scaling_function="triangle", h=0.3, preserve_variance=True, denoise_coefficients=[3], noise=1.2),
+                {}, dict(denoise_coefficients=[4, 2], soft_threshold=False),
+                dict(bilateral=1, denoise_coefficients=[3, 1], n_scales=2)]
+
+
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+def test_oracle_wow_nd_golden(dt):
+    """wow() on 1-D signals and 3-D volumes against the real reference (make_golden.py --wow-nd)."""
+    g = load_golden(f"wow_nd_{dt}")
+    for k, kw in enumerate(WOW_ND_CASES):
+        kw = dict(kw)
+        name = kw.pop("scaling_function", "b3spline")
+        recon, planes, noise = orc.wow(g[f"in{k}"].copy(), name=name, backend="cv2", **kw)
+        bil = "bilateral" in kw
+        assert planes.shape == g[f"planes{k}"].shape
+        if kw.get("soft_threshold", True):
+            # fp32 volumes: the oracle's n-D smooth rounds once, the reference's slice-wise cv2 passes round twice
+            assert orc.emax(recon, g[f"recon{k}"]) < ((2e-5 if bil else 1e-5) if dt == "float32" else 1e-12), k
+            for p in range(len(planes)):
+                assert orc.emax(planes[p], g[f"planes{k}"][p]) < ((2e-4 if bil else 5e-5) if dt == "float32" else 1e-12), (k, p)
+        else:
+            assert (np.abs(recon - g[f"recon{k}"]) > 1e-5 * np.abs(recon).max()).mean() < 1e-3

@@ -402,3 +402,39 @@ def test_wow_options_golden(dt):
     co = wb.AtrousTransform(wb.B3spline)(img, wb.utils._wow_plan(img.shape, wb.B3spline, None, [], [5, 2], None)[0])
     r2, co2 = wb.wow(co, h=0.4, denoise_coefficients=[5, 2], gamma=2.5)
     assert co2 is co and orc.emax(r2.cpu().numpy(), r1) < (1e-6 if dt == "float32" else 1e-13)
+
+
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+def test_wow_nd_golden(dt):
+    """wow() on 1-D signals and 3-D volumes (watroo/utils.py:121-219 is dimension-generic) against the real
+    reference's outputs and the float64 oracle: default, thresholds + weights, gamma blend + preserve_variance, hard
+    thresholds on a volume, bilateral volume."""
+    import wavelets_b200 as wb
+    from tests.test_oracle import WOW_ND_CASES
+    g = load_golden(f"wow_nd_{dt}")
+    for k, kw in enumerate(WOW_ND_CASES):
+        kw = dict(kw)
+        name = kw.pop("scaling_function", "b3spline")
+        arr = g[f"in{k}"]
+        keep = arr.copy()
+        recon, co = wb.wow(arr, scaling_function=_sf(name), **kw)
+        assert np.array_equal(arr, keep)
+        ref_r, ref_p = g[f"recon{k}"], g[f"planes{k}"]
+        assert isinstance(recon, np.ndarray) and recon.dtype == ref_r.dtype and recon.shape == ref_r.shape
+        got = co.data.cpu().numpy()
+        assert got.shape == ref_p.shape
+        ref_noise = float(g[f"noise{k}"])
+        if np.isnan(ref_noise):
+            assert co.noise is None
+        else:
+            assert abs(co.noise / ref_noise - 1) < (2e-5 if dt == "float32" else 1e-12)
+        r64, p64, _ = orc.wow(arr.astype(np.float64), name=name, backend="numpy", **kw)
+        if not kw.get("soft_threshold", True):
+            assert (np.abs(recon - r64) > 1e-4 * np.abs(r64).max()).mean() < (5e-3 if dt == "float32" else 1e-9)
+            continue
+        bil = "bilateral" in kw
+        tol_r = dual_tol(ref_r, r64, dt, fp64_tol=1e-10 if bil else 1e-12)
+        assert orc.emax(recon, r64) <= tol_r, (k, orc.emax(recon, r64), tol_r)
+        for p in range(len(ref_p)):
+            tp = dual_tol(ref_p[p], p64[p], dt, fp64_tol=1e-10 if bil else 1e-12, base=2e-5)
+            assert orc.emax(got[p], p64[p]) <= tp, (k, p, orc.emax(got[p], p64[p]), tp)

@@ -49,6 +49,8 @@ SIGNATURES = {
                                           _c_int, _c_int, _c_int, _c_vp]),
     "wb_atrous_scale_bilateral": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll,
                                            _c_ll, _c_ll, _c_int, _c_int, _c_int, _c_dbl, _c_vp]),
+    "wb_atrous_scale_bilateral_nd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_ll, _c_ll, _c_ll, _c_int, _c_int, _c_int,
+                                              _c_dbl, _c_vp]),
     "wb_wow_whiten_scale": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll, _c_int, _c_int,
                                      _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_vp, _c_dbl, _c_vp]),
     "wb_wow_scale_path": (_c_int, [_c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_int, _c_int, _c_int, _c_vp, _c_vp,

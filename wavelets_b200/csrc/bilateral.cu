@@ -34,6 +34,49 @@ template <typename T> __device__ __forceinline__ T nhalf_inverse(T v);
 template <> __device__ __forceinline__ float nhalf_inverse<float>(float v) { return -1.4426950408889634f / (2.0f * v); }
 template <> __device__ __forceinline__ double nhalf_inverse<double>(double v) { return -1.0 / (2.0 * v); }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fp64 range weights: 2^a with a <= 0 from a 256-entry table of 2^(i/256) and a degree-4 polynomial -- 8 double-precision
+// operations and one shared-memory load instead of the ~28 of exp() (the fp64 kernel is bound by the FP64 pipe: 24
+// exponentials per pixel were 70 % of its work).  a = n / 256 + r with n = round(256 a) read off the mantissa after
+// adding 1.5 * 2^44 (ulp 2^-8), |r| <= 2^-9: 2^a = 2^(n >> 8) * tab[n & 255] * exp(r ln 2); the truncated series is
+// good to (2^-9 ln 2)^5 / 120 = 4e-17 and the table is the host's exp2, so the weights are accurate to ~2 ulp.
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int kExp2TabBits = 8;
+static constexpr int kExp2TabSize = 1 << kExp2TabBits;
+__device__ double g_exp2_tab[kExp2TabSize];
+
+static int ensure_exp2_table() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done[dev]) return 0;
+    double host[kExp2TabSize];
+    for (int i = 0; i < kExp2TabSize; ++i) host[i] = exp2((double)i / kExp2TabSize);
+    cudaError_t e = cudaMemcpyToSymbol(g_exp2_tab, host, sizeof(host));
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return 0;
+}
+
+__device__ __forceinline__ double exp2_tab(double a, const double *tab) {
+    a = fmax(a, -1000.0);  // 2^-1000 == 0 for every purpose here; keeps the exponent arithmetic below in range
+    const double magic = 26388279066624.0;  // 1.5 * 2^44
+    const double t = a + magic;
+    const int n = __double2loint(t);  // round(256 a), two's complement (the low mantissa word of 1.5 * 2^44 is zero)
+    const double r = (a - (t - magic)) * 0.6931471805599453;  // (a - n / 256) ln 2
+    double p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+    p = fma(r, p, 0.5);
+    p = fma(r, p, 1.0);
+    p = fma(r, p, 1.0);
+    const double v = tab[n & (kExp2TabSize - 1)] * p;
+    return __hiloint2double(__double2hiint(v) + ((n >> kExp2TabBits) << 20), __double2loint(v));
+}
+template <int TAPS> struct TapLog2d;
+template <> struct TapLog2d<3> { __host__ __device__ static constexpr double l(int k) { return k == 1 ? -1.0 : -2.0; } };
+template <> struct TapLog2d<5> {
+    __host__ __device__ static constexpr double l(int k) { return k == 2 ? -1.4150374992788437 : ((k == 1 || k == 3) ? -2.0 : -4.0); }
+};
+
 // Values of the TAPS horizontal taps of one staged row for the V columns of a vector.
 template <typename T, int TAPS, int DMODE>
 __device__ __forceinline__ void row_taps(const T *srow, const TapPlan<PlanSize<TAPS, DMODE>::NV> &tp,
@@ -75,6 +118,7 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
     T *rows = reinterpret_cast<T *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)p.slots * p.row_stride * sizeof(T));
     uint64_t *empty = full + p.slots;
+    double *tab = reinterpret_cast<double *>(empty + p.slots);  // fp64: 2^(i/256), see exp2_tab
 
     const int nt = blockDim.x - 32;
     const int nwc = nt >> 5;
@@ -106,6 +150,9 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
             mbar_init(&empty[s], nwc);
         }
         fence_mbar_init();
+    }
+    if constexpr (sizeof(T) == 8) {
+        for (int i = tid; i < kExp2TabSize; i += blockDim.x) tab[i] = g_exp2_tab[i];
     }
     __syncthreads();
     pdl_wait();  // everything below touches global memory written or read by the previous launch
@@ -176,7 +223,8 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
                 for (int e = 0; e < V; ++e) {
                     T var = s2[e] - s1[e] * s1[e];
                     if (var <= T(0)) var = T(1e-20);
-                    const T nhi = nhalf_inverse<T>(var * var_factor);
+                    T nhi = nhalf_inverse<T>(var * var_factor);
+                    if constexpr (sizeof(T) == 8) nhi *= 1.4426950408889634;  // exponent in base 2 for exp2_tab
                     T num = T(0);
                     T den = Taps<T, TAPS>::h(C) * Taps<T, TAPS>::h(C);
 #pragma unroll
@@ -185,7 +233,11 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
                         for (int k = 0; k < TAPS; ++k) {
                             if (i == C && k == C) continue;
                             const T dd = dlt[i][k][e];
-                            const T gw = range_weight(Taps<T, TAPS>::h(i) * Taps<T, TAPS>::h(k), dd * dd, nhi);
+                            T gw;
+                            if constexpr (sizeof(T) == 8)
+                                gw = exp2_tab(fma(dd * dd, nhi, TapLog2d<TAPS>::l(i) + TapLog2d<TAPS>::l(k)), tab);
+                            else
+                                gw = range_weight(Taps<T, TAPS>::h(i) * Taps<T, TAPS>::h(k), dd * dd, nhi);
                             den += gw;
                             num = fma_t<T>(gw, dd, num);
                         }
@@ -521,11 +573,11 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
 // selects the old kernel; tests/test_wide_parity_gpu.py compares the two).
 // ---------------------------------------------------------------------------------------------------------------
 // 8 consumer warps + a ninth warp whose lane 0 streams the rows.  Two blocks per SM at the 96 registers ptxas budgets
-// for this block size (a few spilled values in the prologue; __maxnreg__(112) removes them but the register file then
-// holds ONE block per SM: 204 instead of 150 us).  Measured and not kept: 256-thread blocks whose thread 0 tops the ring
+// for this block size (a few spilled values; __maxnreg__(104) or (112) removes them but the register file then
+// holds ONE block per SM: 204 - 222 instead of 150 us).  Measured and not kept: 256-thread blocks whose thread 0 tops the ring
 // up with non-blocking probes (213 us: instruction-cache misses and a lagging warp 0).
 template <int TAPS, int DMODE>
-__global__ void __maxnreg__(104) bilateral_window_kernel(const BilateralParams bp) {
+__global__ void __launch_bounds__(288, 2) bilateral_window_kernel(const BilateralParams bp) {
     const ScaleParams &p = bp.sp;
     pdl_launch_dependents();
     constexpr int C = TAPS / 2;
@@ -974,7 +1026,11 @@ template <typename T, int TAPS, int DMODE>
 static int launch_bilateral(const BilateralParams &bp, int batch, int nt, cudaStream_t st) {
     auto kern = bilateral_rows_kernel<T, TAPS, DMODE>;
     const ScaleParams &p = bp.sp;
-    const size_t smem = (size_t)p.slots * p.row_stride * sizeof(T) + 16 * (size_t)p.slots;
+    if (sizeof(T) == 8) {
+        const int rc = ensure_exp2_table();
+        if (rc) return rc;
+    }
+    const size_t smem = (size_t)p.slots * p.row_stride * sizeof(T) + 16 * (size_t)p.slots + kExp2TabSize * sizeof(double);
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1000,8 +1056,9 @@ static bool plan_bilateral(ScaleParams &p, int taps, int esize, int batch) {
     p.row_stride = (int)rs;
     int slots = taps + 3;
     const int min_slots = taps + 1;
-    while (slots > min_slots && (long long)slots * p.row_stride * esize + 16LL * slots > kMaxSmem) --slots;
-    if ((long long)slots * p.row_stride * esize + 16LL * slots > kMaxSmem) return false;
+    const long long extra = kExp2TabSize * (long long)sizeof(double);
+    while (slots > min_slots && (long long)slots * p.row_stride * esize + 16LL * slots + extra > kMaxSmem) --slots;
+    if ((long long)slots * p.row_stride * esize + 16LL * slots + extra > kMaxSmem) return false;
     p.slots = slots;
     const int n_max = (p.H + p.d - 1) / p.d;
     // compute-bound kernel: many short segments balance better than few long ones; halo rows only cost L2 reads

@@ -221,6 +221,80 @@ __global__ void __launch_bounds__(256) axis_filter_kernel(const T *in, const T *
 }
 
 
+// One scale of the BILATERAL cascade of a 1-D signal or a 3-D volume (watroo/wavelets.py:433-442 with the n-D branches
+// of convolution, :46-69, and the dimension-generic atrous_convolution, :74-105).  One thread per sample:
+//   var = S[x^2] - S[x]^2 with the border of `convolution` for that dimensionality (1-D: whole-sample 'mirror', 3-D:
+//         half-sample symmetric on every axis), in the centred form sum k_t D_t^2 - (sum k_t D_t)^2;
+//   c'  = x - sum_t g_t D_t / (k_c + sum_t g_t),  g_t = k_t exp(-D_t^2 / (2 V)),  V = max(var, 1e-20) * var_factor,
+//         over the K^n - 1 off-centre taps read through np.pad(..., 'symmetric') -- ALWAYS symmetric, also in 1-D.
+// A parity path (124 exponentials per voxel for B3spline volumes), not a fast path.
+__device__ __forceinline__ long long reflect_border(long long i, long long n, bool mirror) {
+    const long long period = mirror ? 2 * (n - 1) : 2 * n;
+    if (period <= 0) return 0;
+    long long m = i % period;
+    if (m < 0) m += period;
+    if (m >= n) m = mirror ? period - m : period - 1 - m;
+    return m;
+}
+
+template <typename T, int TAPS>
+__global__ void __launch_bounds__(256) bilateral_nd_kernel(const T *in, T *out_c, T *out_w, long long n0, long long n1,
+                                                           long long n2, int ndim, long long d, T var_factor) {
+    constexpr int C = TAPS / 2;
+    const long long total = n0 * n1 * n2;
+    const int t0 = ndim == 3 ? TAPS : 1, t1 = ndim == 3 ? TAPS : 1;  // a 1-D signal is (1, 1, n)
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long x = idx % n2, y = (idx / n2) % n1, z = idx / (n1 * n2);
+        const T xc = in[idx];
+        // local variance, with the border rule of convolution() for this dimensionality
+        T s1 = T(0), s2 = T(0);
+        for (int a = 0; a < t0; ++a) {
+            const long long zz = ndim == 3 ? reflect_border(z + (long long)(a - C) * d, n0, false) : 0;
+            for (int b = 0; b < t1; ++b) {
+                const long long yy = ndim == 3 ? reflect_border(y + (long long)(b - C) * d, n1, false) : 0;
+                const T kab = (ndim == 3 ? Taps<T, TAPS>::h(a) * Taps<T, TAPS>::h(b) : T(1));
+                const T *row = in + (zz * n1 + yy) * n2;
+#pragma unroll
+                for (int c = 0; c < TAPS; ++c) {
+                    const long long xx = reflect_border(x + (long long)(c - C) * d, n2, ndim == 1);
+                    const T dd = xc - row[xx];
+                    const T kd = kab * Taps<T, TAPS>::h(c) * dd;
+                    s1 += kd;
+                    s2 = fma_t<T>(kd, dd, s2);
+                }
+            }
+        }
+        T var = s2 - s1 * s1;
+        if (var <= T(0)) var = T(1e-20);
+        const T nhi = T(-1) / (T(2) * var * var_factor);
+        // range-weighted gather through the symmetric border
+        T num = T(0), den = T(0);
+        for (int a = 0; a < t0; ++a) {
+            const long long zz = ndim == 3 ? reflect_border(z + (long long)(a - C) * d, n0, false) : 0;
+            for (int b = 0; b < t1; ++b) {
+                const long long yy = ndim == 3 ? reflect_border(y + (long long)(b - C) * d, n1, false) : 0;
+                const T kab = (ndim == 3 ? Taps<T, TAPS>::h(a) * Taps<T, TAPS>::h(b) : T(1));
+                const T *row = in + (zz * n1 + yy) * n2;
+#pragma unroll
+                for (int c = 0; c < TAPS; ++c) {
+                    const T k = kab * Taps<T, TAPS>::h(c);
+                    const bool centre = (ndim == 1 || (a == C && b == C)) && c == C;
+                    const long long xx = reflect_border(x + (long long)(c - C) * d, n2, false);
+                    const T dd = xc - row[xx];
+                    const T gw = centre ? k : k * exp(dd * dd * nhi);
+                    den += gw;
+                    num = fma_t<T>(gw, dd, num);
+                }
+            }
+        }
+        const T cn = xc - num / den;
+        if (out_c) out_c[idx] = cn;
+        if (out_w) out_w[idx] = xc - cn;
+    }
+}
+
+
 // Dense 2-D correlation with a small arbitrary kernel (the PSF of richardson_lucy, watroo/utils.py:252-255,283-286:
 // cv2.filter2D(img, -1, psf, out, (-1,-1), 0, cv2.BORDER_REFLECT)): anchor at the kernel centre (kh/2, kw/2), half-sample
 // symmetric border.  One thread per pixel; coefficients are warp-uniform loads, pixels coalesced and L1-resident.
@@ -350,6 +424,29 @@ int wb_atrous_axis(const void *in, const void *sub_from, void *out_c, void *out_
         if (taps == WB_TRIANGLE) WB_AXIS(double, 3); else WB_AXIS(double, 5);
     }
 #undef WB_AXIS
+    return wb::launch_status();
+}
+
+int wb_atrous_scale_bilateral_nd(const void *in, void *out_c, void *out_w, int ndim, long long n0, long long n1,
+                                 long long n2, int scale, int taps, int dtype, double var_factor, void *stream) {
+    if (dtype != WB_F32 && dtype != WB_F64) return WB_EINVAL_DTYPE;
+    if (taps != WB_TRIANGLE && taps != WB_B3SPLINE) return WB_EINVAL_TAPS;
+    if ((ndim != 1 && ndim != 3) || n0 < 1 || n1 < 1 || n2 < 1 || (ndim == 1 && (n0 != 1 || n1 != 1))) return WB_EINVAL_SHAPE;
+    if (scale < 0 || scale > 30) return WB_EINVAL_SCALE;
+    if (!in || (!out_c && !out_w) || in == out_c || in == out_w) return WB_EINVAL_POINTER;
+    if (!(var_factor > 0)) return WB_EINVAL_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = wb::grid_for(n0 * n1 * n2);
+    const long long d = 1LL << scale;
+#define WB_BNd(T, TAPS)                                                                                          \
+    wb::bilateral_nd_kernel<T, TAPS><<<grid, 256, 0, st>>>(reinterpret_cast<const T *>(in), reinterpret_cast<T *>(out_c), \
+                                                          reinterpret_cast<T *>(out_w), n0, n1, n2, ndim, d, (T)var_factor)
+    if (dtype == WB_F32) {
+        if (taps == WB_TRIANGLE) WB_BNd(float, 3); else WB_BNd(float, 5);
+    } else {
+        if (taps == WB_TRIANGLE) WB_BNd(double, 3); else WB_BNd(double, 5);
+    }
+#undef WB_BNd
     return wb::launch_status();
 }
 

@@ -57,7 +57,11 @@ class AbstractScalingFunction:
         dimensionality; the bilateral table whenever ``bilateral is not None`` (None where the reference has none)."""
         plain = {1: self.sigma_e_1d, 2: self.sigma_e_2d, 3: self.sigma_e_3d}
         bil = {1: self.sigma_e_1d_bilateral, 2: self.sigma_e_2d_bilateral, 3: self.sigma_e_3d_bilateral}
-        return (plain if bilateral is None else bil)[self.n_dim]
+        table = (plain if bilateral is None else bil)[self.n_dim]
+        if table is None:  # the reference has no such attribute (e.g. sigma_e_1d_bilateral): same exception type
+            raise AttributeError(f"'{type(self).__name__}' object has no attribute "
+                                 f"'sigma_e_{self.n_dim}d{'_bilateral' if bilateral is not None else ''}'")
+        return table
 
     def compute_noise_weights(self, n_scales, n_trials=100, bilateral=None, fields=None, seed=None):
         """Monte-Carlo estimate of ``sigma_e`` (watroo/wavelets.py:221-229), entirely on the GPU.

@@ -7,6 +7,7 @@ results; torch tensor in -> torch CUDA tensor out.  ``coefficients.data`` always
 from __future__ import annotations
 
 import copy
+import os
 import warnings
 
 import numpy as np
@@ -21,6 +22,19 @@ __all__ = ["denoise", "wow", "wow_batch", "wow_stream", "generalized_anscombe", 
 
 # Development switch (tests compare the fused one-pass WOW scales against the two-pass route bit for bit).
 FUSED_WOW = True
+# Bilateral WOW: run the memory-bound half of every scale (exact median, whitening K3) on a high-priority side stream
+# while the compute-bound bilateral kernel K2 of the next scale runs on the caller's stream (A/B switch).
+OVERLAP_BILATERAL = os.environ.get("WB_OVERLAP_BILATERAL", "1") != "0"
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device):
+    """One high-priority stream per device for the whitening passes that overlap with K2 (created once)."""
+    key = (device.type, device.index)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device, priority=-1)
+    return st
 
 
 def generalized_anscombe(signal, alpha=1, g=0, sigma=0, inverse=False):
@@ -30,6 +44,14 @@ def generalized_anscombe(signal, alpha=1, g=0, sigma=0, inverse=False):
         return ((alpha * signal / 2) ** 2 + alpha * g - sigma ** 2 - 3 * alpha / 8) / alpha
     dum = alpha * signal + 3 * alpha ** 2 / 8 + sigma ** 2 - alpha * g
     return 2 * torch.sqrt(torch.clamp(dum, min=0)) / alpha
+
+
+class _NullContext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
 
 
 def _result(t, as_numpy):
@@ -55,7 +77,7 @@ def denoise(data, weights, scaling_function=B3spline, noise=None, bilateral=None
 
 
 def _wow_plan(shape, scaling_function, n_scales, weights, denoise_coefficients, bilateral, from_coefficients=None,
-              h=0):
+              h=0, n_dims=2):
     """Scale-count and per-scale parameter lists of wow() (watroo/utils.py:121-146, :160-170)."""
     n_taps = len(scaling_function.coefficients_1d)
     if from_coefficients is None:
@@ -66,7 +88,7 @@ def _wow_plan(shape, scaling_function, n_scales, weights, denoise_coefficients, 
             n_scales = max_scales
     else:
         n_scales = len(from_coefficients) - 1
-    table_len = len(scaling_function(2).sigma_e(bilateral=bilateral))
+    table_len = len(scaling_function(n_dims).sigma_e(bilateral=bilateral))
     if len(denoise_coefficients) >= table_len:
         warnings.warn(f"Required number of scales lager then the maximum for scaling function. Using {table_len}.")
         n_scales = table_len
@@ -146,9 +168,16 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
     if L == 0:
         planes[:, 0].copy_(stack)
     scratch = torch.empty((2, b, h, w), dtype=dt, device=dev) if L > 1 else None
-    raw_plane = None  # one-plane scratch for the raw w_s of the two-pass route, allocated on first use
+    raw_planes = None  # scratch for the raw w_s of the two-pass route, allocated on first use
     nz = noise  # _Noise or None
     src = stack
+    # Bilateral cascade with whitening: K2 is bound by the MUFU/FMA pipes and leaves HBM idle, the exact median and the
+    # whitening pass K3 are bound by HBM.  They go to a high-priority side stream: K3 of scale s then runs under K2 of
+    # scale s+1 (its blocks are scheduled as K2 blocks retire).  Two raw planes alternate; events order the hand-over.
+    overlap = OVERLAP_BILATERAL and whitening and bilateral is not None and L > 1 and dev.type == "cuda"
+    main = torch.cuda.current_stream(dev) if overlap else None
+    side = _side_stream(dev) if overlap else None
+    ev_k3 = [None, None]  # whitening of the scale that last used raw_planes[i]
     for s in range(L):
         dst_c = planes[:, L] if s == L - 1 else scratch[s & 1]
         d, wt = dns[s], wts[s]
@@ -157,6 +186,8 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
         if whitening:
             if need_sig and nz is None and s > 0:
                 # lazily, from the current state of plane 0 (already whitened here) -- watroo/wavelets.py:131-132
+                if overlap:
+                    main.wait_stream(side)
                 nz = _Noise(dev=abs_median_noise(planes[:, 0], sigma_e[0]))
             # One pass (K1+K3 fused, raw w_s stays on chip) unless the scale is bilateral, the MAD noise has to be
             # estimated from the raw w_0 first (grid-wide dependency), or the shape is outside the fused kernel.
@@ -164,13 +195,22 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
                 _wow_scale_fused(lib, src, dst_c, planes[:, s], s, sf, mode, d, sigma_e[s] if need_sig else 1.0,
                                  nz if need_sig else _Noise(), wt)
             if not fused:
-                if raw_plane is None:
-                    raw_plane = torch.empty((b, h, w), dtype=dt, device=dev)
+                if raw_planes is None:
+                    raw_planes = torch.empty((2 if overlap else 1, b, h, w), dtype=dt, device=dev)
+                raw_plane = raw_planes[s & 1] if overlap else raw_planes[0]
+                if overlap and ev_k3[s & 1] is not None:
+                    main.wait_event(ev_k3[s & 1])  # the whitening that read this raw plane two scales ago is done
                 atrous_scale(src, s, sf, out_c=dst_c, out_w=raw_plane, var_factor=factors[s])
-                if need_sig and nz is None:
-                    nz = _Noise(dev=abs_median_noise(raw_plane, sigma_e[0]))  # s == 0: from the raw w_0
-                _whiten_scale(lib, raw_plane, planes[:, s], s, sf, mode, d, sigma_e[s] if need_sig else 1.0,
-                              nz if need_sig else _Noise(), wt)
+                if overlap:
+                    side.wait_stream(main)
+                with torch.cuda.stream(side) if overlap else _NullContext():
+                    if need_sig and nz is None:
+                        nz = _Noise(dev=abs_median_noise(raw_plane, sigma_e[0]))  # s == 0: from the raw w_0
+                    _whiten_scale(lib, raw_plane, planes[:, s], s, sf, mode, d, sigma_e[s] if need_sig else 1.0,
+                                  nz if need_sig else _Noise(), wt)
+                    if overlap:
+                        ev_k3[s & 1] = torch.cuda.Event()
+                        ev_k3[s & 1].record(side)
         else:
             atrous_scale(src, s, sf, out_c=dst_c, out_w=planes[:, s], var_factor=factors[s])
             if need_sig and nz is None:
@@ -183,6 +223,8 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
                                                     float(sigma_e[s]) if need_sig else 1.0, use.host, use.dev_ptr, 0,
                                                     float(wt), _lib.stream_ptr(dev)))
         src = dst_c
+    if overlap:
+        main.wait_stream(side)  # every whitened plane is complete before the tail (and before any buffer is freed)
     # residual plane: c_L *= wt_L / std(c_L)  (watroo/utils.py:185-189, :203)
     last = planes[:, L]
     if whitening:
@@ -214,7 +256,16 @@ def wow(data, scaling_function=B3spline, n_scales=None, weights=[], whitening=Tr
         return _wow_coefficients(data, weights, whitening, denoise_coefficients, bilateral, soft_threshold)
     if not isinstance(data, (np.ndarray, torch.Tensor)):
         raise ValueError("Unknown input type")  # watroo/utils.py:133
-    img, was_numpy = to_device_image(data)
+    img, was_numpy = to_device_image(data, ndim_ok=(1, 2, 3))
+    if img.ndim != 2:
+        # 1-D signals and 3-D volumes: the reference's loop is dimension-generic (watroo/utils.py:148-150, :194)
+        n_scales, sigma_bilateral, wts, dns = _wow_plan(img.shape, scaling_function, n_scales, weights,
+                                                        denoise_coefficients, bilateral, h=h, n_dims=img.ndim)
+        transform = AtrousTransform(scaling_function, bilateral=sigma_bilateral, bilateral_scaling=bilateral_scaling)
+        co = transform(img, n_scales)
+        co.noise = noise
+        recon = _wow_nd(co, wts, dns, whitening, soft_threshold, preserve_variance, gamma, gamma_min, gamma_max, h)
+        return _result(recon, was_numpy), co
     n_scales, sigma_bilateral, wts, dns = _wow_plan(img.shape, scaling_function, n_scales, weights,
                                                     denoise_coefficients, bilateral, h=h)
     if general:
@@ -241,6 +292,55 @@ def wow(data, scaling_function=B3spline, n_scales=None, weights=[], whitening=Tr
     else:
         co.noise = None
     return _result(recon[0], was_numpy), co
+
+
+def _wow_nd(co, wts, dns, whitening, soft_threshold, preserve_variance, gamma, gamma_min, gamma_max, h):
+    """The loop of wow() (watroo/utils.py:172-217) on the coefficients of a 1-D signal or a 3-D volume, every option
+    included: the transform and the n-D smooth of the local power run in the library's kernels, the plane-wise factors
+    are element-wise device arithmetic in the reference's order and dtypes.  A parity path, whitened in place."""
+    from .wavelets import _smooth_nd
+    data = co.data
+    dt = data.dtype
+    L = len(co) - 1
+    white = whitening and h < 1
+    gamma_scaled = torch.zeros_like(data[0]) if h > 0 else None
+    for s in range(L + 1):
+        c = data[s]
+        power = c * c
+        power_norm = None
+        if preserve_variance:  # utils.py:178-184
+            power_norm = c.to(torch.float64).std(unbiased=False).to(dt) if s == L else torch.sqrt(power.mean())
+        if s == L:
+            local_power = None
+            if white:
+                sd = plane_moments(c.reshape(1, -1))[0, 2].to(dt)
+                local_power = torch.where(sd <= 0, torch.full_like(sd, 1e-15), sd)
+        else:
+            local_power = None
+            if white:
+                local_power = _smooth_nd(power.contiguous(), s, co.scaling_function)  # plain smooth, utils.py:194
+                local_power = torch.sqrt(torch.where(local_power <= 0, torch.full_like(local_power, 1e-15), local_power))
+            sig = co.significance(dns[s], s, soft_threshold=soft_threshold)
+            if sig.dtype == torch.bool or sig.dtype == torch.float64:
+                c.copy_((c.to(torch.float64) * sig.to(torch.float64)).to(dt))  # product in float64, rounded once
+        if gamma_scaled is not None:
+            gamma_scaled += c
+        factor = torch.as_tensor(wts[s], dtype=dt, device=c.device)
+        if power_norm is not None:
+            factor = factor * power_norm
+        if local_power is not None:
+            factor = factor / local_power
+        c.mul_(factor)
+    recon = synthesis(data.reshape(L + 1, 1, -1)).reshape(data.shape[1:])
+    if gamma_scaled is not None:  # utils.py:207-217
+        lo = gamma_scaled.min() if gamma_min is None else gamma_min
+        hi = gamma_scaled.max() if gamma_max is None else gamma_max
+        gamma_scaled -= lo
+        gamma_scaled /= (hi - lo)
+        gamma_scaled.clamp_(0, 1)
+        gamma_scaled.pow_(1 / gamma)
+        recon = (1 - h) * recon + h * gamma_scaled
+    return recon
 
 
 def wow_batch(frames, scaling_function=B3spline, n_scales=None, weights=[], whitening=True, denoise_coefficients=[],

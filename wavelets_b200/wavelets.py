@@ -380,7 +380,7 @@ class AtrousTransform:
 
         2-D images take the row-pipeline kernels.  1-D signals (whole-sample 'mirror' border, watroo/wavelets.py:64-69)
         and 3-D volumes (2-D smooth of every slice, then the depth pass, watroo/wavelets.py:46-63) run the plain
-        cascade through ``wb_atrous_axis``; their bilateral variants are not built.
+        cascade through ``wb_atrous_axis`` and the bilateral one through ``wb_atrous_scale_bilateral_nd``.
 
         ``recursive=True`` on a plain 2-D transform reproduces the RESULT of the reference's recursive algorithm
         (watroo/wavelets.py:330-406; it differs from the standard one near the borders: symmetric pad by
@@ -394,8 +394,6 @@ class AtrousTransform:
         elif img.ndim == 2:
             planes = self._run(img, int(level), scaling_function)
         else:
-            if self.bilateral is not None:
-                raise NotImplementedError("wavelets_b200: the bilateral cascade is built for 2-D images only")
             planes = self._run_nd(img, int(level), scaling_function)
         return Coefficients(planes, scaling_function, self.bilateral)
 
@@ -437,10 +435,17 @@ class AtrousTransform:
         sf2 = self.scaling_function_class(2)
         tmp = torch.empty_like(arr) if arr.ndim == 3 else None
         src = arr
+        factors = self.var_factors(level) if self.bilateral is not None else None
         with torch.cuda.device(arr.device):
             for s in range(level):
                 dst_c = planes[level] if s == level - 1 else scratch[s & 1]
-                if arr.ndim == 1:
+                if factors is not None:
+                    # bilateral cascade of a signal / volume (watroo/wavelets.py:433-442 on n-D input): parity kernel
+                    shape3 = (1, 1, arr.shape[0]) if arr.ndim == 1 else tuple(arr.shape)
+                    _lib.check(lib.wb_atrous_scale_bilateral_nd(src.data_ptr(), dst_c.data_ptr(), planes[s].data_ptr(),
+                                                                arr.ndim, *shape3, s, taps, code, factors[s],
+                                                                _lib.stream_ptr(arr.device)))
+                elif arr.ndim == 1:
                     _lib.check(lib.wb_atrous_axis(src.data_ptr(), src.data_ptr(), dst_c.data_ptr(), planes[s].data_ptr(),
                                                   1, arr.shape[0], 1, s, taps, code, _lib.WB_BORDER_MIRROR,
                                                   _lib.stream_ptr(arr.device)))
@@ -583,8 +588,6 @@ def randn_field(shape, seed, offset=0, device=None):
 def noise_weights(scaling_function, n_scales, n_trials=100, bilateral=None, fields=None, seed=None):
     """compute_noise_weights (watroo/wavelets.py:221-229) on the device; see AbstractScalingFunction."""
     nd = scaling_function.n_dim
-    if nd != 2 and bilateral is not None:
-        raise NotImplementedError("wavelets_b200: the bilateral cascade is built for 2-D images only")
     transform = AtrousTransform(scaling_function.__class__, bilateral=bilateral)
     side = len(scaling_function.sigma_e_1d) * 2 ** n_scales
     if seed is None:
