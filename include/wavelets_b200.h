@@ -111,6 +111,15 @@ int wb_atrous_scale_lattice(const void *in, void *out_c, void *out_w, int H, int
                             long long out_c_pitch, long long out_w_pitch, int scale, int taps, int dtype, void *stream);
 
 /*
+ * The bilateral counterpart of wb_atrous_scale_lattice: one scale of the reference's RECURSIVE algorithm with
+ * AtrousTransform(bilateral=...) (watroo/wavelets.py:371-378: sdev_loc and atrous_convolution on every decimated
+ * sub-array, each with the symmetric border at ITS OWN edges).  Generic gather kernel (a parity mode).
+ */
+int wb_atrous_scale_bilateral_lattice(const void *in, void *out_c, void *out_w, int H, int W, long long in_pitch,
+                                      long long out_c_pitch, long long out_w_pitch, int scale, int taps, int dtype,
+                                      double var_factor, void *stream);
+
+/*
  * wb_wow_whiten_scale on ONE ROW BAND of a taller image (row-band sharded WOW, no reference equivalent): same window
  * conventions as wb_atrous_scale_band -- `w_raw` holds the band's raw detail rows plus the halo rows of the
  * neighbours (c * 2^scale above and below, filled by the caller), reflections about global_H.  `noise_dev`, when

@@ -190,11 +190,13 @@ def smooth_nd(arr: np.ndarray, name: str, s: int = 0) -> np.ndarray:
     return out.astype(arr.dtype)
 
 
-def atrous_transform_recursive(arr: np.ndarray, level: int, name: str = "b3spline") -> np.ndarray:
-    """AtrousTransform(sf)(arr, level, recursive=True).data for a plain 2-D transform (wavelets.py:330-406), restated
-    without the recursion: symmetric pad by (K // 2) * 2**(level - 1); at scale s every pixel's taps reflect
-    (half-sample symmetric) inside its own decimated sub-array {o, o + 2^s, o + 2*2^s, ...}, which is what filtering
-    each `conv[oy::2^s, ox::2^s]` sub-array with BORDER_REFLECT does; crop the pad at the end."""
+def atrous_transform_recursive(arr: np.ndarray, level: int, name: str = "b3spline", bilateral=None,
+                               bilateral_scaling: bool = False) -> np.ndarray:
+    """AtrousTransform(sf, bilateral, bilateral_scaling)(arr, level, recursive=True).data for a 2-D transform
+    (wavelets.py:330-406), restated without the recursion: symmetric pad by (K // 2) * 2**(level - 1); at scale s every
+    pixel's taps reflect (half-sample symmetric) inside its own decimated sub-array {o, o + 2^s, o + 2*2^s, ...}, which
+    is what filtering each `conv[oy::2^s, ox::2^s]` sub-array with BORDER_REFLECT (plain) or through sdev_loc +
+    atrous_convolution(mode='symmetric') (bilateral, :371-378) does; crop the pad at the end."""
     if arr.dtype in _RECAST:
         arr = np.float64(arr)
     taps = TAPS[name]
@@ -202,6 +204,7 @@ def atrous_transform_recursive(arr: np.ndarray, level: int, name: str = "b3splin
     hw = c * 2 ** (level - 1)
     cur = np.pad(arr, hw, mode="symmetric").astype(np.float64)
     planes = np.empty((level + 1,) + cur.shape, dtype=arr.dtype)
+    sb = _bilateral_list(bilateral, level)
 
     def lattice(n, off, d):
         i = np.arange(n)
@@ -210,17 +213,42 @@ def atrous_transform_recursive(arr: np.ndarray, level: int, name: str = "b3splin
         m = np.mod(t + off, 2 * n_sub)
         return o + np.where(m < n_sub, m, 2 * n_sub - 1 - m) * d
 
+    def smooth_lattice(a64, d):
+        rows = np.zeros_like(a64)
+        for j, t in enumerate(taps):
+            rows += t * a64[:, lattice(a64.shape[1], j - c, d)]
+        out = np.zeros_like(a64)
+        for i, t in enumerate(taps):
+            out += t * rows[lattice(a64.shape[0], i - c, d), :]
+        return out
+
     cur = cur.astype(arr.dtype)
     for s in range(level):
         d = 2 ** s
-        a64 = cur.astype(np.float64)
-        rows = np.zeros_like(a64)
-        for j, t in enumerate(taps):
-            rows += t * a64[:, lattice(cur.shape[1], j - c, d)]
-        nxt = np.zeros_like(a64)
-        for i, t in enumerate(taps):
-            nxt += t * rows[lattice(cur.shape[0], i - c, d), :]
-        nxt = nxt.astype(arr.dtype)
+        if bilateral is None:
+            nxt = smooth_lattice(cur.astype(np.float64), d).astype(arr.dtype)
+        else:
+            # sdev_loc in the image dtype (squares, subtraction), then the range-weighted gather on the same lattice
+            mean2 = smooth_lattice(cur.astype(np.float64), d).astype(arr.dtype) ** 2
+            vari = smooth_lattice((cur ** 2).astype(np.float64), d).astype(arr.dtype)
+            vari -= mean2
+            vari[vari <= 0] = 1e-20
+            vari = vari * sb[s] ** 2
+            if bilateral_scaling:
+                vari *= s + 1
+            k2d = np.outer(taps, taps).astype(arr.dtype)
+            out = k2d[c, c] * cur
+            norm = np.full_like(cur, k2d[c, c])
+            for i in range(len(taps)):
+                yy = lattice(cur.shape[0], i - c, d)
+                for j in range(len(taps)):
+                    if i == c and j == c:
+                        continue
+                    shifted = cur[yy][:, lattice(cur.shape[1], j - c, d)]
+                    weight = k2d[i, j] * np.exp(-((cur - shifted) ** 2) / vari / 2)
+                    norm += weight
+                    out += shifted * weight
+            nxt = (out / norm).astype(arr.dtype)
         planes[s] = cur - nxt
         cur = nxt
     planes[level] = cur

@@ -67,6 +67,17 @@ def main_recursive():
             out[f"out{k}"] = AtrousTransform(SF[sf])(img.copy(), level, recursive=True).data
             out[f"level{k}"] = np.int64(level)
         save(f"transform_recursive_{sf}", n=np.int64(len(cases)), **out)
+    # recursive algorithm of the BILATERAL cascade (wavelets.py:371-378)
+    out = {}
+    cases = [((64, 64), 3, "float64", "b3spline", dict(bilateral=1)),
+             ((40, 56), 3, "float32", "triangle", dict(bilateral=[2, 1.5], bilateral_scaling=True)),
+             ((37, 53), 2, "float64", "b3spline", dict(bilateral=1.5))]
+    for k, (shape, level, dt, sf, kw) in enumerate(cases):
+        img = gaussian(shape, 50 + k, dt) * 3 + 10
+        out[f"in{k}"] = img
+        out[f"out{k}"] = AtrousTransform(SF[sf], **kw)(img.copy(), level, recursive=True).data
+        out[f"level{k}"] = np.int64(level)
+    save("transform_recursive_bilateral", n=np.int64(len(cases)), **out)
 
 
 def gaussian_psf(n, sigma):

@@ -414,3 +414,17 @@ def test_oracle_wow_nd_golden(dt):
                 assert orc.emax(planes[p], g[f"planes{k}"][p]) < ((2e-4 if bil else 5e-5) if dt == "float32" else 1e-12), (k, p)
         else:
             assert (np.abs(recon - g[f"recon{k}"]) > 1e-5 * np.abs(recon).max()).mean() < 1e-3
+
+
+RECURSIVE_BILATERAL_CASES = [("b3spline", dict(bilateral=1)), ("triangle", dict(bilateral=[2, 1.5], bilateral_scaling=True)),
+                             ("b3spline", dict(bilateral=1.5))]
+
+
+def test_oracle_recursive_bilateral_golden():
+    """recursive=True with a bilateral cascade (wavelets.py:371-378) against the real reference."""
+    g = load_golden("transform_recursive_bilateral")
+    for k, (sf, kw) in enumerate(RECURSIVE_BILATERAL_CASES):
+        ref = g[f"out{k}"]
+        out = orc.atrous_transform_recursive(g[f"in{k}"], int(g[f"level{k}"]), sf, **kw)
+        for p in range(len(ref)):
+            assert orc.emax(out[p], ref[p]) < (5e-5 if ref.dtype == np.float32 else 1e-12), (k, p)

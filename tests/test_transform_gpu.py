@@ -277,3 +277,22 @@ def test_nd_bilateral_golden(dt):
         else:
             with pytest.raises(AttributeError):
                 co.get_noise()
+
+
+def test_recursive_bilateral_golden():
+    """recursive=True on a bilateral 2-D transform (wb_atrous_scale_bilateral_lattice) reproduces the planes of the
+    reference's recursive algorithm (watroo/wavelets.py:371-378), which differ from the standard ones near the borders."""
+    import wavelets_b200 as wb
+    from tests.test_oracle import RECURSIVE_BILATERAL_CASES
+    g = load_golden("transform_recursive_bilateral")
+    for k, (sf, kw) in enumerate(RECURSIVE_BILATERAL_CASES):
+        img, level, ref = g[f"in{k}"], int(g[f"level{k}"]), g[f"out{k}"]
+        out = wb.AtrousTransform(_sf(sf), **kw)(img, level, recursive=True).data.cpu().numpy()
+        assert out.shape == ref.shape and out.dtype == ref.dtype
+        ref64 = orc.atrous_transform_recursive(img.astype(np.float64), level, sf, **kw)
+        for p in range(level + 1):
+            floor = orc.emax(ref[p], ref64[p])
+            e = orc.emax(out[p], ref64[p])
+            assert e <= (max(1e-5, 2 * floor) if ref.dtype == np.float32 else 1e-12), (k, p, e, floor)
+        std = wb.AtrousTransform(_sf(sf), **kw)(img, level).data.cpu().numpy()
+        assert max(orc.emax(std[p], ref[p]) for p in range(level + 1)) > 1e-3

@@ -455,18 +455,7 @@ template <typename T, int TAPS, int OP>
 static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
     constexpr int V = VecOf<T>::V;
     K1Config cfg;
-    // WB_K3_NT=<threads> caps the consumer threads of the whitening pass (A/B: a 256-thread block fits on an SM next to a
-    // block of the bilateral kernel, so that K3 of scale s can run under K2 of scale s + 1)
-    int nt_max = 512;
-    if (OP == OP_WHITEN) {
-        static int v = -1;
-        if (v < 0) {
-            const char *e = getenv("WB_K3_NT");
-            v = e ? atoi(e) : 0;
-        }
-        if (v >= 32) nt_max = v;
-    }
-    if (fast_path_ok(p, TAPS, (int)sizeof(T)) && plan_fast(p, TAPS, (int)sizeof(T), batch, scale, &cfg, nt_max)) {
+    if (fast_path_ok(p, TAPS, (int)sizeof(T)) && plan_fast(p, TAPS, (int)sizeof(T), batch, scale, &cfg)) {
         const int dmode = (p.d % V == 0) ? 0 : p.d;
         if constexpr (sizeof(T) == 4 && OP == OP_TRANSFORM) {
             // whole-row strips with two vectors per thread and the default ring: the lean kernel

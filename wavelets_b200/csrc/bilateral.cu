@@ -107,8 +107,14 @@ __device__ __forceinline__ void row_taps(const T *srow, const TapPlan<PlanSize<T
     }
 }
 
+// Row pipeline for float64 (and the fp32 shapes the pair kernels decline): one 16-byte vector of columns per thread.
+// Round 2: nothing is held in registers across output rows except the accumulators (the 25 x V differences of round 1
+// cost 166 registers, ONE block per SM, and left the FP64 pipe half idle): the taps are re-read from the staged rows
+// where they are used, the variance comes from per-row statistics kept in a per-thread shared-memory ring (the same
+// law-of-total-variance form as the fp32 kernels, see row_stats), and the fp64 weights come from exp2_tab -- two blocks
+// per SM.  Per pixel ~330 double-precision operations instead of ~800.
 template <typename T, int TAPS, int DMODE>
-__global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralParams bp) {
+__global__ void __launch_bounds__(288, 2) bilateral_rows_kernel(const BilateralParams bp) {
     const ScaleParams &p = bp.sp;
     pdl_launch_dependents();
     constexpr int V = VecOf<T>::V;
@@ -119,6 +125,8 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)p.slots * p.row_stride * sizeof(T));
     uint64_t *empty = full + p.slots;
     double *tab = reinterpret_cast<double *>(empty + p.slots);  // fp64: 2^(i/256), see exp2_tab
+    // row statistics (a, b) of the last TAPS chain rows: [TAPS][256 threads][2][V], row j lives in slot j % TAPS
+    T *stats = reinterpret_cast<T *>(tab + kExp2TabSize);
 
     const int nt = blockDim.x - 32;
     const int nwc = nt >> 5;
@@ -163,7 +171,9 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
             int slot = 0;
             uint32_t round = 0;
             for (int j = 0; j < n_load; ++j) {
-                if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
+                if (round > 0) {
+                    while (!mbar_test(&empty[slot], (round - 1) & 1)) __nanosleep(500);
+                }
                 const long long y = reflect_any(p.gwy0 + r + (long long)(i0 - C + j) * p.d, p.Hg) - p.gwy0 + p.row_off_in;
                 mbar_arrive_expect_tx(&full[slot], row_bytes);
                 tma_load_1d(rows + (size_t)slot * p.row_stride, src + y * p.in_pitch, row_bytes,
@@ -182,38 +192,102 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
     const int xg = x0 + tid * V;
     const bool act = xg < p.W;
     const TapPlan<NV> plan = make_tap_plan<V, NV>(act ? xg : x0, DMODE == 0 ? p.d : V, p.W, lo);
+    const int own = (act ? xg : x0) - lo;  // this thread's own vector inside a staged row
     const T var_factor = (T)bp.var_factor;
+    T *my_stats = stats + (size_t)tid * 2 * V;
+    constexpr int kStatSlot = 256 * 2 * V;  // elements per stats slot
 
     long long orow = (long long)r + (long long)i0 * p.d;
     int slot = 0, fslot = 0;  // slot of row j, slot of row j - 2C (first row of the window, next to be released)
+    int sslot = 0;            // j % TAPS
     uint32_t parity = 0;
     for (int j = 0; j < n_load; ++j) {
         mbar_wait(&full[slot], parity);
+        {
+            // statistics of the newest row relative to its own centre column:
+            // a = sum_k h_k (x_k - x_c), b = sum_k h_k (x_k - x_c)^2
+            T tv[TAPS][V];
+            row_taps<T, TAPS, DMODE>(rows + (size_t)slot * p.row_stride, plan, tv);
+            Pack<T, V> sa, sb;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                T a = T(0), b = T(0);
+#pragma unroll
+                for (int k = 0; k < C; ++k) {
+                    const T dl = tv[k][e] - tv[C][e], dr = tv[TAPS - 1 - k][e] - tv[C][e];
+                    a = fma_t<T>(Taps<T, TAPS>::h(k), dl + dr, a);
+                    b = fma_t<T>(Taps<T, TAPS>::h(k), fma_t<T>(dr, dr, dl * dl), b);
+                }
+                sa.v[e] = a;
+                sb.v[e] = b;
+            }
+            st_vec(my_stats + (size_t)sslot * kStatSlot, sa);
+            st_vec(my_stats + (size_t)sslot * kStatSlot + V, sb);
+        }
         if (j >= 2 * C) {
             if (act) {
-                // centre pixel: row j - C of the window, columns xg .. xg+V-1
                 int cs = fslot + C;
                 if (cs >= p.slots) cs -= p.slots;
-                Pack<T, V> xc = ld_vec(rows + (size_t)cs * p.row_stride + (xg - lo));
-                T dlt[TAPS][TAPS][V];
+                const Pack<T, V> xc = ld_vec(rows + (size_t)cs * p.row_stride + own);
+                // window moments from the row statistics, rows top to bottom (window row i is chain row j - 2C + i)
                 T s1[V], s2[V];
 #pragma unroll
                 for (int e = 0; e < V; ++e) { s1[e] = T(0); s2[e] = T(0); }
-                int ws = fslot;
+                int ws = fslot, ss = sslot + 1;  // (j - 2C) % TAPS == (j + 1) % TAPS
+                if (ss == TAPS) ss = 0;
+#pragma unroll
+                for (int i = 0; i < TAPS; ++i) {
+                    const T hi_ = Taps<T, TAPS>::h(i);
+                    const Pack<T, V> sa = ld_vec(my_stats + (size_t)ss * kStatSlot);
+                    const Pack<T, V> sb = ld_vec(my_stats + (size_t)ss * kStatSlot + V);
+                    if (i == C) {
+#pragma unroll
+                        for (int e = 0; e < V; ++e) {
+                            s1[e] = fma_t<T>(-hi_, sa.v[e], s1[e]);
+                            s2[e] = fma_t<T>(hi_, sb.v[e], s2[e]);
+                        }
+                    } else {
+                        const Pack<T, V> xi = ld_vec(rows + (size_t)ws * p.row_stride + own);
+#pragma unroll
+                        for (int e = 0; e < V; ++e) {
+                            const T dc = xc.v[e] - xi.v[e];
+                            const T t = fma_t<T>(T(-2), sa.v[e], dc);
+                            const T u = fma_t<T>(dc, t, sb.v[e]);
+                            s1[e] = fma_t<T>(hi_, dc - sa.v[e], s1[e]);
+                            s2[e] = fma_t<T>(hi_, u, s2[e]);
+                        }
+                    }
+                    if (++ws == p.slots) ws = 0;
+                    if (++ss == TAPS) ss = 0;
+                }
+                T nhi[V], num[V], den[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    T var = s2[e] - s1[e] * s1[e];
+                    if (var <= T(0)) var = T(1e-20);
+                    nhi[e] = nhalf_inverse<T>(var * var_factor);
+                    if constexpr (sizeof(T) == 8) nhi[e] *= 1.4426950408889634;  // exponent in base 2 for exp2_tab
+                    num[e] = T(0);
+                    den[e] = Taps<T, TAPS>::h(C) * Taps<T, TAPS>::h(C);
+                }
+                ws = fslot;
 #pragma unroll
                 for (int i = 0; i < TAPS; ++i) {
                     T tv[TAPS][V];
                     row_taps<T, TAPS, DMODE>(rows + (size_t)ws * p.row_stride, plan, tv);
 #pragma unroll
                     for (int k = 0; k < TAPS; ++k) {
-                        const T kk = Taps<T, TAPS>::h(i) * Taps<T, TAPS>::h(k);
+                        if (i == C && k == C) continue;
 #pragma unroll
                         for (int e = 0; e < V; ++e) {
                             const T dd = xc.v[e] - tv[k][e];
-                            dlt[i][k][e] = dd;
-                            const T kd = kk * dd;
-                            s1[e] += kd;
-                            s2[e] = fma_t<T>(kd, dd, s2[e]);
+                            T gw;
+                            if constexpr (sizeof(T) == 8)
+                                gw = exp2_tab(fma(dd * dd, nhi[e], TapLog2d<TAPS>::l(i) + TapLog2d<TAPS>::l(k)), tab);
+                            else
+                                gw = range_weight(Taps<T, TAPS>::h(i) * Taps<T, TAPS>::h(k), dd * dd, nhi[e]);
+                            den[e] += gw;
+                            num[e] = fma_t<T>(gw, dd, num[e]);
                         }
                     }
                     if (++ws == p.slots) ws = 0;
@@ -221,27 +295,7 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
                 Pack<T, V> cn, wv;
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
-                    T var = s2[e] - s1[e] * s1[e];
-                    if (var <= T(0)) var = T(1e-20);
-                    T nhi = nhalf_inverse<T>(var * var_factor);
-                    if constexpr (sizeof(T) == 8) nhi *= 1.4426950408889634;  // exponent in base 2 for exp2_tab
-                    T num = T(0);
-                    T den = Taps<T, TAPS>::h(C) * Taps<T, TAPS>::h(C);
-#pragma unroll
-                    for (int i = 0; i < TAPS; ++i)
-#pragma unroll
-                        for (int k = 0; k < TAPS; ++k) {
-                            if (i == C && k == C) continue;
-                            const T dd = dlt[i][k][e];
-                            T gw;
-                            if constexpr (sizeof(T) == 8)
-                                gw = exp2_tab(fma(dd * dd, nhi, TapLog2d<TAPS>::l(i) + TapLog2d<TAPS>::l(k)), tab);
-                            else
-                                gw = range_weight(Taps<T, TAPS>::h(i) * Taps<T, TAPS>::h(k), dd * dd, nhi);
-                            den += gw;
-                            num = fma_t<T>(gw, dd, num);
-                        }
-                    cn.v[e] = xc.v[e] - num / den;
+                    cn.v[e] = xc.v[e] - num[e] / den[e];
                     wv.v[e] = xc.v[e] - cn.v[e];
                 }
                 if (out_c) st_vec(out_c + orow * p.c_pitch + xg, cn);
@@ -253,6 +307,7 @@ __global__ void __launch_bounds__(288) bilateral_rows_kernel(const BilateralPara
             if (++fslot == p.slots) fslot = 0;
         }
         if (++slot == p.slots) { slot = 0; parity ^= 1; }
+        if (++sslot == TAPS) sslot = 0;
     }
 }
 
@@ -993,10 +1048,13 @@ __global__ void __launch_bounds__(256) bilateral_generic_kernel(const BilateralP
         T s1 = T(0), s2 = T(0);
 #pragma unroll
         for (int i = 0; i < TAPS; ++i) {
-            const T *row = in + (long long)reflect_any((long long)y + (long long)(i - C) * p.d, p.Hg) * p.in_pitch;
+            // lattice: the recursive algorithm's border rule (every decimated sub-array reflects at its own edges)
+            const T *row = in + (long long)(p.lattice ? reflect_lattice(y, i - C, p.d, p.H)
+                                                      : reflect_any((long long)y + (long long)(i - C) * p.d, p.Hg)) * p.in_pitch;
 #pragma unroll
             for (int k = 0; k < TAPS; ++k) {
-                const T dd = xc - row[reflect_any((long long)x + (long long)(k - C) * p.d, p.W)];
+                const T dd = xc - row[p.lattice ? reflect_lattice(x, k - C, p.d, p.W)
+                                                : reflect_any((long long)x + (long long)(k - C) * p.d, p.W)];
                 dlt[i][k] = dd;
                 const T kd = Taps<T, TAPS>::h(i) * Taps<T, TAPS>::h(k) * dd;
                 s1 += kd;
@@ -1030,7 +1088,8 @@ static int launch_bilateral(const BilateralParams &bp, int batch, int nt, cudaSt
         const int rc = ensure_exp2_table();
         if (rc) return rc;
     }
-    const size_t smem = (size_t)p.slots * p.row_stride * sizeof(T) + 16 * (size_t)p.slots + kExp2TabSize * sizeof(double);
+    const size_t smem = (size_t)p.slots * p.row_stride * sizeof(T) + 16 * (size_t)p.slots + kExp2TabSize * sizeof(double) +
+                        (size_t)TAPS * 256 * 32;  // + row-statistics ring: TAPS slots x 256 threads x 2 vectors
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1056,8 +1115,9 @@ static bool plan_bilateral(ScaleParams &p, int taps, int esize, int batch) {
     p.row_stride = (int)rs;
     int slots = taps + 3;
     const int min_slots = taps + 1;
-    const long long extra = kExp2TabSize * (long long)sizeof(double);
-    while (slots > min_slots && (long long)slots * p.row_stride * esize + 16LL * slots + extra > kMaxSmem) --slots;
+    const long long extra = kExp2TabSize * (long long)sizeof(double) + (long long)taps * 256 * 32;
+    // two resident blocks per SM when the rows allow it
+    while (slots > min_slots && (long long)slots * p.row_stride * esize + 16LL * slots + extra > kMaxSmem / 2 - 1024) --slots;
     if ((long long)slots * p.row_stride * esize + 16LL * slots + extra > kMaxSmem) return false;
     p.slots = slots;
     const int n_max = (p.H + p.d - 1) / p.d;
@@ -1197,6 +1257,39 @@ static int dispatch_bilateral(BilateralParams &bp, int batch, cudaStream_t st) {
 }  // namespace wb
 
 extern "C" {
+
+int wb_atrous_scale_bilateral_lattice(const void *in, void *out_c, void *out_w, int H, int W, long long in_pitch,
+                                      long long out_c_pitch, long long out_w_pitch, int scale, int taps, int dtype,
+                                      double var_factor, void *stream) {
+    int rc = wb::check_common(1, H, W, taps, dtype);
+    if (rc) return rc;
+    if (scale < 0 || scale > 30) return WB_EINVAL_SCALE;
+    if (!in || (!out_c && !out_w) || in == out_c || in == out_w) return WB_EINVAL_POINTER;
+    if (in_pitch < W || (out_c && out_c_pitch < W) || (out_w && out_w_pitch < W) || !(var_factor > 0)) return WB_EINVAL_ARG;
+    wb::BilateralParams bp;
+    memset(&bp, 0, sizeof(bp));
+    wb::ScaleParams &p = bp.sp;
+    p.in = in; p.out_c = out_c; p.out_w = out_w;
+    p.H = H; p.W = W; p.d = 1 << scale; p.Hg = H;
+    p.in_pitch = in_pitch; p.c_pitch = out_c_pitch; p.w_pitch = out_w_pitch;
+    p.lattice = 1;
+    bp.var_factor = var_factor;
+    bp.var_factor_f = (float)var_factor;
+    const long long n = (long long)H * W;
+    long long blocks = (n + 255) / 256;
+    const long long cap = 32LL * wb::device_sm_count();
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)blocks, 1);
+    if (dtype == WB_F32) {
+        if (taps == 3) wb::bilateral_generic_kernel<float, 3><<<grid, 256, 0, st>>>(bp);
+        else wb::bilateral_generic_kernel<float, 5><<<grid, 256, 0, st>>>(bp);
+    } else {
+        if (taps == 3) wb::bilateral_generic_kernel<double, 3><<<grid, 256, 0, st>>>(bp);
+        else wb::bilateral_generic_kernel<double, 5><<<grid, 256, 0, st>>>(bp);
+    }
+    return wb::launch_status();
+}
 
 int wb_atrous_scale_bilateral(const void *in, void *out_c, void *out_w, int batch, int H, int W, long long in_pitch,
                               long long in_bstride, long long out_c_pitch, long long out_c_bstride,

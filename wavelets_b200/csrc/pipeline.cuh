@@ -463,7 +463,7 @@ inline bool fast_path_ok(const ScaleParams &p, int taps, int esize) {
 }
 
 // Fill in the strip/segment/ring geometry.  Returns false if no geometry fits in shared memory.
-inline bool plan_fast(ScaleParams &p, int taps, int esize, int batch, int scale, K1Config *cfg_out, int nt_max = 512) {
+inline bool plan_fast(ScaleParams &p, int taps, int esize, int batch, int scale, K1Config *cfg_out) {
     const int V = 16 / esize;
     const int c = taps / 2;
     K1Config cfg;
@@ -476,7 +476,7 @@ inline bool plan_fast(ScaleParams &p, int taps, int esize, int batch, int scale,
         // a strip is at most 16 KiB of row data (4096 fp32 / 2048 fp64 columns)
         const int nt_cap = 16384 / (16 * cfg.ng);
         if (cfg.nt > nt_cap) cfg.nt = nt_cap;
-        if (cfg.nt > nt_max) cfg.nt = nt_max;
+        if (cfg.nt > 512) cfg.nt = 512;
         cfg.slots = 8;
         cfg.seg = 0;  // decided below
     }

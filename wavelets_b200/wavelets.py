@@ -385,11 +385,11 @@ class AtrousTransform:
         ``recursive=True`` on a plain 2-D transform reproduces the RESULT of the reference's recursive algorithm
         (watroo/wavelets.py:330-406; it differs from the standard one near the borders: symmetric pad by
         ``(taps // 2) * 2**(level-1)``, then every scale reflects inside its decimated sub-arrays) through a parity
-        kernel (``wb_atrous_scale_lattice``), not its CPU-side recursion.  For the bilateral cascade and for 1-D / 3-D
-        inputs the flag is ignored and the standard algorithm runs."""
+        kernel (``wb_atrous_scale_lattice`` / ``wb_atrous_scale_bilateral_lattice``), not its CPU-side recursion.  For
+        1-D / 3-D inputs the flag is ignored and the standard algorithm runs."""
         img, _ = to_device_image(arr, ndim_ok=(1, 2, 3))
         scaling_function = self.scaling_function_class(img.ndim)
-        if recursive and img.ndim == 2 and self.bilateral is None and int(level) >= 1:
+        if recursive and img.ndim == 2 and int(level) >= 1:
             planes = self._run_recursive(img, int(level), scaling_function)
         elif img.ndim == 2:
             planes = self._run(img, int(level), scaling_function)
@@ -398,7 +398,7 @@ class AtrousTransform:
         return Coefficients(planes, scaling_function, self.bilateral)
 
     def _run_recursive(self, img, level, scaling_function):
-        """Planes of ``atrous_recursive`` (watroo/wavelets.py:330-406) for a plain 2-D transform, level >= 1."""
+        """Planes of ``atrous_recursive`` (watroo/wavelets.py:330-406) for a 2-D transform (plain or bilateral), level >= 1."""
         lib = _lib.load(require_cuda=True)
         n_taps = len(scaling_function.coefficients_1d)
         hw = (n_taps // 2) * 2 ** (level - 1)
@@ -412,11 +412,17 @@ class AtrousTransform:
         hp, wp = cur.shape
         full = torch.empty((level + 1, hp, wp), dtype=img.dtype, device=img.device)
         code, taps = _lib.dtype_code(img.dtype), scaling_function.taps_code
+        factors = self.var_factors(level) if self.bilateral is not None else None
         with torch.cuda.device(img.device):
             for s in range(level):
                 nxt = full[level] if s == level - 1 else torch.empty_like(cur)
-                _lib.check(lib.wb_atrous_scale_lattice(cur.data_ptr(), nxt.data_ptr(), full[s].data_ptr(), hp, wp, wp, wp,
-                                                       wp, s, taps, code, _lib.stream_ptr(img.device)))
+                if factors is None:
+                    _lib.check(lib.wb_atrous_scale_lattice(cur.data_ptr(), nxt.data_ptr(), full[s].data_ptr(), hp, wp, wp,
+                                                           wp, wp, s, taps, code, _lib.stream_ptr(img.device)))
+                else:  # watroo/wavelets.py:371-378: variance and range-weighted gather per decimated sub-array
+                    _lib.check(lib.wb_atrous_scale_bilateral_lattice(cur.data_ptr(), nxt.data_ptr(), full[s].data_ptr(), hp,
+                                                                     wp, wp, wp, wp, s, taps, code, factors[s],
+                                                                     _lib.stream_ptr(img.device)))
                 cur = nxt
         return full[:, hw:hw + h, hw:hw + w].contiguous()
 
