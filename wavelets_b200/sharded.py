@@ -164,6 +164,7 @@ def push_plan(height: int, world: int, rank: int, halo_next: int, pad: int, row_
 
 
 _PEER_BUFFERS: dict = {}
+TRACE_EVENTS = None  # tools/trace_push.py: a list that receives one CUDA event per scale boundary of the push cascade
 
 
 class PeerBandBuffers:
@@ -235,6 +236,10 @@ class BandedTransform:
             peer.peer(rank + 1)[0, pad - h0: pad].copy_(band[rows - h0:])
         y0 = band_range(global_height, rank, world)[0]
         for s in range(level):
+            if TRACE_EVENTS is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                TRACE_EVENTS.append(ev)
             # every rank has received its halo of c_s and has finished reading the half this scale overwrites
             peer.barrier()
             last = s == level - 1
@@ -268,6 +273,10 @@ class BandedTransform:
             out_c = planes[level] if last else peer.buf[(s + 1) & 1]
             band_scale_p2p(peer.ptrs(s & 1), y0s, rank, out_c, planes[s], width, width, s, sf.taps_code, band.dtype,
                            band.device)
+        if TRACE_EVENTS is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            TRACE_EVENTS.append(ev)
         peer.barrier()  # nobody may refill the buffers (next call) while a neighbour still reads them
         return planes
 
