@@ -111,6 +111,18 @@ int wb_atrous_scale_lattice(const void *in, void *out_c, void *out_w, int H, int
                             long long out_c_pitch, long long out_w_pitch, int scale, int taps, int dtype, void *stream);
 
 /*
+ * wb_atrous_scale_bilateral on ONE ROW BAND of a taller image (multi-GPU row bands, no reference equivalent): same
+ * window conventions as wb_atrous_scale_band -- `in` holds the band's rows of c_s plus the halo rows of the neighbours
+ * ((taps/2) * 2^scale above and below, filled by the caller), taps reflect about global_H.  Same arithmetic as the
+ * unsharded kernel: bit-identical planes.
+ */
+int wb_atrous_scale_bilateral_band(const void *in, void *out_c, void *out_w, int band_rows, int W, int global_H,
+                                   long long band_y0, long long in_row_offset, long long in_pitch,
+                                   long long out_c_row_offset, long long out_c_pitch, long long out_w_row_offset,
+                                   long long out_w_pitch, int scale, int taps, int dtype, double var_factor,
+                                   void *stream);
+
+/*
  * The bilateral counterpart of wb_atrous_scale_lattice: one scale of the reference's RECURSIVE algorithm with
  * AtrousTransform(bilateral=...) (watroo/wavelets.py:371-378: sdev_loc and atrous_convolution on every decimated
  * sub-array, each with the symmetric border at ITS OWN edges).  Generic gather kernel (a parity mode).

@@ -47,7 +47,7 @@ def test_exchange_plan_is_symmetric_and_complete():
             assert got == need
 
 
-def _oracle_band_scale(ext_in, pad, out_c, out_pad, w_out, rows, width, height, y0, scale, taps_code):
+def _oracle_band_scale(ext_in, pad, out_c, out_pad, w_out, rows, width, height, y0, scale, taps_code, var_factor=None):
     """One scale of one band with the oracle's arithmetic (float64), reading only rows the band is entitled to."""
     name = "b3spline" if taps_code == 5 else "triangle"
     taps = orc.TAPS[name]
@@ -55,6 +55,29 @@ def _oracle_band_scale(ext_in, pad, out_c, out_pad, w_out, rows, width, height, 
     a = ext_in.numpy()
     xs = np.arange(width)
     gy = np.arange(y0, y0 + rows)
+    if var_factor is not None:
+        # bilateral scale (wavelets.py:433-442) on the band: variance and range-weighted gather from the same 25 taps
+        x = a[pad:pad + rows]
+        tap = {}
+        for i in range(len(taps)):
+            src = a[orc.reflect_index(gy + (i - c) * d, height) - y0 + pad]
+            for j in range(len(taps)):
+                tap[i, j] = src[:, orc.reflect_index(xs + (j - c) * d, width)]
+        assert all(np.isfinite(t).all() for t in tap.values()), "a halo row that was never exchanged has been read"
+        mean = sum(taps[i] * taps[j] * tap[i, j] for i, j in tap)
+        var = sum(taps[i] * taps[j] * tap[i, j] ** 2 for i, j in tap) - mean ** 2
+        var[var <= 0] = 1e-20
+        var = var * var_factor
+        num, den = taps[c] ** 2 * x, np.full_like(x, taps[c] ** 2)
+        for (i, j), t in tap.items():
+            if (i, j) != (c, c):
+                g = taps[i] * taps[j] * np.exp(-((x - t) ** 2) / var / 2)
+                num = num + g * t
+                den = den + g
+        res = num / den
+        out_c[out_pad:out_pad + rows] = torch.from_numpy(res)
+        w_out[:] = torch.from_numpy(x - res)
+        return
     out = np.zeros((rows, width))
     for i, ti in enumerate(taps):
         src = a[orc.reflect_index(gy + (i - c) * d, height) - y0 + pad]
@@ -67,7 +90,7 @@ def _oracle_band_scale(ext_in, pad, out_c, out_pad, w_out, rows, width, height, 
     w_out[:] = torch.from_numpy(a[pad:pad + rows] - out)
 
 
-def _worker(rank, world, port, height, width, level, sf_name, result_dir):
+def _worker(rank, world, port, height, width, level, sf_name, result_dir, bilateral=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -76,8 +99,8 @@ def _worker(rank, world, port, height, width, level, sf_name, result_dir):
         img = np.random.default_rng(42).standard_normal((height, width))
         y0, y1 = band_range(height, rank, world)
         sf = {"b3spline": wb.B3spline, "triangle": wb.Triangle}[sf_name]
-        planes = BandedTransform(sf, scale_fn=_oracle_band_scale, poison=True)(torch.from_numpy(img[y0:y1].copy()),
-                                                                              level, height)
+        planes = BandedTransform(sf, scale_fn=_oracle_band_scale, poison=True, bilateral=bilateral,
+                                 bilateral_scaling=bilateral is not None)(torch.from_numpy(img[y0:y1].copy()), level, height)
         np.save(os.path.join(result_dir, f"band{rank}.npy"), planes.numpy())
     finally:
         dist.destroy_process_group()
@@ -101,6 +124,18 @@ def test_banded_cascade_over_gloo(tmp_path, world, height, width, level, sf):
     assert got.shape == want.shape
     for p in range(level + 1):
         assert orc.emax(got[p], want[p]) < 1e-13, (p, orc.emax(got[p], want[p]))
+
+
+@pytest.mark.parametrize("world,height,width,level,sf,bilateral", [(2, 64, 48, 3, "b3spline", 1),
+                                                                   (3, 60, 40, 4, "triangle", [2, 1.5])])
+def test_banded_bilateral_cascade_over_gloo(tmp_path, world, height, width, level, sf, bilateral):
+    """Row bands + per-scale halo exchange reproduce the unsharded BILATERAL oracle cascade (same halo as the plain one)."""
+    mp.spawn(_worker, args=(world, _free_port(), height, width, level, sf, str(tmp_path), bilateral), nprocs=world, join=True)
+    img = np.random.default_rng(42).standard_normal((height, width))
+    want = orc.atrous_transform(img, level, sf, bilateral=bilateral, bilateral_scaling=True, backend="numpy")
+    got = np.concatenate([np.load(tmp_path / f"band{r}.npy") for r in range(world)], axis=1)
+    for p in range(level + 1):
+        assert orc.emax(got[p], want[p]) < 1e-12, (p, orc.emax(got[p], want[p]))
 
 
 class _OracleWowBackend:
@@ -166,6 +201,7 @@ def _wow_worker(rank, world, port, height, width, kw, result_dir):
     (3, 48, 40, dict(denoise_coefficients=[3], noise=2.0, soft_threshold=False)),
     (3, 60, 52, dict(denoise_coefficients=[4, 2])),   # noise=None: distributed exact MAD estimate of the raw w_0
     (2, 60, 52, dict(denoise_coefficients=[0, 3])),   # first threshold at scale 1: MAD of the WHITENED plane 0
+    (2, 64, 56, dict(bilateral=1, denoise_coefficients=[4, 2])),   # bilateral cascade on bands, bilateral sigma_e table
     (3, 64, 64, dict(denoise_coefficients=[0, 0, 2], soft_threshold=False)),
 ])
 def test_banded_wow_over_gloo(tmp_path, world, height, width, kw):

@@ -128,6 +128,39 @@ def test_halo_push_scale_equals_rows_of_full_transform(dt, shape, level, world):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_band_bilateral_equals_rows_of_full_transform(dt):
+    """wb_atrous_scale_bilateral_band on every band of every scale (halo rows copied in by hand) equals the rows of the
+    unsharded bilateral cascade bit for bit: multi-strip fp32 pair kernel, fp64 row kernel and the generic kernel."""
+    import wavelets_b200 as wb
+    from wavelets_b200.sharded import _cuda_band_scale, band_range, halo_rows
+    for h, w, level, world in ((192, 1024, 4, 3), (96, 130, 3, 2)):
+        gen = torch.Generator(device="cuda").manual_seed(6)
+        img = (torch.randn((h, w), generator=gen, device="cuda", dtype=torch.float32) * 3 + 20).to(dt)
+        for sf, bil in ((wb.B3spline, 1), (wb.Triangle, [2, 1.5])):
+            tr = wb.AtrousTransform(sf, bilateral=bil, bilateral_scaling=True)
+            full = tr(img, level).data
+            factors = tr.var_factors(level)
+            taps = len(sf.coefficients_1d)
+            pad = halo_rows(level - 1, taps)
+            c = [img]
+            for s in range(level):
+                c.append(wb.atrous_scale(c[-1], s, sf(2), out_w=False, var_factor=factors[s])[0])
+            for rank in range(world):
+                y0, y1 = band_range(h, rank, world)
+                rows = y1 - y0
+                for s in range(level):
+                    halo = halo_rows(s, taps)
+                    ext = torch.full((rows + 2 * pad, w), float("nan"), dtype=dt, device="cuda")
+                    g0, g1 = max(0, y0 - halo), min(h, y1 + halo)
+                    ext[pad + (g0 - y0): pad + (g1 - y0)] = c[s][g0:g1]
+                    out_c = torch.empty((rows + 2 * pad, w), dtype=dt, device="cuda")
+                    out_w = torch.empty((rows, w), dtype=dt, device="cuda")
+                    _cuda_band_scale(ext, pad, out_c, pad, out_w, rows, w, h, y0, s, sf.taps_code, var_factor=factors[s])
+                    assert torch.equal(out_w, full[s, y0:y1]), (sf.__name__, rank, s)
+                    assert torch.equal(out_c[pad:pad + rows], c[s + 1][y0:y1]), (sf.__name__, rank, s)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
 def test_band_whitening_equals_rows_of_unsharded_whitening(dt):
     """wb_wow_whiten_scale_band on every band of every scale (halo rows of the raw w_s copied in by hand) equals the
     rows of wb_wow_whiten_scale on the whole plane bit for bit, for the three significance modes."""

@@ -42,6 +42,8 @@ SIGNATURES = {
                                           _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_vp, _c_dbl, _c_vp]),
     "wb_atrous_scale_lattice": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_int, _c_int, _c_int,
                                          _c_vp]),
+    "wb_atrous_scale_bilateral_band": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll,
+                                                _c_ll, _c_ll, _c_ll, _c_int, _c_int, _c_int, _c_dbl, _c_vp]),
     "wb_atrous_scale_bilateral_lattice": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_int, _c_int,
                                                    _c_int, _c_dbl, _c_vp]),
     "wb_atrous_scale_band_push": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll,

@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(544) atrous_rows_kernel(const ScaleParams p) {
 // ---------------------------------------------------------------------------------------------------------------
 static constexpr int kLeanSlots = 8;
 
-template <int TAPS, int DMODE, bool HINTS>
+// OP_WHITEN (K3 of the two-pass WOW routes, MODE = significance compiled into the epilogue): the row pass filters the
+// SQUARES of the staged raw w_s rows and the epilogue whitens the raw centre value -- same pipeline, 2*T bytes per pixel.
+template <int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0>
 __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams p) {
     using T = float;
     constexpr int V = 4, NG = 2;
@@ -260,6 +262,8 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
     // ---------------- consumer warps ----------------
     const PackedTaps<TAPS> H;
     const uint64_t pol_keep = policy_evict_last();  // c_{s+1}: the next scale reads it back
+    WhitenEpilogue<T> epi;
+    if constexpr (OP == OP_WHITEN) epi.init(p, frame);
 
     uint32_t own[NG], tap[NG][NV];
     unsigned rev[NG];
@@ -309,12 +313,22 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
         P4 cv[NG];
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
-            const P4 v = lean_row_pass<TAPS, DMODE, I * RB, false, MIRROR>(tap[q], rev[q], H);
+            const P4 v = lean_row_pass<TAPS, DMODE, I * RB, OP == OP_WHITEN, MIRROR>(tap[q], rev[q], H);
             cv[q].lo = col_feed_p<TAPS>(S[q][0], v.lo, H);
             cv[q].hi = col_feed_p<TAPS>(S[q][1], v.hi, H);
         }
         constexpr int SC = (I - C + 8) & (kLeanSlots - 1);  // raw centre row j-C
         if (j >= 2 * C) {
+            if constexpr (OP == OP_WHITEN) {
+#pragma unroll
+                for (int q = 0; q < NG; ++q) {
+                    P4 raw = lds_p4_imm<SC * RB>(own[q]);
+                    raw.lo = epi.template apply2<MODE>(raw.lo, cv[q].lo);
+                    raw.hi = epi.template apply2<MODE>(raw.hi, cv[q].hi);
+                    if (act[q]) stg_p4_cs(w_ptr + q * q_off, raw);
+                }
+                w_ptr += w_step;
+            } else {
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
                 if (has_c && act[q]) {
@@ -332,6 +346,7 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
             if (has_c) c_ptr += c_step;
             if (has_w) w_ptr += w_step;
             out_row += p.d;
+            }
         }
         if (j >= C) {
             // the raw row j-C is not needed any more: hand its slot back to the producer
@@ -435,9 +450,9 @@ static bool k1_lean_enabled() {
     return v != 0;
 }
 
-template <int TAPS, int DMODE, bool HINTS>
+template <int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0>
 static int launch_rows_lean(const ScaleParams &p, int batch, int nt, cudaStream_t st) {
-    auto kern = atrous_rows_lean_kernel<TAPS, DMODE, HINTS>;
+    auto kern = atrous_rows_lean_kernel<TAPS, DMODE, HINTS, OP, MODE>;
     const size_t smem = (size_t)kLeanSlots * kLeanRB + 16 * (size_t)kLeanSlots;
     static bool configured[64] = {};  // per instantiation, per device
     int dev = 0;
@@ -467,6 +482,20 @@ static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
                 if (dmode == 1) return WB_LEAN(1);
                 if (dmode == 2) return WB_LEAN(2);
 #undef WB_LEAN
+            }
+        }
+        if constexpr (sizeof(T) == 4 && OP == OP_WHITEN) {
+            // the whitening pass of the two-pass WOW routes on whole-row strips: lean kernel, hints on
+            if (p.n_strips == 1 && cfg.ng == 2 && p.W > 1024 && cfg.slots == kLeanSlots && k1_lean_enabled() &&
+                !(scale < 32 && g_override_set[scale])) {
+#define WB_LEANW(DM)                                                                                              \
+    (p.sig_mode == 0 ? launch_rows_lean<TAPS, DM, true, OP_WHITEN, 0>(p, batch, cfg.nt, st)                        \
+                     : (p.sig_mode == 1 ? launch_rows_lean<TAPS, DM, true, OP_WHITEN, 1>(p, batch, cfg.nt, st)     \
+                                        : launch_rows_lean<TAPS, DM, true, OP_WHITEN, 2>(p, batch, cfg.nt, st)))
+                if (dmode == 0) return WB_LEANW(0);
+                if (dmode == 1) return WB_LEANW(1);
+                if (dmode == 2) return WB_LEANW(2);
+#undef WB_LEANW
             }
         }
 #define WB_LAUNCH(DM)                                                                   \

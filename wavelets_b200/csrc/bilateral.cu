@@ -298,8 +298,8 @@ __global__ void __launch_bounds__(288, 2) bilateral_rows_kernel(const BilateralP
                     cn.v[e] = xc.v[e] - num[e] / den[e];
                     wv.v[e] = xc.v[e] - cn.v[e];
                 }
-                if (out_c) st_vec(out_c + orow * p.c_pitch + xg, cn);
-                if (out_w) st_vec_cs(out_w + orow * p.w_pitch + xg, wv);
+                if (out_c) st_vec(out_c + (orow + p.row_off_c) * p.c_pitch + xg, cn);
+                if (out_w) st_vec_cs(out_w + (orow + p.row_off_w) * p.w_pitch + xg, wv);
             }
             orow += p.d;
             __syncwarp();
@@ -599,8 +599,8 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
                     statb[i] = stat_t + (uint32_t)ws * (256u * 16u);
                     if (++ws == p.slots) ws = 0;
                 }
-                float *c_dst = out_c ? out_c + orow * p.c_pitch + xg : nullptr;
-                float *w_dst = out_w ? out_w + orow * p.w_pitch + xg : nullptr;
+                float *c_dst = out_c ? out_c + (orow + p.row_off_c) * p.c_pitch + xg : nullptr;
+                float *w_dst = out_w ? out_w + (orow + p.row_off_w) * p.w_pitch + xg : nullptr;
                 pair_step<TAPS, DMODE, false, true, MIRROR>(D, xc_old, nhi, rowb, statb, cb, colb, rev, var_factor, c_dst, w_dst, act, pol_keep);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[fslot]);  // the window rows are only read in pass 1
@@ -735,8 +735,8 @@ __global__ void __launch_bounds__(288, 2) bilateral_window_kernel(const Bilatera
 
     // per-thread output pointers of the first output row; one add per row afterwards
     const long long orow0 = (long long)r + (long long)i0 * p.d;
-    float *c_dst = out_c ? out_c + (long long)frame * p.c_bstride + orow0 * p.c_pitch + xg : nullptr;
-    float *w_dst = out_w ? out_w + (long long)frame * p.w_bstride + orow0 * p.w_pitch + xg : nullptr;
+    float *c_dst = out_c ? out_c + (long long)frame * p.c_bstride + (orow0 + p.row_off_c) * p.c_pitch + xg : nullptr;
+    float *w_dst = out_w ? out_w + (long long)frame * p.w_bstride + (orow0 + p.row_off_w) * p.w_pitch + xg : nullptr;
     const long long c_step = (long long)p.d * p.c_pitch, w_step = (long long)p.d * p.w_pitch;
 
     auto run = [&](auto mirror) {
@@ -938,8 +938,8 @@ __global__ void __maxnreg__(56) bilateral_stream_kernel(const BilateralParams bp
     const float kc = Taps<float, TAPS>::h(C) * Taps<float, TAPS>::h(C);
 
     const long long orow0 = (long long)r + (long long)i0 * p.d;
-    float *c_dst = out_c ? out_c + (long long)frame * p.c_bstride + orow0 * p.c_pitch + xg : nullptr;
-    float *w_dst = out_w ? out_w + (long long)frame * p.w_bstride + orow0 * p.w_pitch + xg : nullptr;
+    float *c_dst = out_c ? out_c + (long long)frame * p.c_bstride + (orow0 + p.row_off_c) * p.c_pitch + xg : nullptr;
+    float *w_dst = out_w ? out_w + (long long)frame * p.w_bstride + (orow0 + p.row_off_w) * p.w_pitch + xg : nullptr;
     const long long c_step = (long long)p.d * p.c_pitch, w_step = (long long)p.d * p.w_pitch;
 
     auto run = [&](auto mirror) {
@@ -1043,14 +1043,16 @@ __global__ void __launch_bounds__(256) bilateral_generic_kernel(const BilateralP
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (long long)gridDim.x * blockDim.x) {
         const int y = (int)(idx / p.W), x = (int)(idx % p.W);
-        const T xc = in[(long long)y * p.in_pitch + x];
+        // band mode: output row y is global row gwy0 + y, found at buffer row y + row_off_in (see ScaleParams)
+        const T xc = in[((long long)y + p.row_off_in) * p.in_pitch + x];
         T dlt[TAPS][TAPS];
         T s1 = T(0), s2 = T(0);
 #pragma unroll
         for (int i = 0; i < TAPS; ++i) {
             // lattice: the recursive algorithm's border rule (every decimated sub-array reflects at its own edges)
-            const T *row = in + (long long)(p.lattice ? reflect_lattice(y, i - C, p.d, p.H)
-                                                      : reflect_any((long long)y + (long long)(i - C) * p.d, p.Hg)) * p.in_pitch;
+            const T *row = in + (p.lattice ? (long long)reflect_lattice(y, i - C, p.d, p.H)
+                                           : (long long)reflect_any(p.gwy0 + y + (long long)(i - C) * p.d, p.Hg) - p.gwy0 +
+                                                 p.row_off_in) * p.in_pitch;
 #pragma unroll
             for (int k = 0; k < TAPS; ++k) {
                 const T dd = xc - row[p.lattice ? reflect_lattice(x, k - C, p.d, p.W)
@@ -1075,8 +1077,8 @@ __global__ void __launch_bounds__(256) bilateral_generic_kernel(const BilateralP
                 num = fma_t<T>(gw, dlt[i][k], num);
             }
         const T cn = xc - num / den;
-        if (out_c) out_c[(long long)frame * p.c_bstride + (long long)y * p.c_pitch + x] = cn;
-        if (out_w) out_w[(long long)frame * p.w_bstride + (long long)y * p.w_pitch + x] = xc - cn;
+        if (out_c) out_c[(long long)frame * p.c_bstride + ((long long)y + p.row_off_c) * p.c_pitch + x] = cn;
+        if (out_w) out_w[(long long)frame * p.w_bstride + ((long long)y + p.row_off_w) * p.w_pitch + x] = xc - cn;
     }
 }
 
@@ -1257,6 +1259,34 @@ static int dispatch_bilateral(BilateralParams &bp, int batch, cudaStream_t st) {
 }  // namespace wb
 
 extern "C" {
+
+int wb_atrous_scale_bilateral_band(const void *in, void *out_c, void *out_w, int band_rows, int W, int global_H,
+                                   long long band_y0, long long in_row_offset, long long in_pitch,
+                                   long long out_c_row_offset, long long out_c_pitch, long long out_w_row_offset,
+                                   long long out_w_pitch, int scale, int taps, int dtype, double var_factor,
+                                   void *stream) {
+    int rc = wb::check_common(1, band_rows, W, taps, dtype);
+    if (rc) return rc;
+    if (scale < 0 || scale > 30) return WB_EINVAL_SCALE;
+    if (!in || (!out_c && !out_w) || in == out_c || in == out_w) return WB_EINVAL_POINTER;
+    if (global_H < band_rows || band_y0 < 0 || band_y0 + band_rows > global_H || in_pitch < W ||
+        (out_c && out_c_pitch < W) || (out_w && out_w_pitch < W) || !(var_factor > 0))
+        return WB_EINVAL_ARG;
+    wb::BilateralParams bp;
+    memset(&bp, 0, sizeof(bp));
+    wb::ScaleParams &p = bp.sp;
+    p.in = in; p.out_c = out_c; p.out_w = out_w;
+    p.H = band_rows; p.W = W; p.d = 1 << scale; p.Hg = global_H;
+    p.gwy0 = band_y0; p.row_off_in = in_row_offset; p.row_off_c = out_c_row_offset; p.row_off_w = out_w_row_offset;
+    p.in_pitch = in_pitch; p.c_pitch = out_c_pitch; p.w_pitch = out_w_pitch;
+    bp.var_factor = var_factor;
+    bp.var_factor_f = (float)var_factor;
+    p.l2_hints = wb::l2_hints_enabled();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WB_F32)
+        return taps == 3 ? wb::dispatch_bilateral<float, 3>(bp, 1, st) : wb::dispatch_bilateral<float, 5>(bp, 1, st);
+    return taps == 3 ? wb::dispatch_bilateral<double, 3>(bp, 1, st) : wb::dispatch_bilateral<double, 5>(bp, 1, st);
+}
 
 int wb_atrous_scale_bilateral_lattice(const void *in, void *out_c, void *out_w, int H, int W, long long in_pitch,
                                       long long out_c_pitch, long long out_w_pitch, int scale, int taps, int dtype,

@@ -100,14 +100,22 @@ def exchange_halos(ext: torch.Tensor, pad: int, height: int, halo: int, group=No
         w.wait()
 
 
-def _cuda_band_scale(ext_in, pad, ext_out, out_pad, w_out, band_rows, width, height, y0, scale, taps_code):
-    """One scale of one band on the device: wb_atrous_scale_band."""
+def _cuda_band_scale(ext_in, pad, ext_out, out_pad, w_out, band_rows, width, height, y0, scale, taps_code,
+                     var_factor=None):
+    """One scale of one band on the device: wb_atrous_scale_band, or wb_atrous_scale_bilateral_band when ``var_factor``
+    (sigma_b[s]**2 * (s + 1 if bilateral_scaling), watroo/wavelets.py:434-436) is given."""
     lib = _lib.load(require_cuda=True)
     with torch.cuda.device(ext_in.device):
-        _lib.check(lib.wb_atrous_scale_band(ext_in.data_ptr(), ext_out.data_ptr(), w_out.data_ptr(), band_rows, width,
-                                            height, y0, pad, ext_in.stride(0), out_pad, ext_out.stride(0), 0,
-                                            w_out.stride(0), scale, taps_code, _lib.dtype_code(ext_in.dtype),
-                                            _lib.stream_ptr(ext_in.device)))
+        if var_factor is None:
+            _lib.check(lib.wb_atrous_scale_band(ext_in.data_ptr(), ext_out.data_ptr(), w_out.data_ptr(), band_rows, width,
+                                                height, y0, pad, ext_in.stride(0), out_pad, ext_out.stride(0), 0,
+                                                w_out.stride(0), scale, taps_code, _lib.dtype_code(ext_in.dtype),
+                                                _lib.stream_ptr(ext_in.device)))
+        else:
+            _lib.check(lib.wb_atrous_scale_bilateral_band(
+                ext_in.data_ptr(), ext_out.data_ptr(), w_out.data_ptr(), band_rows, width, height, y0, pad,
+                ext_in.stride(0), out_pad, ext_out.stride(0), 0, w_out.stride(0), scale, taps_code,
+                _lib.dtype_code(ext_in.dtype), float(var_factor), _lib.stream_ptr(ext_in.device)))
 
 
 def band_scale_p2p(peer_ptrs, peer_y0, rank, out_c, out_w, width, pitch, scale, taps_code, dtype, device):
@@ -194,14 +202,18 @@ class PeerBandBuffers:
 
 
 class BandedTransform:
-    """Plain à trous cascade of ONE image sharded by row bands over the ranks of a process group.
+    """À trous cascade (plain, or bilateral with ``bilateral=``) of ONE image sharded by row bands over the ranks of a
+    process group.
 
     ``band`` is this rank's rows ``band_range(global_height, rank, world)`` of the image (device tensor on NCCL,
     CPU tensor with a custom ``scale_fn`` in the gloo tests).  Returns this rank's rows of the coefficient planes,
     shape ``(level + 1, band_rows, W)``.  ``scale_fn`` computes one scale of one band (default: the CUDA kernel)."""
 
-    def __init__(self, scaling_function_class=B3spline, group=None, scale_fn=None, poison=False, p2p=False, push=False):
+    def __init__(self, scaling_function_class=B3spline, group=None, scale_fn=None, poison=False, p2p=False, push=False,
+                 bilateral=None, bilateral_scaling=False):
         self.scaling_function_class = scaling_function_class
+        self.bilateral = bilateral                  # as AtrousTransform: None, a scalar or a per-scale list
+        self.bilateral_scaling = bilateral_scaling  # (the bilateral cascade takes the halo-exchange transport)
         self.group = group
         self.scale_fn = scale_fn or _cuda_band_scale
         self.poison = poison  # tests: NaN-fill the padded buffers so that any read of an unfilled halo row shows up
@@ -292,12 +304,16 @@ class BandedTransform:
         if level == 0:
             planes[0].copy_(band)
             return planes
-        if self.push and world > 1:
+        factors = None
+        if self.bilateral is not None:
+            from .wavelets import AtrousTransform
+            factors = AtrousTransform(self.scaling_function_class, self.bilateral, self.bilateral_scaling).var_factors(level)
+        if self.push and world > 1 and factors is None:
             min_rows = min(band_range(global_height, k, world)[1] - band_range(global_height, k, world)[0]
                            for k in range(world))
             if halo_rows(level - 1, n_taps) <= min_rows:  # single-hop halos; otherwise the exchange below (multi-hop)
                 return self._call_push(band, planes, level, global_height, sf, rank, world)
-        if self.p2p and world > 1:
+        if self.p2p and world > 1 and factors is None:
             return self._call_p2p(band, planes, level, global_height, sf, rank, world)
         pad = halo_rows(level - 1, n_taps) if world > 1 else 0
         pad = min(pad, global_height)
@@ -314,7 +330,11 @@ class BandedTransform:
                 exchange_halos(cur, pad, global_height, halo, self.group)
             last = s == level - 1
             out_c, out_pad = (planes[level], 0) if last else (nxt, pad)
-            self.scale_fn(cur, pad, out_c, out_pad, planes[s], rows, width, global_height, y0, s, sf.taps_code)
+            if factors is None:
+                self.scale_fn(cur, pad, out_c, out_pad, planes[s], rows, width, global_height, y0, s, sf.taps_code)
+            else:  # same halo (the bilateral gather reads the same taps), the range-weighted kernel on the band
+                self.scale_fn(cur, pad, out_c, out_pad, planes[s], rows, width, global_height, y0, s, sf.taps_code,
+                              var_factor=factors[s])
         return planes
 
 
@@ -399,7 +419,8 @@ def distributed_abs_median(x: torch.Tensor, group=None) -> torch.Tensor:
 
 
 class BandedWow:
-    """``wow(image)`` (watroo/utils.py:105-219, plain cascade, whitening on) of ONE image sharded by row bands.
+    """``wow(image)`` (watroo/utils.py:105-219, plain or bilateral cascade, whitening on) of ONE image sharded by row
+    bands.
 
     Per scale: halo exchange of ``c_s`` -> band scale kernel (``c_{s+1}``, raw ``w_s``) -> halo exchange of the raw
     ``w_s`` (the local power is a second dilated filter) -> band whitening kernel.  The residual plane needs the
@@ -416,8 +437,9 @@ class BandedWow:
         self.poison = poison
 
     def __call__(self, band, global_height, n_scales=None, weights=(), denoise_coefficients=(), noise=None,
-                 soft_threshold=True):
+                 soft_threshold=True, bilateral=None, bilateral_scaling=False):
         from .utils import _wow_plan
+        from .wavelets import AtrousTransform
         sf = self.scaling_function_class(2)
         n_taps = len(sf.coefficients_1d)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
@@ -425,9 +447,12 @@ class BandedWow:
         y0, y1 = band_range(global_height, rank, world)
         rows, width = band.shape
         assert rows == y1 - y0, f"rank {rank}: band has {rows} rows, expected {y1 - y0}"
-        level, _, wts, dns = _wow_plan((global_height, width), self.scaling_function_class, n_scales, list(weights),
-                                       list(denoise_coefficients), None)
-        sigma_e = sf.sigma_e()
+        level, sigma_bilateral, wts, dns = _wow_plan((global_height, width), self.scaling_function_class, n_scales,
+                                                     list(weights), list(denoise_coefficients), bilateral)
+        sigma_e = sf.sigma_e(bilateral=sigma_bilateral)  # the bilateral table when the cascade is bilateral
+        factors = None
+        if sigma_bilateral is not None:
+            factors = AtrousTransform(self.scaling_function_class, sigma_bilateral, bilateral_scaling).var_factors(level)
         be = self.backend
         planes = torch.empty((level + 1, rows, width), dtype=band.dtype, device=band.device)
         pad = min(halo_rows(max(level - 1, 0), n_taps), global_height) if world > 1 else 0
@@ -444,7 +469,11 @@ class BandedWow:
                 exchange_halos(cur, pad, global_height, halo, self.group)
             last = s == level - 1
             out_c, out_pad = (planes[level], 0) if last else (nxt, pad)
-            be.scale(cur, pad, out_c, out_pad, wext[pad:pad + rows], rows, width, global_height, y0, s, sf.taps_code)
+            if factors is None:
+                be.scale(cur, pad, out_c, out_pad, wext[pad:pad + rows], rows, width, global_height, y0, s, sf.taps_code)
+            else:
+                be.scale(cur, pad, out_c, out_pad, wext[pad:pad + rows], rows, width, global_height, y0, s, sf.taps_code,
+                         var_factor=factors[s])
             d = dns[s]
             if d != 0 and noise is None:
                 # MAD estimate over the WHOLE image, lazily at the first scale that thresholds (watroo/wavelets.py:126-127,
