@@ -495,11 +495,12 @@ def run_ours(args):
     g1.record(stream)
     barrier()
     e2e_wow_ms = g0.elapsed_time(g1)
+    ceil_wow_ms = copy_ceiling(dev, h * w * 4, h * w * 4, barrier)  # one frame each way, both directions at once
 
-    times = torch.tensor([elapsed_ms, e2e_ms, ceil_ms, e2e_wow_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([elapsed_ms, e2e_ms, ceil_ms, e2e_wow_ms, ceil_wow_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, ceil_ms, e2e_wow_ms = times.tolist()
+    elapsed_ms, e2e_ms, ceil_ms, e2e_wow_ms, ceil_wow_ms = times.tolist()
 
     units_per_step = h * w * LEVELS / 1e6  # Mpixel*scales
     value = units_per_step * args.steps * world / (elapsed_ms / 1e3)
@@ -531,6 +532,7 @@ def run_ours(args):
                     "frac_of_plain_copy": ceil_ms / (e2e_ms / e2e_steps)},
             "e2e_wow": {"frames_per_s": world * e2e_steps / (e2e_wow_ms / 1e3), "ms_per_frame": e2e_wow_ms / e2e_steps,
                         "h2d_bytes_per_step": h * w * 4, "d2h_bytes_per_step": h * w * 4,
+                        "plain_copy_ms_per_step": ceil_wow_ms, "frac_of_plain_copy": ceil_wow_ms / (e2e_wow_ms / e2e_steps),
                         "api": "wow_stream(pinned host frames) -> pinned host reconstructions (wow() per frame)"},
             "gpu_launches": args.steps * LEVELS,
             "clocks": clocks,

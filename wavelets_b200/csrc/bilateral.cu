@@ -631,8 +631,24 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
 // for this block size (a few spilled values; __maxnreg__(104) or (112) removes them but the register file then
 // holds ONE block per SM: 204 - 222 instead of 150 us).  Measured and not kept: 256-thread blocks whose thread 0 tops the ring
 // up with non-blocking probes (213 us: instruction-cache misses and a lagging warp 0).
-template <int TAPS, int DMODE>
-__global__ void __launch_bounds__(288, 2) bilateral_window_kernel(const BilateralParams bp) {
+// Block geometries (WG).  ptxas orders the tap loop by its register budget: at 96 registers (two 288-thread blocks per
+// SM, the round-2 default) it emits sub -> mul -> fma -> 2 MUFU -> accumulate serially per tap, every MUFU consumed the
+// instruction after it is issued (mean distance 3 instructions); from 128 registers on it keeps several taps in flight
+// (mean distance 8), whatever the source order.  The register file holds 16 warps at 128 registers, so:
+//   WG 0: 8 consumer warps + 1 producer warp, 2 blocks per SM, 96 registers (16 consumer warps per SM);
+//   WG 3: 4 consumer warps + 1 producer warp (160 threads, 256-column strips), 3 blocks per SM, 128 registers
+//         (12 consumer warps per SM, interleaved taps);
+//   WG 1 / 2 / 4: warp-group register reallocation (setmaxnreg): the block carries a producer WARP GROUP of four warps
+//         that gives its registers back (24 left; three of its warps exit at once) and the consumers grow to CREGS.
+template <int WG> struct WindowGeom {
+    static constexpr int CW = (WG == 2) ? 16 : ((WG == 3 || WG == 4) ? 4 : 8);              // consumer warps
+    static constexpr bool REALLOC = (WG == 1 || WG == 2 || WG == 4);                        // setmaxnreg
+    static constexpr int THREADS = CW * 32 + (REALLOC ? 128 : 32);                          // block size
+    static constexpr int BLOCKS = (WG == 2) ? 1 : ((WG == 3 || WG == 4) ? 3 : 2);           // resident blocks per SM
+    static constexpr int CREGS = (WG == 2) ? 112 : (WG == 4 ? 136 : 104);                   // consumer registers after the inc
+};
+template <int TAPS, int DMODE, int WG>
+__device__ __forceinline__ void bilateral_window_body(const BilateralParams &bp) {
     const ScaleParams &p = bp.sp;
     pdl_launch_dependents();
     constexpr int C = TAPS / 2;
@@ -642,7 +658,7 @@ __global__ void __launch_bounds__(288, 2) bilateral_window_kernel(const Bilatera
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)p.slots * p.row_stride * sizeof(float));
     uint64_t *empty = full + p.slots;
 
-    const int nt = blockDim.x - 32;  // consumer threads; the last warp is the TMA producer
+    const int nt = WindowGeom<WG>::CW * 32;  // consumer threads; the warp after them is the TMA producer
     const int nwc = nt >> 5;
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -700,8 +716,9 @@ __global__ void __launch_bounds__(288, 2) bilateral_window_kernel(const Bilatera
         m_pos += d_mod;
         if (m_pos >= period) m_pos -= period;
     };
-    if (warp == nwc) {
-        if (lane == 0) {
+    if (warp >= nwc) {
+        if constexpr (WindowGeom<WG>::REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (warp == nwc && lane == 0) {
             while (next_load < n_load) {
                 // the producer runs rows ahead of the consumers: poll rarely, its spinning would take issue slots
                 // from the warps doing the arithmetic
@@ -712,6 +729,7 @@ __global__ void __launch_bounds__(288, 2) bilateral_window_kernel(const Bilatera
         }
         return;
     }
+    if constexpr (WindowGeom<WG>::REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WindowGeom<WG>::CREGS));
 
     float *out_c = reinterpret_cast<float *>(p.out_c);
     float *out_w = reinterpret_cast<float *>(p.out_w);
@@ -837,6 +855,16 @@ __global__ void __launch_bounds__(288, 2) bilateral_window_kernel(const Bilatera
     // mirror selects; the choice is warp-uniform, so no thread diverges inside the step
     if (__any_sync(0xffffffffu, rev != 0)) run(IC<1>{});
     else run(IC<0>{});
+}
+
+template <int TAPS, int DMODE, int WG = 0>
+__global__ void __launch_bounds__(WindowGeom<WG>::THREADS, WindowGeom<WG>::BLOCKS) bilateral_window_kernel(const BilateralParams bp) {
+    bilateral_window_body<TAPS, DMODE, WG>(bp);
+}
+// WG 3 with the register budget spelled out (launch bounds alone make ptxas stop at 119 and serialise the taps again)
+template <int TAPS, int DMODE>
+__global__ void __maxnreg__(128) bilateral_window128_kernel(const BilateralParams bp) {
+    bilateral_window_body<TAPS, DMODE, 3>(bp);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1141,7 +1169,7 @@ static bool plan_bilateral(ScaleParams &p, int taps, int esize, int batch) {
 // bit-identity test.
 static int k2_window_mode() {
     const char *e = getenv("WB_K2_WINDOW");  // read on every call: the bit-identity test flips it inside one process
-    return (e && (e[0] == '0' || e[0] == '3')) ? e[0] - '0' : 1;
+    return (e && (e[0] == '0' || (e[0] >= '3' && e[0] <= '7'))) ? e[0] - '0' : 1;
 }
 
 template <int TAPS, int DMODE>
@@ -1161,9 +1189,10 @@ static int launch_bilateral_stream(const BilateralParams &bp, int batch, cudaStr
     return launch_pdl<BilateralParams>(kern, grid, dim3(256 + 32), smem, st, bp);
 }
 
-template <int TAPS, int DMODE>
+template <int TAPS, int DMODE, int WG = 0>
 static int launch_bilateral_window(const BilateralParams &bp, int batch, cudaStream_t st) {
-    auto kern = bilateral_window_kernel<TAPS, DMODE>;
+    void (*kern)(const BilateralParams) = bilateral_window_kernel<TAPS, DMODE, WG>;
+    if constexpr (WG == 3) kern = bilateral_window128_kernel<TAPS, DMODE>;
     const ScaleParams &p = bp.sp;
     const size_t smem = (size_t)p.slots * p.row_stride * sizeof(float) + 16 * (size_t)p.slots;
     static bool configured[64] = {};
@@ -1175,13 +1204,17 @@ static int launch_bilateral_window(const BilateralParams &bp, int batch, cudaStr
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
-    return launch_pdl<BilateralParams>(kern, grid, dim3(256 + 32), smem, st, bp);
+    return launch_pdl<BilateralParams>(kern, grid, dim3(WindowGeom<WG>::THREADS), smem, st, bp);
 }
 
 template <int TAPS, int DMODE>
 static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStream_t st) {
     const int wm = k2_window_mode();
     if (wm == 1) return launch_bilateral_window<TAPS, DMODE>(bp, batch, st);
+    if (wm == 4) return launch_bilateral_window<TAPS, DMODE, 1>(bp, batch, st);
+    if (wm == 5) return launch_bilateral_window<TAPS, DMODE, 2>(bp, batch, st);
+    if (wm == 6) return launch_bilateral_window<TAPS, DMODE, 3>(bp, batch, st);
+    if (wm == 7) return launch_bilateral_window<TAPS, DMODE, 4>(bp, batch, st);
     if (wm == 3) return launch_bilateral_stream<TAPS, DMODE>(bp, batch, st);
     auto kern = bilateral_pairs_kernel<TAPS, DMODE>;
     const ScaleParams &p = bp.sp;
@@ -1199,11 +1232,13 @@ static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStre
 }
 
 static int k2_window_mode();
+static int k2_blocks_per_sm(int wm) { return wm == 3 ? 4 : (wm == 5 ? 1 : (wm >= 6 ? 3 : 2)); }
+static int k2_consumer_threads(int wm) { return wm == 5 ? 512 : (wm >= 6 ? 128 : 256); }
 
 // Geometry for the fp32 pair kernel: 256 consumer threads x 2 pixels = 512-column strips.
-static bool plan_bilateral_pairs(ScaleParams &p, int taps, int batch, int occ) {
+static bool plan_bilateral_pairs(ScaleParams &p, int taps, int batch, int occ, int cthreads = 256, long long stats = kPairStats) {
     const int c = taps / 2;
-    p.wt = 512;
+    p.wt = 2 * cthreads;
     p.n_strips = (p.W + p.wt - 1) / p.wt;
     p.halo_al = round_up(c * p.d, 4);
     long long rs = (long long)p.wt + 2LL * p.halo_al;
@@ -1213,8 +1248,8 @@ static bool plan_bilateral_pairs(ScaleParams &p, int taps, int batch, int occ) {
     const int min_slots = taps + 1;
     // `occ` resident blocks per SM (register-limited: 2, or 4 for the streaming kernel): keep a block under that share
     // of the shared memory if possible
-    while (slots > min_slots && (long long)slots * (p.row_stride * 4 + 16LL + kPairStats) > kMaxSmem / occ - 1024) --slots;
-    if ((long long)slots * (p.row_stride * 4 + 16LL + kPairStats) > kMaxSmem) return false;
+    while (slots > min_slots && (long long)slots * (p.row_stride * 4 + 16LL + stats) > kMaxSmem / occ - 1024) --slots;
+    if ((long long)slots * (p.row_stride * 4 + 16LL + stats) > kMaxSmem) return false;
     p.slots = slots;
     const int n_max = (p.H + p.d - 1) / p.d;
     // Compute-bound kernel: about 4 waves of 2 resident blocks per SM; halo rows only cost L2 reads.
@@ -1237,7 +1272,8 @@ static int dispatch_bilateral(BilateralParams &bp, int batch, cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
         // packed fp32x2 pair kernel: dilation 1 or even (every scale of a dyadic cascade)
         if (fast_path_ok(p, TAPS, 4) && (p.d == 1 || p.d % 2 == 0) &&
-            plan_bilateral_pairs(p, TAPS, batch, k2_window_mode() == 3 ? 4 : 2))
+            plan_bilateral_pairs(p, TAPS, batch, k2_blocks_per_sm(k2_window_mode()), k2_consumer_threads(k2_window_mode()),
+                                 (k2_window_mode() == 0 || k2_window_mode() == 3) ? kPairStats : 0))
             return p.d == 1 ? launch_bilateral_pairs<TAPS, 1>(bp, batch, st) : launch_bilateral_pairs<TAPS, 0>(bp, batch, st);
     }
     if (fast_path_ok(p, TAPS, (int)sizeof(T)) && plan_bilateral(p, TAPS, (int)sizeof(T), batch)) {

@@ -167,12 +167,24 @@ __global__ void __launch_bounds__(256) select_pass_kernel(const T *x, long long 
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
     if (vec_ok) {
-        for (long long i = tid; i < nvec; i += nth) {
+        // four independent 16-byte loads in flight per thread: one load per iteration left the pass latency-bound
+        // (64 MiB in 34 us); the visits only touch registers and (rarely) shared-memory atomics
+        long long i = tid;
+        for (; i + 3 * nth < nvec; i += 4 * nth) {
+            Pack<T, V> p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = ld_vec(xf + (i + u * nth) * V);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int e = 0; e < V; ++e) visit(p[u].v[e]);
+        }
+        for (; i < nvec; i += nth) {
             Pack<T, V> p = ld_vec(xf + i * V);
 #pragma unroll
             for (int e = 0; e < V; ++e) visit(p.v[e]);
         }
-        for (long long i = nvec * V + tid; i < n; i += nth) visit(xf[i]);
+        for (long long i2 = nvec * V + tid; i2 < n; i2 += nth) visit(xf[i2]);
     } else {
         for (long long i = tid; i < n; i += nth) visit(xf[i]);
     }
@@ -381,7 +393,18 @@ __global__ void __launch_bounds__(256) moments_partial_kernel(const T *x, long l
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
     if ((reinterpret_cast<uintptr_t>(xf) & 15u) == 0) {
-        for (long long i = tid; i < nvec; i += nth) {
+        // (same summation order as a one-load-per-iteration loop: the four vectors are consumed in index order)
+        long long i = tid;
+        for (; i + 3 * nth < nvec; i += 4 * nth) {
+            Pack<T, V> p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = ld_vec(xf + (i + u * nth) * V);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int e = 0; e < V; ++e) { double dlt = (double)p[u].v[e] - K; s1 += dlt; s2 = fma(dlt, dlt, s2); }
+        }
+        for (; i < nvec; i += nth) {
             Pack<T, V> p = ld_vec(xf + i * V);
 #pragma unroll
             for (int e = 0; e < V; ++e) { double dlt = (double)p.v[e] - K; s1 += dlt; s2 = fma(dlt, dlt, s2); }
