@@ -211,8 +211,10 @@ def test_lean_fused_wow_scale_vs_oracle(dt):
 
 @pytest.mark.parametrize("sf", ["b3spline", "triangle"])
 def test_bilateral_kernel_variants_bit_identical(sf):
-    """The register-window K2 (WB_K2_WINDOW=1, default) and the low-register streaming K2 (=3) perform the operations of the round-1
-    kernel (=0) in the same order: bit-identical c_{s+1} and w_s on multi-strip frames, every dilation, batch of 2."""
+    """The register-window K2 in every block geometry (WB_K2_WINDOW=1 and the setmaxnreg / 160-thread / prefetch variants
+    4..9; unset = the per-scale choice the library makes) and the low-register streaming K2 (=3) perform the operations
+    of the round-1 kernel (=0) in the same order: bit-identical c_{s+1} and w_s on multi-strip frames, every dilation,
+    batch of 2."""
     import wavelets_b200 as wb
     sfn = _sf(sf)(2)
     c = len(orc.TAPS[sf]) // 2
@@ -224,8 +226,11 @@ def test_bilateral_kernel_variants_bit_identical(sf):
                 if c * 2 ** s > w:
                     break
                 outs = []
-                for mode in ("0", "1", "3"):
-                    os.environ["WB_K2_WINDOW"] = mode
+                for mode in ("0", "1", "3", "4", "5", "6", "7", "8", "9", None):
+                    if mode is None:
+                        os.environ.pop("WB_K2_WINDOW", None)
+                    else:
+                        os.environ["WB_K2_WINDOW"] = mode
                     outs.append(wb.atrous_scale(src, s, sfn, var_factor=1.7))
                 for o in outs[1:]:
                     assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]), (sf, b, h, w, s)

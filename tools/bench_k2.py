@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--side", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--modes", default="0,1,3")
+    ap.add_argument("--scales", default="0,1,3,6,9")
     ap.add_argument("--out", default="gpurun_out/bench_k2.json")
     args = ap.parse_args()
     n = args.side
@@ -30,14 +31,20 @@ def main():
     res = {"side": n, "us": {}, "bit_identical": True}
     for sfc in (wb.B3spline, wb.Triangle):
         sf = sfc(2)
-        for s in (0, 1, 3, 6, 9):
+        for s in ([int(x) for x in args.scales.split(",")]):
             outs = {}
             row = {}
             for mode in args.modes.split(","):
-                os.environ["WB_K2_WINDOW"] = mode
+                # "7" or "1:WB_K2_WAVES=2:WB_K2_POLL=200" (kernel variant plus environment knobs of csrc/bilateral.cu)
+                parts = mode.split(":")
+                os.environ["WB_K2_WINDOW"] = parts[0]
+                knobs = dict(kv.split("=") for kv in parts[1:])
+                os.environ.update(knobs)
                 c, w = torch.empty_like(img), torch.empty_like(img)
                 row[mode] = 1e3 * timed(lambda: atrous_scale(img, s, sf, out_c=c, out_w=w, var_factor=1.0), args.reps)
                 outs[mode] = (c, w)
+                for k in knobs:
+                    os.environ.pop(k, None)
             ref = outs[args.modes.split(",")[0]]
             same = all(torch.equal(ref[0], o[0]) and torch.equal(ref[1], o[1]) for o in outs.values())
             res["bit_identical"] &= same

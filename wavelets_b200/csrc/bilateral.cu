@@ -20,6 +20,7 @@ struct BilateralParams {
     ScaleParams sp;
     double var_factor;    // sigma_b[s]^2 * (s + 1 if bilateral_scaling else 1)
     float var_factor_f;   // the same, rounded once on the host (no F2F in the fp32 step loop)
+    unsigned poll_ns;     // window kernel: sleep between the producer's polls of a ring slot (0: the default)
 };
 
 __device__ __forceinline__ float exp2_fast(float x) {
@@ -640,12 +641,17 @@ __global__ void __launch_bounds__(288, 2) bilateral_pairs_kernel(const Bilateral
 //         (12 consumer warps per SM, interleaved taps);
 //   WG 1 / 2 / 4: warp-group register reallocation (setmaxnreg): the block carries a producer WARP GROUP of four warps
 //         that gives its registers back (24 left; three of its warps exit at once) and the consumers grow to CREGS.
+//   WG 5 / 6: WG 2 / 4 with the staged row fetched ONE STEP AHEAD into a sixth row of registers (the try_wait -> LDS.64 ->
+//         statistics -> variance -> rcp chain at the head of a step otherwise leaves the warp without exponentials
+//         to issue for ~150 cycles: tools/k2mimic.cu).
 template <int WG> struct WindowGeom {
-    static constexpr int CW = (WG == 2) ? 16 : ((WG == 3 || WG == 4) ? 4 : 8);              // consumer warps
-    static constexpr bool REALLOC = (WG == 1 || WG == 2 || WG == 4);                        // setmaxnreg
-    static constexpr int THREADS = CW * 32 + (REALLOC ? 128 : 32);                          // block size
-    static constexpr int BLOCKS = (WG == 2) ? 1 : ((WG == 3 || WG == 4) ? 3 : 2);           // resident blocks per SM
-    static constexpr int CREGS = (WG == 2) ? 112 : (WG == 4 ? 136 : 104);                   // consumer registers after the inc
+    static constexpr bool PF = (WG == 5 || WG == 6);                                       // prefetch the next row
+    static constexpr int G = (WG == 5) ? 2 : (WG == 6 ? 4 : WG);                           // block geometry
+    static constexpr int CW = (G == 2) ? 16 : ((G == 3 || G == 4) ? 4 : 8);                // consumer warps
+    static constexpr bool REALLOC = (G == 1 || G == 2 || G == 4);                          // setmaxnreg
+    static constexpr int THREADS = CW * 32 + (REALLOC ? 128 : 32);                         // block size
+    static constexpr int BLOCKS = (G == 2) ? 1 : ((G == 3 || G == 4) ? 3 : 2);             // resident blocks per SM
+    static constexpr int CREGS = (G == 2) ? 112 : (G == 4 ? 136 : 104);                    // consumer registers after the inc
 };
 template <int TAPS, int DMODE, int WG>
 __device__ __forceinline__ void bilateral_window_body(const BilateralParams &bp) {
@@ -722,8 +728,13 @@ __device__ __forceinline__ void bilateral_window_body(const BilateralParams &bp)
             while (next_load < n_load) {
                 // the producer runs rows ahead of the consumers: poll rarely, its spinning would take issue slots
                 // from the warps doing the arithmetic
-                if (lround > 0)
-                    while (!mbar_test(&empty[lslot], (lround - 1) & 1)) __nanosleep(1000);
+                // blocking try_wait (the hardware parks the warp for up to the suspend-time hint): the test + nanosleep
+                // poll of round 2 executed ~30 warp instructions per consumer warp-row, and this kernel is bound by
+                // instruction DISPATCH (tools/k2mimic.cu), so every instruction of the producer is paid for
+                if (lround > 0) {
+                    if (bp.poll_ns) while (!mbar_test(&empty[lslot], (lround - 1) & 1)) __nanosleep(bp.poll_ns);
+                    else mbar_wait(&empty[lslot], (lround - 1) & 1);
+                }
                 issue_load();
             }
         }
@@ -765,14 +776,25 @@ __device__ __forceinline__ void bilateral_window_body(const BilateralParams &bp)
         uint32_t parity = 0;
         // Step j = TAPS u + I: chain row j lands -> its tap pairs and statistics enter slot I; from j = 2C on, the
         // output row j - C (centre slot (I - C) mod TAPS) is produced from the window.
-        auto step = [&](auto ic, const int j) {
-            constexpr int I = decltype(ic)::value;
-            if (j >= n_load) return;
+        auto fetch = [&](u64 (&dst)[TAPS]) {
             mbar_wait(&full[slot], parity);
-            pair_taps<TAPS, DMODE, MIRROR>((uint32_t)slot * RB, colb, rev, X[I]);
+            pair_taps<TAPS, DMODE, MIRROR>((uint32_t)slot * RB, colb, rev, dst);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);  // the staged row is read exactly once per thread
             if (++slot == p.slots) { slot = 0; parity ^= 1; }
+        };
+        u64 N[TAPS];  // prefetch geometries: the tap pairs of the next chain row
+        if constexpr (WindowGeom<WG>::PF) fetch(N);
+        auto step = [&](auto ic, const int j) {
+            constexpr int I = decltype(ic)::value;
+            if (j >= n_load) return;
+            if constexpr (WindowGeom<WG>::PF) {
+#pragma unroll
+                for (int k = 0; k < TAPS; ++k) X[I][k] = N[k];
+                if (j + 1 < n_load) fetch(N);
+            } else {
+                fetch(X[I]);
+            }
             {
                 const P4 st = row_stats<TAPS>(X[I]);
                 SA[I] = st.lo;
@@ -1169,7 +1191,16 @@ static bool plan_bilateral(ScaleParams &p, int taps, int esize, int batch) {
 // bit-identity test.
 static int k2_window_mode() {
     const char *e = getenv("WB_K2_WINDOW");  // read on every call: the bit-identity test flips it inside one process
-    return (e && (e[0] == '0' || (e[0] >= '3' && e[0] <= '7'))) ? e[0] - '0' : 1;
+    return (e && (e[0] == '0' || e[0] == '1' || (e[0] >= '3' && e[0] <= '9'))) ? e[0] - '0' : -1;
+}
+// Geometry actually launched.  Without WB_K2_WINDOW: the 288-thread register-window kernel, except for the B3spline
+// scales with 8 <= d <= 128 where three 256-thread blocks per SM with reallocated registers (WG 4: the taps of a
+// warp interleaved, 256-column strips) measure 3 - 7 % faster (profiles/r2_bench_k2_scales.json); at d >= 256 their
+// narrow strips re-read too much of every row from L2.
+static int k2_mode_for(int taps, int d) {
+    const int wm = k2_window_mode();
+    if (wm >= 0) return wm;
+    return (taps == 5 && d >= 8 && d <= 128) ? 7 : 1;
 }
 
 template <int TAPS, int DMODE>
@@ -1193,6 +1224,8 @@ template <int TAPS, int DMODE, int WG = 0>
 static int launch_bilateral_window(const BilateralParams &bp, int batch, cudaStream_t st) {
     void (*kern)(const BilateralParams) = bilateral_window_kernel<TAPS, DMODE, WG>;
     if constexpr (WG == 3) kern = bilateral_window128_kernel<TAPS, DMODE>;
+    BilateralParams bq = bp;
+    if (const char *e = getenv("WB_K2_POLL")) bq.poll_ns = (unsigned)atoi(e);
     const ScaleParams &p = bp.sp;
     const size_t smem = (size_t)p.slots * p.row_stride * sizeof(float) + 16 * (size_t)p.slots;
     static bool configured[64] = {};
@@ -1204,17 +1237,19 @@ static int launch_bilateral_window(const BilateralParams &bp, int batch, cudaStr
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
-    return launch_pdl<BilateralParams>(kern, grid, dim3(WindowGeom<WG>::THREADS), smem, st, bp);
+    return launch_pdl<BilateralParams>(kern, grid, dim3(WindowGeom<WG>::THREADS), smem, st, bq);
 }
 
 template <int TAPS, int DMODE>
 static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStream_t st) {
-    const int wm = k2_window_mode();
+    const int wm = k2_mode_for(TAPS, bp.sp.d);
     if (wm == 1) return launch_bilateral_window<TAPS, DMODE>(bp, batch, st);
     if (wm == 4) return launch_bilateral_window<TAPS, DMODE, 1>(bp, batch, st);
     if (wm == 5) return launch_bilateral_window<TAPS, DMODE, 2>(bp, batch, st);
     if (wm == 6) return launch_bilateral_window<TAPS, DMODE, 3>(bp, batch, st);
     if (wm == 7) return launch_bilateral_window<TAPS, DMODE, 4>(bp, batch, st);
+    if (wm == 8) return launch_bilateral_window<TAPS, DMODE, 5>(bp, batch, st);
+    if (wm == 9) return launch_bilateral_window<TAPS, DMODE, 6>(bp, batch, st);
     if (wm == 3) return launch_bilateral_stream<TAPS, DMODE>(bp, batch, st);
     auto kern = bilateral_pairs_kernel<TAPS, DMODE>;
     const ScaleParams &p = bp.sp;
@@ -1232,8 +1267,14 @@ static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStre
 }
 
 static int k2_window_mode();
-static int k2_blocks_per_sm(int wm) { return wm == 3 ? 4 : (wm == 5 ? 1 : (wm >= 6 ? 3 : 2)); }
-static int k2_consumer_threads(int wm) { return wm == 5 ? 512 : (wm >= 6 ? 128 : 256); }
+static int k2_mode_for(int taps, int d);
+static int k2_blocks_per_sm(int wm) { return wm == 3 ? 4 : ((wm == 5 || wm == 8) ? 1 : ((wm == 6 || wm == 7 || wm == 9) ? 3 : 2)); }
+static int k2_consumer_threads(int wm) { return (wm == 5 || wm == 8) ? 512 : ((wm == 6 || wm == 7 || wm == 9) ? 128 : 256); }
+static int k2_waves() {
+    const char *e = getenv("WB_K2_WAVES");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 4;
+}
 
 // Geometry for the fp32 pair kernel: 256 consumer threads x 2 pixels = 512-column strips.
 static bool plan_bilateral_pairs(ScaleParams &p, int taps, int batch, int occ, int cthreads = 256, long long stats = kPairStats) {
@@ -1254,7 +1295,7 @@ static bool plan_bilateral_pairs(ScaleParams &p, int taps, int batch, int occ, i
     const int n_max = (p.H + p.d - 1) / p.d;
     // Compute-bound kernel: about 4 waves of 2 resident blocks per SM; halo rows only cost L2 reads.
     const long long chains = (long long)p.n_strips * (p.d < p.H ? p.d : p.H) * batch;
-    const long long target = 4LL * occ * device_sm_count();
+    const long long target = (long long)k2_waves() * occ * device_sm_count();
     long long per_chain = (target + chains - 1) / chains;
     if (per_chain < 1) per_chain = 1;
     int seg = (int)((n_max + per_chain - 1) / per_chain);
@@ -1272,8 +1313,8 @@ static int dispatch_bilateral(BilateralParams &bp, int batch, cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
         // packed fp32x2 pair kernel: dilation 1 or even (every scale of a dyadic cascade)
         if (fast_path_ok(p, TAPS, 4) && (p.d == 1 || p.d % 2 == 0) &&
-            plan_bilateral_pairs(p, TAPS, batch, k2_blocks_per_sm(k2_window_mode()), k2_consumer_threads(k2_window_mode()),
-                                 (k2_window_mode() == 0 || k2_window_mode() == 3) ? kPairStats : 0))
+            plan_bilateral_pairs(p, TAPS, batch, k2_blocks_per_sm(k2_mode_for(TAPS, p.d)), k2_consumer_threads(k2_mode_for(TAPS, p.d)),
+                                 (k2_mode_for(TAPS, p.d) == 0 || k2_mode_for(TAPS, p.d) == 3) ? kPairStats : 0))
             return p.d == 1 ? launch_bilateral_pairs<TAPS, 1>(bp, batch, st) : launch_bilateral_pairs<TAPS, 0>(bp, batch, st);
     }
     if (fast_path_ok(p, TAPS, (int)sizeof(T)) && plan_bilateral(p, TAPS, (int)sizeof(T), batch)) {
