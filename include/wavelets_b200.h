@@ -229,11 +229,15 @@ int wb_wow_scale(const void *in, void *out_c, void *out_w, int batch, int H, int
  * Replaces np.median(np.abs(data[0])) of Coefficients.get_noise (watroo/wavelets.py:126-127); bit-identical to
  * np.median (mean of the two middle values, in the plane dtype).  `out_median` (dtype of x, one per frame) and/or
  * `out_noise` (float64, one per frame: (median / 0.6745 in the plane dtype) / sigma_e0 in float64, i.e. get_noise
- * under NumPy >= 2) are written.  `workspace`: wb_abs_median_workspace_bytes(dtype, batch) bytes of device memory.
+ * under NumPy >= 2) are written.  `workspace`: `workspace_bytes` bytes of device memory, at least
+ * wb_abs_median_workspace_bytes(dtype, batch, 0) (selection state only: every counting pass then streams the plane);
+ * with wb_abs_median_workspace_bytes(dtype, batch, n) bytes (state + a quarter of the plane per frame) the first pass
+ * copies the values inside the sampled bracket of the median into the workspace and the later passes read only those
+ * (one streaming read of the plane instead of two or more).  The result does not depend on the workspace size.
  */
-size_t wb_abs_median_workspace_bytes(int dtype, int batch);
+size_t wb_abs_median_workspace_bytes(int dtype, int batch, long long n);
 int wb_abs_median(const void *x, long long n, int batch, long long bstride, int dtype, void *out_median,
-                  double *out_noise, double sigma_e0, void *workspace, void *stream);
+                  double *out_noise, double sigma_e0, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * Population moments of n contiguous elements per frame: out[frame] = {mean, variance, std} (float64).

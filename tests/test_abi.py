@@ -42,9 +42,11 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.wb_atrous_scale(ok, ctypes.c_void_p(32), None, 1, 8, 8, 4, 0, 8, 0, 8, 0, 0, 5, 0, None) == -6
     assert lib.wb_atrous_transform(None, ok, ok, 1, 8, 8, 8, 0, 2, 5, 0, None) == -5
     assert lib.wb_wow_whiten_scale(ok, ok, 1, 8, 8, 8, 0, 8, 0, 0, 5, 0, 0, 0.0, 1.0, 0.0, None, 1.0, None) == -5
-    assert lib.wb_abs_median(ok, 0, 1, 0, 0, ok, None, 1.0, ok, None) == -3
+    assert lib.wb_abs_median(ok, 0, 1, 0, 0, ok, None, 1.0, ok, 1 << 20, None) == -3
     assert b"dtype" in lib.wb_error_string(-1)
-    assert lib.wb_abs_median_workspace_bytes(0, 2) == 2 * lib.wb_abs_median_workspace_bytes(0, 1)
+    assert lib.wb_abs_median_workspace_bytes(0, 2, 0) >= 2 * lib.wb_abs_median_workspace_bytes(0, 1, 0) - 512
+    # + a quarter of the plane per frame for the filter pass
+    assert lib.wb_abs_median_workspace_bytes(0, 2, 1 << 20) >= lib.wb_abs_median_workspace_bytes(0, 2, 0) + 2 * (1 << 20)
 
 
 def test_kernel_path_selection(lib):

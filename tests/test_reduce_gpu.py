@@ -32,9 +32,10 @@ def test_abs_median_is_bit_exact(dt):
     for name, arr in _median_cases():
         a = arr.astype(dt)
         want = np.median(np.abs(a))
-        got = abs_median(torch.from_numpy(a).cuda()).cpu().numpy()[0]
-        assert got.dtype == want.dtype
-        assert got == want or (np.isnan(got) and np.isnan(want)), (name, dt, got, want)
+        for compact in (True, False):  # with / without the filter pass's compact buffer: same exact result
+            got = abs_median(torch.from_numpy(a).cuda(), compact=compact).cpu().numpy()[0]
+            assert got.dtype == want.dtype
+            assert got == want or (np.isnan(got) and np.isnan(want)), (name, dt, compact, got, want)
 
 
 def test_abs_median_batched_and_large():
@@ -52,6 +53,15 @@ def test_abs_median_batched_and_large():
     # full-size plane (4096^2), the size the MAD estimate runs on in BASELINE cfg3
     big = torch.randn((4096, 4096), generator=gen, device="cuda")
     assert abs_median(big).cpu().numpy()[0] == np.median(np.abs(big.cpu().numpy()))
+    assert abs_median(big, compact=False).cpu().numpy()[0] == np.median(np.abs(big.cpu().numpy()))
+    # heavy ties around the median (more than a quarter of the plane inside the sampled bracket: the compact buffer
+    # overflows and the passes fall back to the plane), odd element counts, unaligned views
+    ties = torch.round(torch.randn((1500, 1501), generator=gen, device="cuda") * 2)
+    assert abs_median(ties).cpu().numpy()[0] == np.median(np.abs(ties.cpu().numpy()))
+    tall = torch.randn((2049, 1023), generator=gen, device="cuda", dtype=torch.float64) ** 3
+    assert abs_median(tall).cpu().numpy()[0] == np.median(np.abs(tall.cpu().numpy()))
+    off = torch.randn(3_000_001, generator=gen, device="cuda")[1:].reshape(1, -1)  # 4-byte aligned only
+    assert abs_median(off).cpu().numpy()[0] == np.median(np.abs(off.cpu().numpy()))
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])

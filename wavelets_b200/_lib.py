@@ -61,8 +61,8 @@ SIGNATURES = {
                                    _c_vp]),
     "wb_wow_scale": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll, _c_ll, _c_ll,
                               _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_vp, _c_dbl, _c_vp]),
-    "wb_abs_median_workspace_bytes": (_c_sz, [_c_int, _c_int]),
-    "wb_abs_median": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_int, _c_vp, _c_vp, _c_dbl, _c_vp, _c_vp]),
+    "wb_abs_median_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_ll]),
+    "wb_abs_median": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_int, _c_vp, _c_vp, _c_dbl, _c_vp, _c_sz, _c_vp]),
     "wb_plane_moments_workspace_bytes": (_c_sz, [_c_int]),
     "wb_plane_moments": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_int, _c_vp, _c_vp, _c_vp]),
     "wb_significance": (_c_int, [_c_vp, _c_ll, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_vp, _c_vp, _c_int, _c_vp, _c_vp]),

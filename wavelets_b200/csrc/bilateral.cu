@@ -33,7 +33,7 @@ __device__ __forceinline__ float range_weight(float k, float d2, float nhalf_inv
 __device__ __forceinline__ double range_weight(double k, double d2, double nhalf_inv) { return k * exp(d2 * nhalf_inv); }
 template <typename T> __device__ __forceinline__ T nhalf_inverse(T v);
 template <> __device__ __forceinline__ float nhalf_inverse<float>(float v) { return -1.4426950408889634f / (2.0f * v); }
-template <> __device__ __forceinline__ double nhalf_inverse<double>(double v) { return -1.0 / (2.0 * v); }
+template <> __device__ __forceinline__ double nhalf_inverse<double>(double v) { return -0.5 * __drcp_rn(v); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // fp64 range weights: 2^a with a <= 0 from a 256-entry table of 2^(i/256) and a degree-4 polynomial -- 8 double-precision
@@ -296,7 +296,8 @@ __global__ void __launch_bounds__(288, 2) bilateral_rows_kernel(const BilateralP
                 Pack<T, V> cn, wv;
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
-                    cn.v[e] = xc.v[e] - num[e] / den[e];
+                    if constexpr (sizeof(T) == 8) cn.v[e] = xc.v[e] - num[e] * __drcp_rn(den[e]);
+                    else cn.v[e] = xc.v[e] - num[e] / den[e];
                     wv.v[e] = xc.v[e] - cn.v[e];
                 }
                 if (out_c) st_vec(out_c + (orow + p.row_off_c) * p.c_pitch + xg, cn);

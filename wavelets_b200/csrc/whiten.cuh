@@ -16,14 +16,16 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
 // fp32: weight / sqrt(P) is evaluated as weight * rsqrt.approx(P) (MUFU.RSQ, <= 2 ulp) instead of the reference's
 // sqrt -> divide -> multiply chain (three roundings): a few 1e-7 relative, far inside the 1e-5 parity budget, and
 // 5 instructions per pixel instead of ~30 (the fused kernel is issue-bound, not HBM-bound, otherwise).
-// fp64 keeps the exact sqrt and divide.  Soft threshold: erf(|w / thr|) with the reciprocal of thr hoisted (fp32);
+// fp64: weight * rsqrt(P) (CUDA's double-precision rsqrt, <= 1 ulp; the sqrt -> divide chain cost ~40 FP64 instructions per
+// pixel and made the fp64 whitening pass FP64-pipe-bound at twice its HBM time); the difference to the reference's
+// two roundings is <= 3 ulp, four orders of magnitude inside the 1e-12 budget.  Soft threshold: erf(|w / thr|) with the reciprocal of thr hoisted (fp32);
 // hard threshold: NumPy >= 2 compares |w| (fp32) with the float64 threshold; |w| > thr in float64 is equivalent to
 // |w| > RD(thr) in fp32 (RD = round towards -inf), so the mask stays bit-exact without float64 instructions.
 template <typename T> struct WhitenEpilogue {
     int mode;
     T thr_cmp;  // hard threshold in the plane dtype, rounded down
     T thr;      // fp64: the threshold itself (soft); fp32: unused
-    T inv_thr;  // fp32 soft: 1 / thr
+    T inv_thr;  // soft: 1 / thr
     T weight;
     __device__ __forceinline__ void init(const ScaleParams &p, int frame) {
         mode = p.sig_mode;
@@ -42,7 +44,7 @@ template <typename T> struct WhitenEpilogue {
         } else {
             thr_cmp = t;
             thr = t;
-            inv_thr = T(0);
+            inv_thr = fmin(1.0 / t, 1.7976931348623157e308);  // hoisted reciprocal (one rounding more than w / thr)
         }
         weight = (T)p.weight;
     }
@@ -50,11 +52,11 @@ template <typename T> struct WhitenEpilogue {
         power = (power <= T(0)) ? T(1e-15) : power;
         T g;
         if constexpr (sizeof(T) == 4) g = weight * rsqrt_fast(power);
-        else g = weight / sqrt(power);
+        else g = weight * rsqrt(power);  // MUFU.RSQ64H seed + Newton steps, <= 1 ulp: ~10 FP64 instructions instead of the ~40 of sqrt + divide
         if (mode == 1) {
             // the reference multiplies by erf() evaluated in float64 and rounds the product to the plane dtype
             if constexpr (sizeof(T) == 4) w = w * erff(fabsf(w * inv_thr));
-            else w = w * erf(fabs(w / thr));
+            else w = w * erf(fabs(w * inv_thr));
         } else if (mode == 2) {
             w = (fabs(w) > thr_cmp) ? w : T(0);
         }

@@ -22,8 +22,8 @@
 // Rows outside the image are symmetric reflections: the loader fetches the reflected rows; because the symmetric
 // extension commutes with the symmetric smooth, c_{s+1} / w_s evaluated at such a virtual row equal their reflected
 // values (up to the rounding of a reversed summation order), which is what the power filter needs at the border.
-// The strip is always the whole row, so the x border is an index reflection inside the staged row for both row
-// passes (same tap plan).  Away from the top/bottom border the arithmetic is exactly K1 followed by K3.
+// The strip is normally the whole row, so the x border is an index reflection inside the staged row for both row
+// passes (same tap plan); wow_rows_kernel can also walk column strips (see plan_wow).  Away from the top/bottom border the arithmetic is exactly K1 followed by K3.
 #include "pipeline.cuh"
 #include "whiten.cuh"
 
@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
     const int lane = tid & 31;
 
     int bx = blockIdx.x;
+    const int strip = bx % p.n_strips;
+    bx /= p.n_strips;
     const int r = bx % p.d;
     const int g = bx / p.d;
     const int frame = blockIdx.y;
@@ -60,8 +62,16 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
     const int n_out = min(p.seg, n_chain - i0);
     if (n_out <= 0) return;
     const int n_load = n_out + 4 * C;  // input rows i0-2C .. i0+n_out+2C-1 of the chain (virtual rows are reflected)
-    const uint32_t row_bytes = (uint32_t)p.W * (uint32_t)sizeof(T);
-    const T *src = reinterpret_cast<const T *>(p.in) + (long long)frame * p.in_bstride;
+    // Column strip [x0, x1) of the outputs (whole row: one strip, halo_al = 0).  The power filter needs w_s on
+    // [e_lo, e_hi) = strip +- C d, which needs c_s on [lo, hi) = strip +- 2 C d: the block stages [lo, hi), every thread
+    // owns columns of [e_lo, e_hi) for BOTH passes, and only the columns inside the strip are stored (the halo
+    // columns' power sums read ring positions nobody wrote; they are never stored).
+    const int x0 = strip * p.wt;
+    const int x1 = min(p.W, x0 + p.wt);
+    const int e_lo = max(0, x0 - p.halo_al), e_hi = min(p.W, x1 + p.halo_al);
+    const int lo = max(0, x0 - 2 * p.halo_al), hi = min(p.W, x1 + 2 * p.halo_al);
+    const uint32_t row_bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(T);
+    const T *src = reinterpret_cast<const T *>(p.in) + (long long)frame * p.in_bstride + lo;
     const long long y_first = (long long)r + (long long)(i0 - 2 * C) * p.d;  // image row of input row 0
 
     const uint64_t pol_in = policy_evict_first();   // c_s is dead once this launch has read it
@@ -88,15 +98,16 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
 
     uint32_t xb[NG];  // byte offset of this thread's own vector inside a staged row
     int xg[NG];
-    bool act[NG];
+    bool act[NG], outm[NG];  // act: the vector exists (shared-memory stores); outm: it lies inside the strip (global stores)
     BytePlan<NV> plan[NG];
 #pragma unroll
     for (int q = 0; q < NG; ++q) {
-        xg[q] = (q * (int)blockDim.x + tid) * V;
-        act[q] = xg[q] < p.W;
-        if (!act[q]) xg[q] = 0;  // idle threads shadow vector 0; only their stores are masked
-        xb[q] = (uint32_t)xg[q] * (uint32_t)sizeof(T);
-        const TapPlan<NV> tp = make_tap_plan<V, NV>(xg[q], DMODE == 0 ? p.d : V, p.W, 0);
+        xg[q] = e_lo + (q * (int)blockDim.x + tid) * V;
+        act[q] = xg[q] < e_hi;
+        if (!act[q]) xg[q] = e_lo;  // idle threads shadow the first vector; only their stores are masked
+        outm[q] = act[q] && xg[q] >= x0 && xg[q] < x1;
+        xb[q] = (uint32_t)(xg[q] - lo) * (uint32_t)sizeof(T);
+        const TapPlan<NV> tp = make_tap_plan<V, NV>(xg[q], DMODE == 0 ? p.d : V, p.W, lo);
 #pragma unroll
         for (int k = 0; k < NV; ++k) plan[q].off[k] = (uint32_t)tp.off[k] * (uint32_t)sizeof(T);
         plan[q].rev = tp.rev;
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
                     Pack<T, V> raw = lds_vec<T>(wrow + xb[q]);
 #pragma unroll
                     for (int e = 0; e < V; ++e) raw.v[e] = epi.apply(raw.v[e], pw[q].v[e]);
-                    if (act[q]) st_vec_cs(o_ptr + xg[q], raw);
+                    if (outm[q]) st_vec_cs(o_ptr + xg[q], raw);
                 }
                 o_ptr += o_step;
             }
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
             const uint32_t w2row = w2_base + (uint32_t)(mc & (kW2Ring - 1)) * RB;
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
-                if (store_c && act[q]) {
+                if (store_c && outm[q]) {
                     if (hints_c) st_vec_hint(c_ptr + xg[q], cv[q], pol_keep);
                     else st_vec(c_ptr + xg[q], cv[q]);
                 }
@@ -432,26 +443,55 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
 // ---------------------------------------------------------------------------------------------------------------
 struct WowGeom { int nt, ng; size_t smem; };
 
+// WB_WOW_STRIPS=k in the environment forces k column strips (>= 2) where the whole row would fit (A/B measurements).
+static int wow_forced_strips() {
+    const char *e = getenv("WB_WOW_STRIPS");
+    return e ? atoi(e) : 0;
+}
+
 static bool plan_wow(ScaleParams &p, int taps, int esize, int batch, WowGeom *geo) {
     const int V = 16 / esize;
     const int c = taps / 2;
     if (!fast_path_ok(p, taps, esize)) return false;
     if (!p.out_c || !p.out_w) return false;
-    const int vecs = p.W / V;
     const int ng = 2;
-    const int nt = round_up((vecs + ng - 1) / ng, 32);
-    if (nt > 512) return false;  // whole-row strips only: W <= 4096 (fp32) / 2048 (fp64)
-    p.wt = p.W;
-    p.n_strips = 1;
-    p.halo_al = 0;
-    p.row_stride = p.W;
-    const size_t row = (size_t)p.W * esize;
-    const int slots = kInRing;
-    const size_t smem = (size_t)(kInRing + kWRing + kW2Ring) * row + 8 * (size_t)(kInRing + kW2Ring);
-    if (smem > (size_t)kMaxSmem) return false;
-    p.slots = slots;
+    const int rows = kInRing + kWRing + kW2Ring;
+    const int forced = wow_forced_strips();
+    int nt = 0;
+    size_t smem = 0;
+    // Whole-row strips when the row fits 512 threads x 2 vectors (W <= 4096 fp32 / 2048 fp64).  The kernel also runs
+    // COLUMN strips (WB_WOW_STRIPS=k: the fewest >= k strips whose staged range, strip + 4 C d columns, fits the 14-row
+    // ring and whose extended range, strip + 2 C d, fits the block), built for float64 rows of 4096 columns -- and
+    // measured SLOWER than the two-pass route there (4096^2 float64: 142 - 229 us per scale against 75 + 60 us for K1 +
+    // K3, profiles/r2_bench_wow_f64_v2.json: this generic kernel is bound by instruction issue, not by the bytes the
+    // fusion saves), so wider rows are declined (WB_ENOT_FUSABLE -> two passes) unless the variable forces strips.
+    const int halo = round_up(c * p.d, V);
+    int k_strips = 0;
+    for (int k = (forced >= 2 ? forced : 1); k <= 64; ++k) {
+        const int wt = (k == 1) ? p.W : round_up((p.W + k - 1) / k, V);
+        const int h = (k == 1) ? 0 : halo;
+        long long stage = (long long)wt + 4LL * h, ext = (long long)wt + 2LL * h;
+        if (stage > p.W) stage = p.W;
+        if (ext > p.W) ext = p.W;
+        const int need = round_up((int)((ext / V + ng - 1) / ng), 32);
+        const size_t sm = (size_t)rows * (size_t)stage * esize + 8 * (size_t)(kInRing + kW2Ring);
+        if (k > 1 && forced < 2) break;  // see the note above: strips are not chosen automatically
+        if (k > 1 && (2 * h > wt || 5 * ext > 8 * (long long)wt)) break;  // halo too wide: more than 1.6 x the columns
+        if (need <= 512 && sm <= (size_t)kMaxSmem) {
+            k_strips = k;
+            p.wt = wt;
+            p.halo_al = h;
+            p.row_stride = (int)stage;
+            nt = need;
+            smem = sm;
+            break;
+        }
+    }
+    if (!k_strips) return false;
+    p.n_strips = (p.W + p.wt - 1) / p.wt;
+    p.slots = kInRing;
     const int n_max = (p.H + p.d - 1) / p.d;
-    const long long chains = (long long)(p.d < p.H ? p.d : p.H) * batch;
+    const long long chains = (long long)p.n_strips * (p.d < p.H ? p.d : p.H) * batch;
     int occ = (int)(kMaxSmem / (smem + 1024));
     const int occ_regs = 65536 / (nt * 128);
     if (occ > occ_regs) occ = occ_regs;
@@ -494,7 +534,7 @@ static auto wow_kernel_for(bool packed, int sig_mode) -> void (*)(const ScalePar
 template <typename T, int TAPS, int DMODE, bool HINTS>
 static int launch_wow_h(const ScaleParams &p, int batch, const WowGeom &geo, cudaStream_t st) {
     // the lean kernel always runs 512 threads x 2 vectors on 16 KiB ring slots: use it when the row needs them
-    const bool packed = sizeof(T) == 4 && p.W > 2048 && wow_packed_enabled();
+    const bool packed = sizeof(T) == 4 && p.W > 2048 && p.n_strips == 1 && wow_packed_enabled();
     auto kern = wow_kernel_for<T, TAPS, DMODE, HINTS>(packed, p.sig_mode);
     const int nt = packed ? 512 : geo.nt;
     const size_t smem = packed ? (size_t)(kInRing + kWRing) * kLeanRB + 8 * (size_t)(kInRing + kWRing) : geo.smem;
@@ -507,7 +547,7 @@ static int launch_wow_h(const ScaleParams &p, int batch, const WowGeom &geo, cud
         if (e != cudaSuccess) return (int)e;
         if (dev >= 0 && dev < 64) configured[kidx][dev] = true;
     }
-    dim3 grid((unsigned)((long long)p.d * p.n_seg), (unsigned)batch);
+    dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
     return launch_pdl<ScaleParams>(kern, grid, dim3((unsigned)nt), smem, st, p);
 }
 

@@ -168,28 +168,30 @@ def abs_median_noise(plane, sigma_e0, out_noise=None):
         plane = plane.contiguous()
         b, h, w, pitch, bstride = _frame_layout(plane)
     code = _lib.dtype_code(plane.dtype)
-    ws = torch.empty(lib.wb_abs_median_workspace_bytes(code, b), dtype=torch.uint8, device=plane.device)
+    ws = torch.empty(lib.wb_abs_median_workspace_bytes(code, b, h * w), dtype=torch.uint8, device=plane.device)
     if out_noise is None:
         out_noise = torch.empty(b, dtype=torch.float64, device=plane.device)
     with torch.cuda.device(plane.device):
         _lib.check(lib.wb_abs_median(plane.data_ptr(), h * w, b, bstride, code, 0, out_noise.data_ptr(),
-                                     float(sigma_e0), ws.data_ptr(), _lib.stream_ptr(plane.device)))
+                                     float(sigma_e0), ws.data_ptr(), ws.numel(), _lib.stream_ptr(plane.device)))
     return out_noise
 
 
-def abs_median(plane):
-    """Exact ``np.median(np.abs(plane))`` per frame as a tensor of the plane dtype, shape (batch,)."""
+def abs_median(plane, compact=True):
+    """Exact ``np.median(np.abs(plane))`` per frame as a tensor of the plane dtype, shape (batch,).  ``compact=False``
+    gives the kernel the selection state only (every pass streams the plane; same result, for tests / A-B timing)."""
     lib = _lib.load(require_cuda=True)
     b, h, w, pitch, bstride = _frame_layout(plane)
     if pitch != w:
         plane = plane.contiguous()
         b, h, w, pitch, bstride = _frame_layout(plane)
     code = _lib.dtype_code(plane.dtype)
-    ws = torch.empty(lib.wb_abs_median_workspace_bytes(code, b), dtype=torch.uint8, device=plane.device)
+    ws = torch.empty(lib.wb_abs_median_workspace_bytes(code, b, h * w if compact else 0), dtype=torch.uint8,
+                     device=plane.device)
     out = torch.empty(b, dtype=plane.dtype, device=plane.device)
     with torch.cuda.device(plane.device):
         _lib.check(lib.wb_abs_median(plane.data_ptr(), h * w, b, bstride, code, out.data_ptr(), 0, 1.0,
-                                     ws.data_ptr(), _lib.stream_ptr(plane.device)))
+                                     ws.data_ptr(), ws.numel(), _lib.stream_ptr(plane.device)))
     return out
 
 
