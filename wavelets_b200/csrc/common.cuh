@@ -278,4 +278,26 @@ inline int launch_pdl(void (*kern)(const P), dim3 grid, dim3 block, size_t smem,
     return (int)e;
 }
 
+// The same for kernels with any parameter list (the small reduction / point-wise kernels of the WOW tail and of the exact
+// median: a dozen dependent launches of a few microseconds each, where the launch-to-launch gap is a large share).
+template <typename... KArgs, typename... Args>
+inline int launch_pdl_v(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    if (!pdl_enabled()) {
+        kern<<<grid, block, smem, st>>>(KArgs(args)...);
+        return launch_status();
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 }  // namespace wb

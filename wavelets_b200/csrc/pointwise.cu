@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(256) denoise_plane_kernel(T *w, long long n, i
                                                             int sig_mode, double sigma, double sigma_e,
                                                             double noise_host, const double *noise_dev,
                                                             const T *noise_map, double weight) {
+    pdl_launch_dependents();
+    pdl_wait();  // may be launched with programmatic stream serialisation (WOW tail)
     const int frame = blockIdx.y;
     T *wf = w + (long long)frame * bstride;
     int mode = sig_mode;
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(256) denoise_plane_kernel(T *w, long long n, i
 template <typename T>
 __global__ void __launch_bounds__(256) residual_rescale_kernel(T *c, long long n, int batch, long long bstride,
                                                                const double *moments, double weight) {
+    pdl_launch_dependents();
+    pdl_wait();  // may be launched with programmatic stream serialisation (WOW tail)
     const int frame = blockIdx.y;
     T *cf = c + (long long)frame * bstride;
     T sd = (T)moments[frame * 3 + 2];
@@ -95,6 +99,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) synthesis_kernel(const T *planes, int nplanes, long long plane_stride,
                                                         long long n, int batch, long long in_bstride, T *out,
                                                         long long out_bstride) {
+    pdl_launch_dependents();
+    pdl_wait();  // may be launched with programmatic stream serialisation (WOW tail)
     const int frame = blockIdx.y;
     const T *pf = planes + (long long)frame * in_bstride;
     T *of = out + (long long)frame * out_bstride;
@@ -372,10 +378,8 @@ int wb_residual_rescale(void *c, long long n, int batch, long long bstride, int 
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(wb::grid_for(n / 4 + 1), (unsigned)batch);
     if (dtype == WB_F32)
-        wb::residual_rescale_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<float *>(c), n, batch, bstride, moments, weight);
-    else
-        wb::residual_rescale_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<double *>(c), n, batch, bstride, moments, weight);
-    return wb::launch_status();
+        return wb::launch_pdl_v(wb::residual_rescale_kernel<float>, grid, dim3(256), 0, st, reinterpret_cast<float *>(c), n, batch, bstride, moments, weight);
+    return wb::launch_pdl_v(wb::residual_rescale_kernel<double>, grid, dim3(256), 0, st, reinterpret_cast<double *>(c), n, batch, bstride, moments, weight);
 }
 
 int wb_synthesis(const void *planes, int nplanes, long long plane_stride, long long n, int batch,
@@ -386,12 +390,10 @@ int wb_synthesis(const void *planes, int nplanes, long long plane_stride, long l
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(wb::grid_for(n / 4 + 1), (unsigned)batch);
     if (dtype == WB_F32)
-        wb::synthesis_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float *>(planes), nplanes, plane_stride,
-                                                          n, batch, in_bstride, reinterpret_cast<float *>(out), out_bstride);
-    else
-        wb::synthesis_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double *>(planes), nplanes, plane_stride,
-                                                           n, batch, in_bstride, reinterpret_cast<double *>(out), out_bstride);
-    return wb::launch_status();
+        return wb::launch_pdl_v(wb::synthesis_kernel<float>, grid, dim3(256), 0, st, reinterpret_cast<const float *>(planes), nplanes,
+                                plane_stride, n, batch, in_bstride, reinterpret_cast<float *>(out), out_bstride);
+    return wb::launch_pdl_v(wb::synthesis_kernel<double>, grid, dim3(256), 0, st, reinterpret_cast<const double *>(planes), nplanes,
+                            plane_stride, n, batch, in_bstride, reinterpret_cast<double *>(out), out_bstride);
 }
 
 int wb_randn_f32(float *out, long long n, unsigned long long seed, unsigned long long offset, void *stream) {

@@ -122,6 +122,8 @@ template <typename T>
 __global__ void __launch_bounds__(1024) select_init_kernel(const T *x, long long n, long long bstride,
                                                            Workspace<typename KeyOf<T>::type> *ws_all,
                                                            unsigned long long gcap) {
+    pdl_launch_dependents();
+    pdl_wait();  // launched with programmatic stream serialisation: nothing is read before the predecessor is complete
     using K = typename KeyOf<T>::type;
     __shared__ K s[kSample];
     Workspace<K> *ws = ws_all + blockIdx.x;
@@ -178,6 +180,8 @@ constexpr int kStage = 6144;  // staged values per block; a block-iteration adds
 template <typename T>
 __global__ void __launch_bounds__(256) select_filter_kernel(const T *x, long long n, long long bstride,
                                                             Workspace<typename KeyOf<T>::type> *ws_all, T *compact_all) {
+    pdl_launch_dependents();
+    pdl_wait();  // launched with programmatic stream serialisation: nothing is read before the predecessor is complete
     using K = typename KeyOf<T>::type;
     Workspace<K> *ws = ws_all + blockIdx.y;
     if (ws->st.done || ws->st.mode != 2) return;
@@ -313,6 +317,8 @@ __global__ void __launch_bounds__(256) select_filter_kernel(const T *x, long lon
 template <typename T>
 __global__ void __launch_bounds__(256) select_pass_kernel(const T *x, long long n, long long bstride,
                                                           Workspace<typename KeyOf<T>::type> *ws_all, const T *compact_all) {
+    pdl_launch_dependents();
+    pdl_wait();  // launched with programmatic stream serialisation: nothing is read before the predecessor is complete
     using K = typename KeyOf<T>::type;
     Workspace<K> *ws = ws_all + blockIdx.y;
     if (ws->st.done) return;
@@ -412,6 +418,8 @@ template <typename T>
 __global__ void __launch_bounds__(1024) select_decide_kernel(long long n, Workspace<typename KeyOf<T>::type> *ws_all,
                                                              T *out_median, double *out_noise, double sigma_e0,
                                                              int last) {
+    pdl_launch_dependents();
+    pdl_wait();  // launched with programmatic stream serialisation: nothing is read before the predecessor is complete
     using K = typename KeyOf<T>::type;
     Workspace<K> *ws = ws_all + blockIdx.x;
     SelState<K> &st = ws->st;
@@ -620,6 +628,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) moments_partial_kernel(const T *x, long long n, long long bstride,
                                                               double *partial /* [batch][kMomBlocks][2] */,
                                                               double *shift_out /* [batch] */) {
+    pdl_launch_dependents();
+    pdl_wait();  // launched with programmatic stream serialisation: nothing is read before the predecessor is complete
     const T *xf = x + (long long)blockIdx.y * bstride;
     // shift K: mean of up to 256 strided samples -- identical in every block, keeps the sums well conditioned
     __shared__ double sh[8];
@@ -684,6 +694,8 @@ __global__ void __launch_bounds__(256) moments_partial_kernel(const T *x, long l
 
 __global__ void __launch_bounds__(256) moments_final_kernel(const double *partial, const double *shift, long long n,
                                                             int nblocks, double *out /* [batch][3] mean,var,std */) {
+    pdl_launch_dependents();
+    pdl_wait();
     const double *src = partial + (long long)blockIdx.x * nblocks * 2;
     double s1 = 0, s2 = 0;
     for (int i = threadIdx.x; i < nblocks; i += blockDim.x) { s1 += src[2 * i]; s2 += src[2 * i + 1]; }
@@ -723,7 +735,7 @@ static int median_impl(const void *x, long long n, int batch, long long bstride,
     if (workspace_bytes > state) gcap = ((workspace_bytes - state) / (size_t)batch / sizeof(T)) & ~(unsigned long long)15;
     if (gcap < 4096) gcap = 0;
     T *compact = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(workspace) + state);
-    select_init_kernel<T><<<batch, 1024, 0, st>>>(xp, n, bstride, ws, gcap);
+    launch_pdl_v(select_init_kernel<T>, dim3((unsigned)batch), dim3(1024), 0, st, xp, n, bstride, ws, gcap);
     long long blocks = (n / VecOf<T>::V + 255) / 256;
     int sms = 148;
     {
@@ -751,13 +763,13 @@ static int median_impl(const void *x, long long n, int batch, long long bstride,
             if (e != cudaSuccess) return (int)e;
             if (dev >= 0 && dev < 64) configured[dev] = true;
         }
-        select_filter_kernel<T><<<dim3((unsigned)fblocks, (unsigned)batch), 256, smem, st>>>(xp, n, bstride, ws, compact);
-        select_decide_kernel<T><<<batch, 1024, 0, st>>>(n, ws, reinterpret_cast<T *>(out_median), out_noise, sigma_e0, 0);
+        launch_pdl_v(select_filter_kernel<T>, dim3((unsigned)fblocks, (unsigned)batch), dim3(256), smem, st, xp, n, bstride, ws, compact);
+        launch_pdl_v(select_decide_kernel<T>, dim3((unsigned)batch), dim3(1024), 0, st, n, ws, reinterpret_cast<T *>(out_median), out_noise, sigma_e0, 0);
     }
     for (int p = 0; p < passes; ++p) {
-        select_pass_kernel<T><<<dim3((unsigned)blocks, (unsigned)batch), 256, 0, st>>>(xp, n, bstride, ws, compact);
-        select_decide_kernel<T><<<batch, 1024, 0, st>>>(n, ws, reinterpret_cast<T *>(out_median), out_noise, sigma_e0,
-                                                        p == passes - 1);
+        launch_pdl_v(select_pass_kernel<T>, dim3((unsigned)blocks, (unsigned)batch), dim3(256), 0, st, xp, n, bstride, ws, (const T *)compact);
+        launch_pdl_v(select_decide_kernel<T>, dim3((unsigned)batch), dim3(1024), 0, st, n, ws, reinterpret_cast<T *>(out_median),
+                     out_noise, sigma_e0, (int)(p == passes - 1));
     }
     return launch_status();
 }
@@ -804,11 +816,10 @@ int wb_plane_moments(const void *x, long long n, int batch, long long bstride, i
     double *shift = partial + (size_t)batch * wb::kMomBlocks * 2;
     dim3 grid(wb::kMomBlocks, (unsigned)batch);
     if (dtype == WB_F32)
-        wb::moments_partial_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float *>(x), n, bstride, partial, shift);
+        wb::launch_pdl_v(wb::moments_partial_kernel<float>, grid, dim3(256), 0, st, reinterpret_cast<const float *>(x), n, bstride, partial, shift);
     else
-        wb::moments_partial_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double *>(x), n, bstride, partial, shift);
-    wb::moments_final_kernel<<<batch, 256, 0, st>>>(partial, shift, n, wb::kMomBlocks, out);
-    return wb::launch_status();
+        wb::launch_pdl_v(wb::moments_partial_kernel<double>, grid, dim3(256), 0, st, reinterpret_cast<const double *>(x), n, bstride, partial, shift);
+    return wb::launch_pdl_v(wb::moments_final_kernel, dim3((unsigned)batch), dim3(256), 0, st, (const double *)partial, (const double *)shift, n, (int)wb::kMomBlocks, out);
 }
 
 }  // extern "C"

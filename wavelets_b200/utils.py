@@ -173,11 +173,12 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
     src = stack
     # Bilateral cascade with whitening: K2 is bound by the MUFU/FMA pipes and leaves HBM idle, the exact median and the
     # whitening pass K3 are bound by HBM.  They go to a high-priority side stream: K3 of scale s then runs under K2 of
-    # scale s+1 (its blocks are scheduled as K2 blocks retire).  Two raw planes alternate; events order the hand-over.
+    # scale s+1 (its blocks are scheduled as K2 blocks retire).  Three raw planes rotate (with two, K2 of scale 2 had to
+    # wait for the whitening of scale 0, which itself waits for the exact median); events order the hand-over.
     overlap = OVERLAP_BILATERAL and whitening and bilateral is not None and L > 1 and dev.type == "cuda"
     main = torch.cuda.current_stream(dev) if overlap else None
     side = _side_stream(dev) if overlap else None
-    ev_k3 = [None, None]  # whitening of the scale that last used raw_planes[i]
+    ev_k3 = [None, None, None]  # whitening of the scale that last used raw_planes[i]
     for s in range(L):
         dst_c = planes[:, L] if s == L - 1 else scratch[s & 1]
         d, wt = dns[s], wts[s]
@@ -196,10 +197,10 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
                                  nz if need_sig else _Noise(), wt)
             if not fused:
                 if raw_planes is None:
-                    raw_planes = torch.empty((2 if overlap else 1, b, h, w), dtype=dt, device=dev)
-                raw_plane = raw_planes[s & 1] if overlap else raw_planes[0]
-                if overlap and ev_k3[s & 1] is not None:
-                    main.wait_event(ev_k3[s & 1])  # the whitening that read this raw plane two scales ago is done
+                    raw_planes = torch.empty((3 if overlap else 1, b, h, w), dtype=dt, device=dev)
+                raw_plane = raw_planes[s % 3] if overlap else raw_planes[0]
+                if overlap and ev_k3[s % 3] is not None:
+                    main.wait_event(ev_k3[s % 3])  # the whitening that read this raw plane three scales ago is done
                 atrous_scale(src, s, sf, out_c=dst_c, out_w=raw_plane, var_factor=factors[s])
                 if overlap:
                     side.wait_stream(main)
@@ -209,8 +210,8 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
                     _whiten_scale(lib, raw_plane, planes[:, s], s, sf, mode, d, sigma_e[s] if need_sig else 1.0,
                                   nz if need_sig else _Noise(), wt)
                     if overlap:
-                        ev_k3[s & 1] = torch.cuda.Event()
-                        ev_k3[s & 1].record(side)
+                        ev_k3[s % 3] = torch.cuda.Event()
+                        ev_k3[s % 3].record(side)
         else:
             atrous_scale(src, s, sf, out_c=dst_c, out_w=planes[:, s], var_factor=factors[s])
             if need_sig and nz is None:
