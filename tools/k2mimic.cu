@@ -3,11 +3,11 @@
 // real kernel per mode, and reports the cycles per warp-row and the share of the MUFU pipe (8 cycles per warp MUFU per
 // SM sub-partition) they correspond to.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/k2mimic tools/k2mimic.cu && /tmp/k2mimic
-//   MODE 0: the 24 range-weighted taps only (sub2, mul2, fma2, 2 ex2, add2, fma2 per packed tap)
-//   MODE 1: + the window variance from row statistics (37 packed operations) and the 4 rcp
-//   MODE 2: + one new window row per step from shared memory (5 LDS.64) and the two float2 stores
-//   MODE 3: MODE 0 with scalar arithmetic on the two pixels (no packed instructions)
-//   MODE 4: MODE 0 with half of the exponentials replaced by a packed FMA-pipe polynomial (pipe balance)
+//   base: window variance from row statistics (37 packed operations), 4 rcp, the 24 range-weighted taps (sub2, mul2, fma2,
+//   2 ex2, add2, fma2 per packed tap); then one memory-side ingredient of the real kernel at a time (see F below).
+// It also holds the dispatch probe: N packed FFMA2 (or 2 N scalar FFMA) plus M independent ALU instructions per
+// iteration -- a packed instruction holds the issue port for TWO cycles (the ALU instructions add one cycle each on top
+// of 2 N instead of hiding under the FMA pipe), i.e. the kernel's issue budget is instructions + packed instructions.
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -21,20 +21,23 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f3
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// MODE >= 10: MODE 1 plus a bit mask of memory-side ingredients: 1 = 5 LDS.64, 2 = 2 STG.64, 4 = 2 STS.64 (instead of
-// the global stores), 8 = one mbarrier try_wait on a completed barrier per step (all lanes), 16 = the same by lane 0 only
-// + __syncwarp, 32 = 6 local-memory loads (the spills of the 96-register kernel)
-template <int MODE, int THREADS, int BLOCKS>
+// F: bit mask of memory-side ingredients: 1 = the new window row comes from shared memory (5 LDS.64; otherwise it is
+// synthesised in registers with 5 packed adds), 2 = 2 STG.64, 4 = 2 STS.64 (instead of the global stores), 8 = one mbarrier
+// try_wait on a completed barrier per step (all lanes), 16 = the same by lane 0 only + __syncwarp, 32 = 6 local-memory
+// loads (the spills of the 96-register kernel).  ARITH: 0 packed fp32x2, 1 scalar, 2 packed with every second exponential
+// as a polynomial on the FMA pipe.
+// Like the real kernel the step loop is unrolled by 5 so that the rotating window row is a compile-time register
+// index; every step brings in a new bottom row, so nothing is loop-invariant.
+template <int I> struct IC { static constexpr int value = I; };
+
+template <int ARITH, int F, int THREADS, int BLOCKS>
 __global__ void __launch_bounds__(THREADS, BLOCKS) mimic(float *out, int iters, float seed) {
     extern __shared__ float smem[];
-    constexpr int F = MODE >= 10 ? MODE - 10 : (MODE == 2 ? 3 : 0);
-    constexpr bool VAR = MODE == 1 || MODE == 2 || MODE >= 10;
     __shared__ unsigned long long bar;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bar)));
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&bar)) : "memory");
     }
-    __syncthreads();
     volatile float lmem[8];
     if (F & 32) for (int i = 0; i < 8; ++i) lmem[i] = seed * i;
     u64 X[5][5], SA[5], SB[5];
@@ -45,16 +48,16 @@ __global__ void __launch_bounds__(THREADS, BLOCKS) mimic(float *out, int iters, 
         SA[i] = pk2(seed * i, seed * (i + 1));
         SB[i] = pk2(seed * seed * i, seed * seed * (i + 2));
     }
-    if (F & 5) {
-        for (int i = threadIdx.x; i < 8 * 1024; i += blockDim.x) smem[i] = seed * i;
-        __syncthreads();
-    }
-    u64 nhi = pk2(-0.7f, -0.8f), acc = 0ull;
+    for (int i = threadIdx.x; i < 8 * 1024; i += blockDim.x) smem[i] = seed * i;
+    __syncthreads();
+    u64 acc = pk2(seed, seed);
     const float lk[5] = {-4.0f, -2.0f, -1.4150375f, -2.0f, -4.0f};
     const float h[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
     float2 *dst = reinterpret_cast<float2 *>(out) + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int it = 0; it < iters; ++it) {
-        const u64 xc = X[2][2];
+    const unsigned row0 = (unsigned)__cvta_generic_to_shared(smem) + (2 * threadIdx.x % 512) * 4;
+
+    auto step = [&](auto ic, int it) {
+        constexpr int I = decltype(ic)::value;  // slot of the new bottom row; the window is slots I+1 .. I+5 (mod 5)
         if (F & 8) {
             unsigned ok;
             do {
@@ -72,58 +75,67 @@ __global__ void __launch_bounds__(THREADS, BLOCKS) mimic(float *out, int iters, 
             }
             __syncwarp();
         }
-        if (VAR) {
-            if (F & 1) {
-                const float *row = smem + (it & 7) * 1024 + 2 * threadIdx.x % 512;
+        // the new row
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    u64 t;
-                    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(t) : "r"((unsigned)__cvta_generic_to_shared(row + 64 * k)));
-                    X[0][k] = t;  // the real kernel rotates the slot by unrolling; one slot suffices here
-                }
+        for (int k = 0; k < 5; ++k) {
+            if (F & 1) {
+                u64 t;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(t) : "r"(row0 + (unsigned)(((it & 7) * 1024 + 64 * k) * 4)));
+                X[I][k] = add2(t, acc);  // (one packed add more than the kernel: keeps the loads from being hoisted)
+            } else {
+                X[I][k] = add2(X[I][k], acc);
             }
-            // row statistics of the newest row + window variance (same operation count as the kernel)
+        }
+        // row statistics of the new row
+        {
             u64 a = 0ull, b = 0ull;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const u64 dl = sub2(X[0][k], X[0][2]), dr = sub2(X[0][4 - k], X[0][2]);
+                const u64 dl = sub2(X[I][k], X[I][2]), dr = sub2(X[I][4 - k], X[I][2]);
                 const u64 sum = add2(dl, dr), sq = fma2(dr, dr, mul2(dl, dl));
                 a = fma2(pk2(h[k], h[k]), sum, a);
                 b = fma2(pk2(h[k], h[k]), sq, b);
             }
-            SA[0] = a; SB[0] = b;
-            u64 s1 = 0ull, s2 = 0ull;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                if (i == 2) {
-                    s1 = fma2(pk2(-h[i], -h[i]), SA[i], s1);
-                    s2 = fma2(pk2(h[i], h[i]), SB[i], s2);
-                } else {
-                    const u64 dc = sub2(xc, X[i][2]);
-                    const u64 t = fma2(pk2(-2.0f, -2.0f), SA[i], dc);
-                    const u64 u = fma2(dc, t, SB[i]);
-                    s1 = fma2(pk2(h[i], h[i]), sub2(dc, SA[i]), s1);
-                    s2 = fma2(pk2(h[i], h[i]), u, s2);
-                }
-            }
-            float v0, v1;
-            up2(sub2(s2, mul2(s1, s1)), v0, v1);
-            v0 = (v0 <= 0.0f) ? 1e-20f : v0;
-            v1 = (v1 <= 0.0f) ? 1e-20f : v1;
-            nhi = pk2(-0.72f * rcpf(fmaxf(v0 * seed, 1e-37f)), -0.72f * rcpf(fmaxf(v1 * seed, 1e-37f)));
+            SA[I] = a;
+            SB[I] = b;
         }
+        constexpr int RC = (I + 5 - 2) % 5;
+        const u64 xc = X[RC][2];
+        u64 s1 = 0ull, s2 = 0ull;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            constexpr int dummy = 0;
+            const int rs = (I + 1 + i) % 5;
+            if (i == 2) {
+                s1 = fma2(pk2(-h[i], -h[i]), SA[rs], s1);
+                s2 = fma2(pk2(h[i], h[i]), SB[rs], s2);
+            } else {
+                const u64 dc = sub2(xc, X[rs][2]);
+                const u64 t = fma2(pk2(-2.0f, -2.0f), SA[rs], dc);
+                const u64 u = fma2(dc, t, SB[rs]);
+                s1 = fma2(pk2(h[i], h[i]), sub2(dc, SA[rs]), s1);
+                s2 = fma2(pk2(h[i], h[i]), u, s2);
+            }
+            (void)dummy;
+        }
+        float v0, v1;
+        up2(sub2(s2, mul2(s1, s1)), v0, v1);
+        v0 = (v0 <= 0.0f) ? 1e-20f : v0;
+        v1 = (v1 <= 0.0f) ? 1e-20f : v1;
+        const float h0 = -0.72f * rcpf(fmaxf(v0 * seed, 1e-37f)), h1 = -0.72f * rcpf(fmaxf(v1 * seed, 1e-37f));
+        const u64 nhi = pk2(h0, h1);
         u64 num = 0ull, den = pk2(0.14f, 0.14f);
-        if (MODE == 3) {
-            float x0, x1, n0 = 0, n1 = 0, d0 = 0.14f, d1 = 0.14f, h0, h1;
+        if (ARITH == 1) {
+            float x0, x1, n0 = 0, n1 = 0, d0 = 0.14f, d1 = 0.14f;
             up2(xc, x0, x1);
-            up2(nhi, h0, h1);
 #pragma unroll
             for (int i = 0; i < 5; ++i)
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
                     if (i == 2 && k == 2) continue;
+                    const int rs = (I + 1 + i) % 5;
                     float t0, t1;
-                    up2(X[i][k], t0, t1);
+                    up2(X[rs][k], t0, t1);
                     const float e0 = x0 - t0, e1 = x1 - t1;
                     const float g0 = ex2f(fmaf(e0 * e0, h0, lk[i] + lk[k])), g1 = ex2f(fmaf(e1 * e1, h1, lk[i] + lk[k]));
                     d0 += g0; d1 += g1;
@@ -137,11 +149,12 @@ __global__ void __launch_bounds__(THREADS, BLOCKS) mimic(float *out, int iters, 
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
                     if (i == 2 && k == 2) continue;
+                    const int rs = (I + 1 + i) % 5;
                     const float l = lk[i] + lk[k];
-                    const u64 dd = sub2(xc, X[i][k]);
+                    const u64 dd = sub2(xc, X[rs][k]);
                     const u64 arg = fma2(mul2(dd, dd), nhi, pk2(l, l));
                     u64 gw;
-                    if (MODE == 4 && ((i * 5 + k) & 1)) {
+                    if (ARITH == 2 && ((i * 5 + k) & 1)) {
                         // 2^arg on the FMA pipe: arg = n + f, degree-5 polynomial of 2^f, exponent add
                         const u64 magic = pk2(12582912.0f, 12582912.0f);
                         const u64 t = add2(arg, magic);
@@ -165,51 +178,51 @@ __global__ void __launch_bounds__(THREADS, BLOCKS) mimic(float *out, int iters, 
                     num = fma2(gw, dd, num);
                 }
         }
-        if (VAR) {
-            float n0, n1, d0, d1, x0, x1;
-            up2(num, n0, n1);
-            up2(den, d0, d1);
-            up2(xc, x0, x1);
-            const float c0 = x0 - n0 * rcpf(d0), c1 = x1 - n1 * rcpf(d1);
-            if (F & 2) {
-                dst[0] = make_float2(c0, c1);
-                __stcs(dst + 1, make_float2(x0 - c0, x1 - c1));
-            }
-            if (F & 4) {
-                float2 *sd = reinterpret_cast<float2 *>(smem + (it & 7) * 1024) + threadIdx.x % 256;
-                sd[0] = make_float2(c0, c1);
-                sd[256] = make_float2(x0 - c0, x1 - c1);
-            }
-            float ls = 0.0f;
-            if (F & 32) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) ls += lmem[i];
-            }
-            acc = add2(acc, pk2(c0 + ls, c1));
-        } else {
-            acc = add2(acc, add2(num, den));
+        float n0, n1, d0, d1, x0, x1;
+        up2(num, n0, n1);
+        up2(den, d0, d1);
+        up2(xc, x0, x1);
+        const float c0 = x0 - n0 * rcpf(d0), c1 = x1 - n1 * rcpf(d1);
+        if (F & 2) {
+            dst[0] = make_float2(c0, c1);
+            __stcs(dst + 1, make_float2(x0 - c0, x1 - c1));
         }
-        // rotate the window by one row (the real kernel does it by unrolling; here a dependent perturbation keeps the
-        // compiler from hoisting anything out of the loop)
+        if (F & 4) {
+            float2 *sd = reinterpret_cast<float2 *>(smem + (it & 7) * 1024) + threadIdx.x % 256;
+            sd[0] = make_float2(c0, c1);
+            sd[256] = make_float2(x0 - c0, x1 - c1);
+        }
+        float ls = 0.0f;
+        if (F & 32) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) X[4][k] = add2(X[4][k], acc);
+            for (int i = 0; i < 6; ++i) ls += lmem[i];
+        }
+        acc = pk2(c0 * 1e-6f + ls, c1 * 1e-6f);
+    };
+#pragma unroll 1
+    for (int it = 0; it < iters; it += 5) {
+        step(IC<0>{}, it);
+        step(IC<1>{}, it + 1);
+        step(IC<2>{}, it + 2);
+        step(IC<3>{}, it + 3);
+        step(IC<4>{}, it + 4);
     }
     float a0, a1;
     up2(acc, a0, a1);
     if (a0 + a1 == 123.456f) out[threadIdx.x] = a0;
 }
 
-template <int MODE, int THREADS, int BLOCKS> void run(const char *name, int mufu_per_iter) {
+template <int ARITH, int F, int THREADS, int BLOCKS> void run(const char *name, int mufu_per_iter) {
     float *out;
-    const int iters = 4000;
+    const int iters = 4000;  // multiple of 5
     const int blocks = 148 * BLOCKS;
     cudaMalloc(&out, (size_t)blocks * THREADS * 16 + 4096);
     const size_t smem = 8 * 1024 * 4;
-    mimic<MODE, THREADS, BLOCKS><<<blocks, THREADS, smem>>>(out, 50, 0.001f);
+    mimic<ARITH, F, THREADS, BLOCKS><<<blocks, THREADS, smem>>>(out, 50, 0.001f);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    mimic<MODE, THREADS, BLOCKS><<<blocks, THREADS, smem>>>(out, iters, 0.001f);
+    mimic<ARITH, F, THREADS, BLOCKS><<<blocks, THREADS, smem>>>(out, iters, 0.001f);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
@@ -272,22 +285,18 @@ template <int NF, int NI, bool SCALAR> void run_probe() {
 
 int main() {
     run_probe<8, 0, false>(); run_probe<8, 2, false>(); run_probe<8, 4, false>(); run_probe<8, 6, false>(); run_probe<8, 8, false>(); run_probe<8, 0, true>(); run_probe<8, 4, true>(); run_probe<8, 8, true>(); run_probe<0, 8, false>();
-    run<0, 256, 2>("taps only, packed", 48);
-    run<0, 256, 3>("taps only, packed", 48);
-    run<0, 128, 3>("taps only, packed (12 warps, more registers)", 48);
-    run<0, 256, 1>("taps only, packed (8 warps)", 48);
-    run<3, 256, 2>("taps only, scalar", 48);
-    run<4, 256, 2>("taps only, half of the exp2 on the FMA pipe", 24);
-    run<1, 256, 2>("+ variance, 4 rcp", 52);
-    run<2, 256, 2>("+ LDS.64 x5, stores", 52);
-    run<2, 128, 3>("+ LDS.64 x5, stores (12 warps)", 52);
-    run<10 + 1, 256, 2>("variance + taps + 5 LDS.64", 52);
-    run<10 + 2, 256, 2>("variance + taps + 2 STG.64", 52);
-    run<10 + 4, 256, 2>("variance + taps + 2 STS.64", 52);
-    run<10 + 1 + 4, 256, 2>("variance + taps + 5 LDS.64 + 2 STS.64", 52);
-    run<10 + 8, 256, 2>("variance + taps + mbarrier try_wait (all lanes)", 52);
-    run<10 + 16, 256, 2>("variance + taps + mbarrier try_wait (lane 0)", 52);
-    run<10 + 32, 256, 2>("variance + taps + 6 LDL", 52);
-    run<10 + 1 + 2 + 8 + 32, 256, 2>("everything", 52);
+    run<0, 0, 256, 2>("variance + 24 taps + 4 rcp, packed", 52);
+    run<0, 0, 128, 3>("  the same, 12 warps per SM", 52);
+    run<0, 0, 256, 1>("  the same, 8 warps per SM", 52);
+    run<1, 0, 256, 2>("  the same, scalar arithmetic", 52);
+    run<2, 0, 256, 2>("  the same, every second exp2 on the FMA pipe", 28);
+    run<0, 1, 256, 2>("+ 5 LDS.64", 52);
+    run<0, 2, 256, 2>("+ 2 STG.64", 52);
+    run<0, 4, 256, 2>("+ 2 STS.64", 52);
+    run<0, 8, 256, 2>("+ mbarrier try_wait (all lanes)", 52);
+    run<0, 16, 256, 2>("+ mbarrier try_wait (lane 0) + syncwarp", 52);
+    run<0, 32, 256, 2>("+ 6 LDL", 52);
+    run<0, 1 + 2 + 8 + 32, 256, 2>("+ all of the kernel's (LDS, STG, try_wait, LDL)", 52);
+    run<0, 1 + 2 + 8 + 32, 128, 3>("  the same, 12 warps per SM", 52);
     return 0;
 }
