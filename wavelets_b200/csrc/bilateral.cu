@@ -456,7 +456,8 @@ __device__ __forceinline__ void pair_step(u64 (&D)[TAPS][TAPS], u64 &xc_old, u64
         up2(num, n0, n1);
         up2(den, d0, d1);
         up2(xc_old, x0v, x1v);
-        const float c0 = x0v - n0 * rcp_fast(d0), c1 = x1v - n1 * rcp_fast(d1);
+        const float c0 = fmaf(-n0, rcp_fast(d0), x0v), c1 = fmaf(-n1, rcp_fast(d1), x1v);  // one FFMA each, spelled out: left to
+            // the compiler's contraction, one kernel fused both halves of the pair and another only one (1-ulp differences)
         if (act) {
             if (c_dst) {
                 if (pol_keep)
@@ -853,7 +854,8 @@ __device__ __forceinline__ void bilateral_window_body(const BilateralParams &bp)
             up2(num, n0, n1);
             up2(den, d0, d1);
             up2(xc, x0v, x1v);
-            const float c0 = x0v - n0 * rcp_fast(d0), c1 = x1v - n1 * rcp_fast(d1);
+            const float c0 = fmaf(-n0, rcp_fast(d0), x0v), c1 = fmaf(-n1, rcp_fast(d1), x1v);  // one FFMA each, spelled out: left to
+            // the compiler's contraction, one kernel fused both halves of the pair and another only one (1-ulp differences)
             if (act) {
                 if (c_dst) {
                     if (pol_keep)
@@ -891,6 +893,250 @@ __global__ void __launch_bounds__(WindowGeom<WG>::THREADS, WindowGeom<WG>::BLOCK
 template <int TAPS, int DMODE>
 __global__ void __maxnreg__(128) bilateral_window128_kernel(const BilateralParams bp) {
     bilateral_window_body<TAPS, DMODE, 3>(bp);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32, round 2 (second half): the register-window kernel made LEAN (bilateral_lean_kernel).  tools/k2mimic.cu replays
+// the arithmetic of one window step (162 packed operations, 52 MUFU, ~15 others) on the same SM: 506 cycles per
+// warp-row whatever the warp count, i.e. 114 us per 4096^2 plane, and every further instruction costs about one more
+// cycle (a packed fp32x2 instruction holds the issue port for two cycles, nothing hides under it).  The window kernel
+// executes 350 - 374 instructions per warp-row: ~130 of them are not arithmetic -- dynamic ring-slot arithmetic (slot *
+// stride, wrap, parity), one address add per LDS.64, null-pointer / activity / hint selects, parameters re-read from the
+// constant bank, spills.  Here the staging ring has as many slots as the unrolled step loop has steps (5 for B3spline,
+// 6 for Triangle: a staged row is read once, on arrival, so a few rows of prefetch suffice) and a fixed 16 KiB
+// stride: ring slot, barrier and parity are compile-time / one bit per loop iteration and every LDS.64 is
+// [register + immediate]; both outputs and the L2 hints are unconditional (the dispatcher sends everything else to the
+// window kernel).  Same operations in the same order: bit-identical planes.
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int kK2LeanRB = 16384;  // ring slot stride in bytes (a 512-column strip + 2 x 2 C d halo columns, d <= 448)
+template <int TAPS> struct K2LeanRing { static constexpr int R = (TAPS == 5) ? 5 : 6; };  // ring slots == unrolled steps
+
+template <int OFF> __device__ __forceinline__ u64 lds64_imm(uint32_t a) {
+    u64 r;
+    asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(r) : "r"(a), "n"(OFF));
+    return r;
+}
+
+template <int TAPS, int DMODE>
+__global__ void __launch_bounds__(288, 2) bilateral_lean_kernel(const BilateralParams bp) {
+    const ScaleParams &p = bp.sp;
+    pdl_launch_dependents();
+    constexpr int C = TAPS / 2;
+    constexpr int NL = PairPlan<TAPS, DMODE>::NL;
+    constexpr int R = K2LeanRing<TAPS>::R;
+    constexpr int RB = kK2LeanRB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)R * RB);
+    uint64_t *empty = full + R;
+    const uint32_t rows0 = smem_u32(smem_raw);
+    constexpr int FULL_OFF = R * RB, EMPTY_OFF = R * RB + 8 * R;  // barriers behind the ring: [ring base + immediate]
+
+    constexpr int nt = 256, nwc = 8;  // consumer threads / warps; warp 8 is the TMA producer
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    int bx = blockIdx.x;
+    const int strip = bx % p.n_strips;
+    bx /= p.n_strips;
+    const int r = bx % p.d;
+    const int g = bx / p.d;
+    const int frame = blockIdx.y;
+
+    const int n_chain = (r < p.H) ? (p.H - r + p.d - 1) / p.d : 0;
+    const int i0 = g * p.seg;
+    const int n_out = min(p.seg, n_chain - i0);
+    if (n_out <= 0) return;
+    const int n_load = n_out + 2 * C;
+
+    const int x0 = strip * p.wt;
+    const int lo = max(0, x0 - p.halo_al);
+    const int hi = min(p.W, x0 + p.wt + p.halo_al);
+    const uint32_t row_bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(float);
+
+    if (tid == 0) {
+        for (int s = 0; s < R; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nwc);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_wait();  // everything below touches global memory written or read by the previous launch
+
+    if (warp == nwc) {
+        if (lane == 0) {
+            // loader: the next chain row's position in the 2 Hg-periodic symmetric extension, walked incrementally
+            const float *src = reinterpret_cast<const float *>(p.in) + (long long)frame * p.in_bstride + lo;
+            const uint64_t pol_in = policy_evict_first();  // c_s is dead once this launch has read it
+            const long long period = 2LL * p.Hg;
+            const long long d_mod = (long long)p.d % period;
+            long long m_pos = (p.gwy0 + r + (long long)(i0 - C) * p.d) % period;
+            if (m_pos < 0) m_pos += period;
+            int lslot = 0;
+            uint32_t lround = 0;
+            for (int j = 0; j < n_load; ++j) {
+                if (lround > 0) mbar_wait(&empty[lslot], (lround - 1) & 1);
+                const long long y = (m_pos < p.Hg ? m_pos : period - 1 - m_pos) - p.gwy0 + p.row_off_in;
+                mbar_arrive_expect_tx(&full[lslot], row_bytes);
+                tma_load_1d_hint(smem_raw + (size_t)lslot * RB, src + y * p.in_pitch, row_bytes, &full[lslot], pol_in);
+                if (++lslot == R) { lslot = 0; ++lround; }
+                m_pos += d_mod;
+                if (m_pos >= period) m_pos -= period;
+            }
+        }
+        return;
+    }
+
+    int xg = x0 + tid * 2;
+    const bool act = xg < p.W && xg < x0 + p.wt;
+    if (!act) xg = x0;  // idle threads shadow the first pair of the strip; their stores are masked
+    uint32_t colb[NL];
+    unsigned rev = 0;
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+        const int pcol = xg + (k - NL / 2) * (DMODE == 0 ? p.d : 2);  // even; one reflection at most
+        const bool left = pcol < 0, right = pcol >= p.W;
+        const int q = left ? (-2 - pcol) : (right ? (2 * p.W - 2 - pcol) : pcol);
+        colb[k] = rows0 + (uint32_t)(q - lo) * 4u;  // absolute address of the tap in ring slot 0
+        if (left || right) rev |= 1u << k;
+    }
+    const float var_factor = bp.var_factor_f;
+    const uint64_t pol_keep = policy_evict_last();  // c_{s+1}: the next scale reads it back
+    const float kc = Taps<float, TAPS>::h(C) * Taps<float, TAPS>::h(C);
+    // values ptxas must HOLD (under register pressure it otherwise recomputes the shared-memory base from special
+    // registers and the 64-bit row steps from the constant bank in every step): ring base, own tap address and tap
+    // stride (interior warps address tap k as own + (k - C) stride), byte steps of the two output pointers
+    const uint32_t sbase = opaque_u32(rows0);
+    const uint32_t own = opaque_u32(colb[NL / 2]);
+    const uint32_t tstep = opaque_u32((uint32_t)(DMODE == 0 ? p.d : 2) * 4u);
+    const bool mirror_warp = __any_sync(0xffffffffu, rev != 0);
+    if (mirror_warp) {
+#pragma unroll
+        for (int k = 0; k < NL; ++k) colb[k] = opaque_u32(colb[k]);
+        rev = opaque_u32(rev);
+    }
+
+    // per-thread output pointers of the first output row; one 32-bit byte step per row afterwards (the host checks that
+    // d * pitch * 4 fits)
+    const long long orow0 = (long long)r + (long long)i0 * p.d;
+    char *c_dst = reinterpret_cast<char *>(reinterpret_cast<float *>(p.out_c) + (long long)frame * p.c_bstride + (orow0 + p.row_off_c) * p.c_pitch + xg);
+    char *w_dst = reinterpret_cast<char *>(reinterpret_cast<float *>(p.out_w) + (long long)frame * p.w_bstride + (orow0 + p.row_off_w) * p.w_pitch + xg);
+    const uint32_t c_step = opaque_u32((uint32_t)((long long)p.d * p.c_pitch * 4)), w_step = opaque_u32((uint32_t)((long long)p.d * p.w_pitch * 4));
+
+    auto run = [&](auto mirror) {
+        constexpr bool MIRROR = decltype(mirror)::value != 0;
+        u64 X[TAPS][TAPS];       // X[window slot][tap]: tap pairs of the last TAPS chain rows (row j lives in slot j % TAPS)
+        u64 SA[TAPS], SB[TAPS];  // row statistics (a, b) of those rows, see row_stats
+        // Step j = R u + I: chain row j lands in ring slot I -> its tap pairs and statistics enter window slot I % TAPS;
+        // from j = 2C on, the output row j - C (centre slot (I - C) mod TAPS) is produced from the window.
+        auto step = [&](auto ic, const int j, const uint32_t parity) {
+            constexpr int I = decltype(ic)::value;
+            constexpr int WS = I % TAPS;
+            if (j >= n_load) return;
+            mbar_wait_imm<FULL_OFF + 8 * I>(sbase, parity);
+            if constexpr (DMODE == 0) {
+#pragma unroll
+                for (int k = 0; k < TAPS; ++k) {
+                    u64 t = lds64_imm<I * RB>(MIRROR ? colb[k] : own + (uint32_t)(k - C) * tstep);
+                    if (MIRROR) {
+                        const u64 u = swap2(t);
+                        t = ((rev >> k) & 1u) ? u : t;
+                    }
+                    X[WS][k] = t;
+                }
+            } else {
+                float win[6];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    u64 t = lds64_imm<I * RB>(MIRROR ? colb[k] : own + (uint32_t)(k - 1) * tstep);
+                    if (MIRROR) {
+                        const u64 u = swap2(t);
+                        t = ((rev >> k) & 1u) ? u : t;
+                    }
+                    up2(t, win[2 * k], win[2 * k + 1]);
+                }
+#pragma unroll
+                for (int k = 0; k < TAPS; ++k) X[WS][k] = pk2(win[2 + (k - C)], win[3 + (k - C)]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_imm<EMPTY_OFF + 8 * I>(sbase);  // the staged row is read exactly once per thread
+            {
+                const P4 st = row_stats<TAPS>(X[WS]);
+                SA[WS] = st.lo;
+                SB[WS] = st.hi;
+            }
+            if (j < 2 * C) return;
+            constexpr int RC = (WS + TAPS - C) % TAPS;  // window slot of the centre row
+            const u64 xc = X[RC][C];
+            // window moments from the row statistics (law of total variance, differences only), rows top to bottom
+            u64 s1 = 0ull, s2 = 0ull;
+#pragma unroll
+            for (int i = 0; i < TAPS; ++i) {
+                const int rs = (WS + 1 + i) % TAPS;  // compile-time after unrolling
+                const float hi_ = Taps<float, TAPS>::h(i);
+                if (i == C) {
+                    s1 = fma2(pk2(-hi_, -hi_), SA[rs], s1);
+                    s2 = fma2(pk2(hi_, hi_), SB[rs], s2);
+                } else {
+                    const u64 dc = sub2(xc, X[rs][C]);
+                    const u64 t = fma2(pk2(-2.0f, -2.0f), SA[rs], dc);
+                    const u64 u = fma2(dc, t, SB[rs]);
+                    s1 = fma2(pk2(hi_, hi_), sub2(dc, SA[rs]), s1);
+                    s2 = fma2(pk2(hi_, hi_), u, s2);
+                }
+            }
+            float v0, v1;
+            up2(sub2(s2, mul2(s1, s1)), v0, v1);
+            v0 = (v0 <= 0.0f) ? 1e-20f : v0;
+            v1 = (v1 <= 0.0f) ? 1e-20f : v1;
+            const u64 nhi = pk2(-0.72134752044448170f * rcp_fast(fmaxf(v0 * var_factor, 1e-37f)),
+                                -0.72134752044448170f * rcp_fast(fmaxf(v1 * var_factor, 1e-37f)));
+            u64 num = 0ull, den = pk2(kc, kc);
+#pragma unroll
+            for (int i = 0; i < TAPS; ++i) {
+                const int rs = (WS + 1 + i) % TAPS;
+#pragma unroll
+                for (int k = 0; k < TAPS; ++k) {
+                    if (i == C && k == C) continue;
+                    const float lk = TapLog2<TAPS>::l(i) + TapLog2<TAPS>::l(k);
+                    const u64 dd = sub2(xc, X[rs][k]);
+                    float a0, a1;
+                    up2(fma2(mul2(dd, dd), nhi, pk2(lk, lk)), a0, a1);
+                    const u64 gw = pk2(exp2_fast(a0), exp2_fast(a1));
+                    den = add2(den, gw);
+                    num = fma2(gw, dd, num);
+                }
+            }
+            float n0, n1, d0, d1, x0v, x1v;
+            up2(num, n0, n1);
+            up2(den, d0, d1);
+            up2(xc, x0v, x1v);
+            const float c0 = fmaf(-n0, rcp_fast(d0), x0v), c1 = fmaf(-n1, rcp_fast(d1), x1v);  // one FFMA each, spelled out: left to
+            // the compiler's contraction, one kernel fused both halves of the pair and another only one (1-ulp differences)
+            if (act) {
+                asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(c_dst), "f"(c0), "f"(c1), "l"(pol_keep) : "memory");
+                __stcs(reinterpret_cast<float2 *>(w_dst), make_float2(x0v - c0, x1v - c1));
+            }
+            c_dst += c_step;
+            w_dst += w_step;
+        };
+        uint32_t parity = 0;
+#pragma unroll 1
+        for (int jb = 0; jb < n_load; jb += R) {
+            step(IC<0>{}, jb + 0, parity);
+            step(IC<1>{}, jb + 1, parity);
+            step(IC<2>{}, jb + 2, parity);
+            step(IC<3>{}, jb + 3, parity);
+            step(IC<4>{}, jb + 4, parity);
+            if constexpr (R == 6) step(IC<5>{}, jb + 5, parity);
+            parity ^= 1u;
+        }
+    };
+    // warps that own no reflected column (all but the first / last strip's edge warps) run the variant without the
+    // mirror selects; the choice is warp-uniform, so no thread diverges inside the step
+    if (mirror_warp) run(IC<1>{});
+    else run(IC<0>{});
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1064,7 +1310,8 @@ __global__ void __maxnreg__(56) bilateral_stream_kernel(const BilateralParams bp
                 up2(num, n0, n1);
                 up2(den, d0, d1);
                 up2(xc, x0v, x1v);
-                const float c0 = x0v - n0 * rcp_fast(d0), c1 = x1v - n1 * rcp_fast(d1);
+                const float c0 = fmaf(-n0, rcp_fast(d0), x0v), c1 = fmaf(-n1, rcp_fast(d1), x1v);  // one FFMA each, spelled out: left to
+            // the compiler's contraction, one kernel fused both halves of the pair and another only one (1-ulp differences)
                 if (act) {
                     if (c_dst) {
                         if (pol_keep)
@@ -1195,16 +1442,16 @@ static bool plan_bilateral(ScaleParams &p, int taps, int esize, int batch) {
 // bit-identity test.
 static int k2_window_mode() {
     const char *e = getenv("WB_K2_WINDOW");  // read on every call: the bit-identity test flips it inside one process
-    return (e && (e[0] == '0' || e[0] == '1' || (e[0] >= '3' && e[0] <= '9'))) ? e[0] - '0' : -1;
+    return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1;
 }
-// Geometry actually launched.  Without WB_K2_WINDOW: the 288-thread register-window kernel, except for the B3spline
-// scales with 8 <= d <= 128 where three 256-thread blocks per SM with reallocated registers (WG 4: the taps of a
-// warp interleaved, 256-column strips) measure 3 - 7 % faster (profiles/r2_bench_k2_scales.json); at d >= 256 their
-// narrow strips re-read too much of every row from L2.
+// Kernel actually launched.  Without WB_K2_WINDOW: the lean kernel (2), 8 - 15 % faster than the register-window kernel
+// in any of its block geometries at every scale (profiles/r2_bench_k2_lean.json; the geometries 4 .. 9 and the
+// prefetch variants all measured within 3 % of geometry 1, profiles/r2_bench_k2_scales.json).
 static int k2_mode_for(int taps, int d) {
     const int wm = k2_window_mode();
     if (wm >= 0) return wm;
-    return (taps == 5 && d >= 8 && d <= 128) ? 7 : 1;
+    (void)taps; (void)d;
+    return 2;  // the lean kernel (falls back to the window kernel, geometry 1, for what it does not take)
 }
 
 template <int TAPS, int DMODE>
@@ -1245,8 +1492,35 @@ static int launch_bilateral_window(const BilateralParams &bp, int batch, cudaStr
 }
 
 template <int TAPS, int DMODE>
+static int launch_bilateral_lean(const BilateralParams &bp, int batch, cudaStream_t st) {
+    auto kern = bilateral_lean_kernel<TAPS, DMODE>;
+    const ScaleParams &p = bp.sp;
+    const size_t smem = (size_t)K2LeanRing<TAPS>::R * kK2LeanRB + 16 * (size_t)K2LeanRing<TAPS>::R;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
+    return launch_pdl<BilateralParams>(kern, grid, dim3(256 + 32), smem, st, bp);
+}
+
+// The lean kernel takes the common case only: both outputs, L2 hints on, staged rows within its 16 KiB ring slots.
+static bool k2_lean_ok(const ScaleParams &p) {
+    return p.out_c && p.out_w && p.l2_hints && (long long)p.row_stride * 4 <= kK2LeanRB &&
+           (long long)p.d * p.c_pitch * 4 < (1LL << 31) && (long long)p.d * p.w_pitch * 4 < (1LL << 31);
+}
+
+template <int TAPS, int DMODE>
 static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStream_t st) {
-    const int wm = k2_mode_for(TAPS, bp.sp.d);
+    int wm = k2_mode_for(TAPS, bp.sp.d);
+    if (wm == 2) {
+        if (k2_lean_ok(bp.sp)) return launch_bilateral_lean<TAPS, DMODE>(bp, batch, st);
+        wm = 1;
+    }
     if (wm == 1) return launch_bilateral_window<TAPS, DMODE>(bp, batch, st);
     if (wm == 4) return launch_bilateral_window<TAPS, DMODE, 1>(bp, batch, st);
     if (wm == 5) return launch_bilateral_window<TAPS, DMODE, 2>(bp, batch, st);
