@@ -12,6 +12,8 @@
 // The centred form has no catastrophic cancellation, so the fp32 kernel follows the reference's float64 result
 // more closely than the reference's own fp32 path does.  Not HBM-bound: 24 exponentials
 // per pixel put it on the MUFU/FMA pipes; it shares the TMA row pipeline of K1 (taps rows resident in the ring).
+#include <utility>
+
 #include "pipeline.cuh"
 
 namespace wb {
@@ -916,8 +918,16 @@ template <int OFF> __device__ __forceinline__ u64 lds64_imm(uint32_t a) {
     asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(r) : "r"(a), "n"(OFF));
     return r;
 }
+// taps k = 0 .. TAPS-1 of an interior pair at dilation 2^LD: [own + slot offset + (k - C) * 4 * 2^LD], all immediates
+template <int TAPS, int SLOT_OFF, int LD, int... K>
+__device__ __forceinline__ void lean_load_taps(uint32_t own, u64 (&x)[TAPS], std::integer_sequence<int, K...>) {
+    ((x[K] = lds64_imm<SLOT_OFF + (K - TAPS / 2) * (4 << LD)>(own)), ...);
+}
 
-template <int TAPS, int DMODE>
+// LD >= 0: the dilation is 2^LD, known at compile time -- the taps of an interior pair are then [own + immediate] and cost
+// neither registers nor address arithmetic (held as five addresses they were spilled: four LDL per step); LD < 0: any
+// dilation, tap addresses formed from own and the stride.
+template <int TAPS, int DMODE, int LD>
 __global__ void __launch_bounds__(288, 2) bilateral_lean_kernel(const BilateralParams bp) {
     const ScaleParams &p = bp.sp;
     pdl_launch_dependents();
@@ -1030,15 +1040,28 @@ __global__ void __launch_bounds__(288, 2) bilateral_lean_kernel(const BilateralP
         u64 SA[TAPS], SB[TAPS];  // row statistics (a, b) of those rows, see row_stats
         // Step j = R u + I: chain row j lands in ring slot I -> its tap pairs and statistics enter window slot I % TAPS;
         // from j = 2C on, the output row j - C (centre slot (I - C) mod TAPS) is produced from the window.
+        // interior warps: tap k of the pair is own + (k - C) * stride, formed where it is used -- held as five addresses
+        // they were spilled (four LDL per step, long-scoreboard stalls); the volatile asm keeps ptxas from hoisting them
+        auto tap_addr = [&](int m) -> uint32_t {
+            if (m == 0) return own;
+            uint32_t a;
+            if (m == 1) asm volatile("add.u32 %0, %1, %2;" : "=r"(a) : "r"(own), "r"(tstep));
+            else if (m == -1) asm volatile("sub.u32 %0, %1, %2;" : "=r"(a) : "r"(own), "r"(tstep));
+            else if (m == 2) asm volatile("mad.lo.u32 %0, %2, 2, %1;" : "=r"(a) : "r"(own), "r"(tstep));
+            else asm volatile("{.reg .u32 t; shl.b32 t, %2, 1; sub.u32 %0, %1, t;}" : "=r"(a) : "r"(own), "r"(tstep));
+            return a;
+        };
         auto step = [&](auto ic, const int j, const uint32_t parity) {
             constexpr int I = decltype(ic)::value;
             constexpr int WS = I % TAPS;
             if (j >= n_load) return;
             mbar_wait_imm<FULL_OFF + 8 * I>(sbase, parity);
-            if constexpr (DMODE == 0) {
+            if constexpr (DMODE == 0 && !MIRROR && LD >= 0) {
+                lean_load_taps<TAPS, I * RB, (LD >= 0 ? LD : 0)>(own, X[WS], std::make_integer_sequence<int, TAPS>{});
+            } else if constexpr (DMODE == 0) {
 #pragma unroll
                 for (int k = 0; k < TAPS; ++k) {
-                    u64 t = lds64_imm<I * RB>(MIRROR ? colb[k] : own + (uint32_t)(k - C) * tstep);
+                    u64 t = lds64_imm<I * RB>(MIRROR ? colb[k] : tap_addr(k - C));
                     if (MIRROR) {
                         const u64 u = swap2(t);
                         t = ((rev >> k) & 1u) ? u : t;
@@ -1049,7 +1072,7 @@ __global__ void __launch_bounds__(288, 2) bilateral_lean_kernel(const BilateralP
                 float win[6];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    u64 t = lds64_imm<I * RB>(MIRROR ? colb[k] : own + (uint32_t)(k - 1) * tstep);
+                    u64 t = lds64_imm<I * RB>(MIRROR ? colb[k] : tap_addr(k - 1));
                     if (MIRROR) {
                         const u64 u = swap2(t);
                         t = ((rev >> k) & 1u) ? u : t;
@@ -1491,9 +1514,9 @@ static int launch_bilateral_window(const BilateralParams &bp, int batch, cudaStr
     return launch_pdl<BilateralParams>(kern, grid, dim3(WindowGeom<WG>::THREADS), smem, st, bq);
 }
 
-template <int TAPS, int DMODE>
+template <int TAPS, int DMODE, int LD = -1>
 static int launch_bilateral_lean(const BilateralParams &bp, int batch, cudaStream_t st) {
-    auto kern = bilateral_lean_kernel<TAPS, DMODE>;
+    auto kern = bilateral_lean_kernel<TAPS, DMODE, LD>;
     const ScaleParams &p = bp.sp;
     const size_t smem = (size_t)K2LeanRing<TAPS>::R * kK2LeanRB + 16 * (size_t)K2LeanRing<TAPS>::R;
     static bool configured[64] = {};
@@ -1518,7 +1541,24 @@ template <int TAPS, int DMODE>
 static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStream_t st) {
     int wm = k2_mode_for(TAPS, bp.sp.d);
     if (wm == 2) {
-        if (k2_lean_ok(bp.sp)) return launch_bilateral_lean<TAPS, DMODE>(bp, batch, st);
+        if (k2_lean_ok(bp.sp)) {
+            if constexpr (TAPS == 5 && DMODE == 0) {
+                // the B3spline scales of a dyadic cascade: dilation as a template parameter (immediate tap offsets)
+                switch (bp.sp.d) {
+                    case 2: return launch_bilateral_lean<TAPS, DMODE, 1>(bp, batch, st);
+                    case 4: return launch_bilateral_lean<TAPS, DMODE, 2>(bp, batch, st);
+                    case 8: return launch_bilateral_lean<TAPS, DMODE, 3>(bp, batch, st);
+                    case 16: return launch_bilateral_lean<TAPS, DMODE, 4>(bp, batch, st);
+                    case 32: return launch_bilateral_lean<TAPS, DMODE, 5>(bp, batch, st);
+                    case 64: return launch_bilateral_lean<TAPS, DMODE, 6>(bp, batch, st);
+                    case 128: return launch_bilateral_lean<TAPS, DMODE, 7>(bp, batch, st);
+                    case 256: return launch_bilateral_lean<TAPS, DMODE, 8>(bp, batch, st);
+                    case 512: return launch_bilateral_lean<TAPS, DMODE, 9>(bp, batch, st);
+                    default: break;
+                }
+            }
+            return launch_bilateral_lean<TAPS, DMODE>(bp, batch, st);
+        }
         wm = 1;
     }
     if (wm == 1) return launch_bilateral_window<TAPS, DMODE>(bp, batch, st);
