@@ -566,8 +566,10 @@ def run_ours(args):
             line["wow_bilateral"] = time_wow(wb, solar, 15, peak, bilateral=1, denoise_coefficients=[5, 2])
             line["wow"]["call"] = "wow(4096x4096 fp32 solar-like)"
             line["wow_bilateral"]["call"] = "wow(4096x4096 fp32 solar-like, bilateral=1, denoise_coefficients=[5, 2])"
-            line["wow_bilateral"]["bound"] = ("MUFU pipe: 24 exponentials per pixel per scale = 87 us per 4096^2 scale at "
-                                              "16 MUFU/clk/SM, against 31 us of HBM time")
+            line["wow_bilateral"]["bound"] = ("instruction issue + MUFU pipe, not HBM: the bilateral scale kernel needs 162 packed "
+                                              "fp32x2 operations (two issue cycles each) and 52 MUFU per 64 pixels; its arithmetic "
+                                              "alone replayed on the same SM (tools/k2mimic.cu) takes 114 us per 4096^2 scale, "
+                                              "the kernel 135-156 us, against 31 us of HBM time for its 3 planes")
             solar64 = solar.to(torch.float64)
             line["wow_f64"] = time_wow(wb, solar64, 10, peak)
             line["wow_bilateral_f64"] = time_wow(wb, solar64, 4, peak, bilateral=1, denoise_coefficients=[5, 2])
