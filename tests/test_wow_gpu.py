@@ -240,6 +240,32 @@ def test_wow_batch_matches_single_frames():
     assert np.array_equal(rb[0].cpu().numpy(), r0)
 
 
+def test_wow_stream_of_host_frames_matches_per_frame_calls():
+    """wow_stream(): host frames in, host reconstructions out on three streams with one set of device buffers per frame
+    in flight; every frame must equal wow(frame)[0] bit for bit, for the fused options (planned once), for the options
+    that fall back to wow() per frame (h > 0), for NumPy and pinned inputs, and across repeated calls (buffer reuse)."""
+    import wavelets_b200 as wb
+    frames = np.stack([orc.solar_like(256, seed=s, flux=0.05, dtype=np.float32) for s in range(5)])
+    for kw in ({}, {"denoise_coefficients": [5, 2]}, {"bilateral": 1, "denoise_coefficients": [5, 2]},
+               {"weights": [0.5, 2], "whitening": False}, {"h": 0.5, "denoise_coefficients": [3, 1]}):
+        out = wb.wow_stream(frames, **kw)
+        assert isinstance(out, np.ndarray) and out.shape == frames.shape and out.dtype == np.float32
+        for i in range(len(frames)):
+            r, _ = wb.wow(frames[i], **kw)
+            assert np.array_equal(out[i], r), (kw, i)
+    pinned = torch.from_numpy(frames.astype(np.float64)).pin_memory()
+    res = torch.empty_like(pinned).pin_memory()
+    got = wb.wow_stream(pinned, out=res, depth=3, scaling_function=wb.Triangle, noise=0.01, denoise_coefficients=[4])
+    assert got is res
+    for i in range(len(frames)):
+        r, _ = wb.wow(pinned[i].cuda(), scaling_function=wb.Triangle, noise=0.01, denoise_coefficients=[4])
+        assert torch.equal(res[i], r.cpu())
+    with pytest.raises(TypeError):
+        wb.wow_stream(frames, no_such_option=1)
+    with pytest.raises(ValueError):
+        wb.wow_stream(frames[0])
+
+
 @pytest.mark.parametrize("sf", ["b3spline", "triangle"])
 def test_noise_weights(sf):
     import wavelets_b200 as wb

@@ -37,6 +37,19 @@ def _side_stream(device):
     return st
 
 
+_PIPELINE_STREAMS: dict = {}
+
+
+def _pipeline_streams(device):
+    """The (upload, compute, download) streams of the host-frame pipelines, created once per device: the caching
+    allocator keeps one pool per stream, so fresh streams per call would start every call with cudaMalloc."""
+    key = (device.type, device.index)
+    st = _PIPELINE_STREAMS.get(key)
+    if st is None:
+        st = _PIPELINE_STREAMS[key] = tuple(torch.cuda.Stream(device) for _ in range(3))
+    return st
+
+
 def generalized_anscombe(signal, alpha=1, g=0, sigma=0, inverse=False):
     """Variance-stabilising transform and its algebraic inverse (watroo/wavelets.py:14-21), element-wise on a torch
     tensor (device or host)."""
@@ -147,8 +160,12 @@ def _scalar_noise(noise, device):
 
 
 def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilateral, bilateral_scaling, whitening,
-               soft_threshold, noise):
+               soft_threshold, noise, buffers=None):
     """The fused WOW pipeline on a stack (B, H, W) of frames.  Returns (recon (B,H,W), planes (B,L+1,H,W), noise).
+
+    ``buffers``: optional dict of preallocated device tensors ("planes", "scratch", "raw_planes", "recon"), filled in
+    on first use and reused by later calls with the same geometry (``wow_stream`` keeps one per frame in flight, so
+    that its steady state allocates nothing large).
 
     Per plain scale ONE fused launch (wb_wow_scale: smooth, detail, local power, significance, whitening; the raw
     detail plane never exists in HBM).  Bilateral scales, and scale 0 when the MAD noise must first be estimated from
@@ -160,14 +177,23 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
     b, h, w = stack.shape
     dev, dt = stack.device, stack.dtype
     L = n_scales
-    planes = torch.empty((b, L + 1, h, w), dtype=dt, device=dev)
+    if buffers is None:
+        buffers = {}
+
+    def buffer(name, shape):
+        t = buffers.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dt or t.device != dev:
+            t = buffers[name] = torch.empty(shape, dtype=dt, device=dev)
+        return t
+
+    planes = buffer("planes", (b, L + 1, h, w))
     bilateral = sigma_bilateral
     sigma_e = sf.sigma_e(bilateral=bilateral)
     transform = AtrousTransform(scaling_function_class, bilateral=bilateral, bilateral_scaling=bilateral_scaling)
     factors = transform.var_factors(L) if bilateral is not None else [None] * L
     if L == 0:
         planes[:, 0].copy_(stack)
-    scratch = torch.empty((2, b, h, w), dtype=dt, device=dev) if L > 1 else None
+    scratch = buffer("scratch", (2, b, h, w)) if L > 1 else None
     raw_planes = None  # scratch for the raw w_s of the two-pass route, allocated on first use
     nz = noise  # _Noise or None
     src = stack
@@ -197,7 +223,7 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
                                  nz if need_sig else _Noise(), wt)
             if not fused:
                 if raw_planes is None:
-                    raw_planes = torch.empty((3 if overlap else 1, b, h, w), dtype=dt, device=dev)
+                    raw_planes = buffer("raw_planes", (3 if overlap else 1, b, h, w))
                 raw_plane = raw_planes[s % 3] if overlap else raw_planes[0]
                 if overlap and ev_k3[s % 3] is not None:
                     main.wait_event(ev_k3[s % 3])  # the whitening that read this raw plane three scales ago is done
@@ -236,7 +262,7 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
                                                mom.data_ptr(), float(wts[L]), _lib.stream_ptr(dev)))
     elif wts[L] != 1:
         last.mul_(wts[L])
-    recon = synthesis(planes)
+    recon = synthesis(planes, out=buffer("recon", (b, h, w)))
     return recon, planes, nz
 
 
@@ -390,12 +416,32 @@ def wow_stream(frames, out=None, depth=2, scaling_function=B3spline, **kwargs):
     _lib.load(require_cuda=True)
     dev = torch.device("cuda", torch.cuda.current_device())
     depth = max(1, min(int(depth), n))
-    s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    s_in, s_cmp, s_out = _pipeline_streams(dev)
     caller = torch.cuda.current_stream(dev)
     for st in (s_in, s_cmp, s_out):
         st.wait_stream(caller)
+    # The options of the fused pipeline are planned ONCE and every frame in flight owns one set of device buffers
+    # (planes, ping-pong scratch, reconstruction): after the first `depth` frames nothing large is allocated -- with
+    # wow() called per frame the caching allocator split and re-grew its blocks while the host ran ahead of the device
+    # (a cudaMalloc of 0.7 GB per frame: 25 ms instead of 1.3).  h > 0, preserve_variance and per-pixel noise maps take
+    # wow() itself, frame by frame.
+    opts = dict(kwargs)
+    unknown = set(opts) - {"n_scales", "weights", "whitening", "denoise_coefficients", "noise", "bilateral",
+                           "bilateral_scaling", "soft_threshold", "preserve_variance", "gamma", "gamma_min", "gamma_max", "h"}
+    if unknown:
+        raise TypeError(f"wow_stream() got unexpected keyword arguments {sorted(unknown)}")
+    plan = None
+    if opts.get("h", 0) == 0 and not opts.get("preserve_variance", False):
+        nz0 = _scalar_noise(opts.get("noise"), dev)
+        if not (isinstance(nz0, str) and nz0 == "map"):
+            n_scales, sigma_bilateral, wts, dns = _wow_plan((h, w), scaling_function, opts.get("n_scales"),
+                                                            opts.get("weights", []), opts.get("denoise_coefficients", []),
+                                                            opts.get("bilateral"), h=0)
+            plan = (n_scales, wts, dns, sigma_bilateral, opts.get("bilateral_scaling", False),
+                    opts.get("whitening", True), opts.get("soft_threshold", True), nz0)
     d_in = [torch.empty((h, w), dtype=host.dtype, device=dev) for _ in range(depth)]
     d_out = [None] * depth
+    bufs = [dict() for _ in range(depth)]
     ev_in = [torch.cuda.Event() for _ in range(depth)]
     ev_cmp = [torch.cuda.Event() for _ in range(depth)]
     ev_out = [torch.cuda.Event() for _ in range(depth)]
@@ -409,13 +455,20 @@ def wow_stream(frames, out=None, depth=2, scaling_function=B3spline, **kwargs):
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[b])
             if i >= depth:
-                s_cmp.wait_event(ev_out[b])      # the download of d_out[b] is done (its memory may be reused)
-            d_out[b], _ = wow(d_in[b], scaling_function=scaling_function, **kwargs)
+                s_cmp.wait_event(ev_out[b])      # the download of d_out[b] is done (its memory is reused)
+            if plan is not None:
+                L, wts, dns, sigma_bilateral, bil_scaling, whitening, soft, nz0 = plan
+                recon, _, _ = _wow_stack(d_in[b].unsqueeze(0), scaling_function, L, wts, dns, sigma_bilateral,
+                                         bil_scaling, whitening, soft, nz0, buffers=bufs[b])
+                d_out[b] = recon[0]
+            else:
+                d_out[b], _ = wow(d_in[b], scaling_function=scaling_function, **kwargs)
             ev_cmp[b].record(s_cmp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_cmp[b])
             dst[i].copy_(d_out[b], non_blocking=True)
-            d_out[b].record_stream(s_out)
+            if plan is None:
+                d_out[b].record_stream(s_out)
             ev_out[b].record(s_out)
     for st in (s_in, s_cmp, s_out):
         caller.wait_stream(st)

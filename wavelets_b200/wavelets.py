@@ -210,20 +210,24 @@ def plane_moments(planes):
     return out
 
 
-def synthesis(planes):
+def synthesis(planes, out=None):
     """``np.sum(planes, axis=0)`` in plane order and plane dtype, on the device.  (N,H,W) -> (H,W); (B,N,H,W) ->
-    (B,H,W)."""
+    (B,H,W).  ``out``: optional contiguous device tensor of that shape and dtype to write into."""
     lib = _lib.load(require_cuda=True)
     if not planes.is_contiguous():
         planes = planes.contiguous()
     if planes.ndim == 3:
         n, h, w = planes.shape
         b, in_bs = 1, 0
-        out = torch.empty((h, w), dtype=planes.dtype, device=planes.device)
+        shape = (h, w)
     else:
         b, n, h, w = planes.shape
         in_bs = n * h * w
-        out = torch.empty((b, h, w), dtype=planes.dtype, device=planes.device)
+        shape = (b, h, w)
+    if out is None:
+        out = torch.empty(shape, dtype=planes.dtype, device=planes.device)
+    elif tuple(out.shape) != shape or out.dtype != planes.dtype or out.device != planes.device or not out.is_contiguous():
+        raise ValueError("synthesis(): out must be a contiguous device tensor of the summed shape and the plane dtype")
     with torch.cuda.device(planes.device):
         _lib.check(lib.wb_synthesis(planes.data_ptr(), n, h * w, h * w, b, in_bs, out.data_ptr(), h * w,
                                     _lib.dtype_code(planes.dtype), _lib.stream_ptr(planes.device)))
