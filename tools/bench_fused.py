@@ -1,0 +1,44 @@
+"""Per-scale launch time of the fused WOW scale kernel and of wow() itself (GPU box only; A/B runs set the WB_WOW_*
+environment switches of csrc/wow_scale.cu before the process starts).
+
+    python tools/bench_fused.py [--side 4096] [--reps 30] [--tag name]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import wavelets_b200 as wb  # noqa: E402
+from wavelets_b200 import _lib, utils  # noqa: E402
+from tools.bench_wow import solar_like_device, timed  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--side", type=int, default=4096)
+    ap.add_argument("--reps", type=int, default=30)
+    ap.add_argument("--tag", default="")
+    args = ap.parse_args()
+    lib = _lib.load(require_cuda=True)
+    n = args.side
+    img = solar_like_device(n, torch.float32)
+    sf = wb.B3spline(2)
+    src = img.unsqueeze(0)
+    c = torch.empty_like(src)
+    o = torch.empty_like(src)
+    nz = utils._Noise(dev=torch.tensor([1.0], dtype=torch.float64, device="cuda"))
+    res = {"tag": args.tag, "side": n, "env": {k: v for k, v in os.environ.items() if k.startswith("WB_")}}
+    res["fused_us"] = [round(1e3 * timed(lambda: utils._wow_scale_fused(lib, src, c, o, s, sf, 0, 0.0, 1.0, utils._Noise(), 1.0),
+                                         args.reps), 2) for s in range(10)]
+    res["fused_soft_us"] = [round(1e3 * timed(lambda: utils._wow_scale_fused(lib, src, c, o, s, sf, 1, 5.0, 0.2, nz, 1.0),
+                                              args.reps), 2) for s in range(10)]
+    res["wow_ms"] = round(timed(lambda: wb.wow(img), args.reps), 4)
+    res["wow_den_ms"] = round(timed(lambda: wb.wow(img, denoise_coefficients=[5, 2], noise=1.0), args.reps), 4)
+    print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

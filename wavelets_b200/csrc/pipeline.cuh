@@ -416,6 +416,37 @@ __device__ __forceinline__ P4 lean_row_pass(const uint32_t (&a)[PlanSize<TAPS, D
     return acc;
 }
 
+// Row pass of a PAIR of vectors one dilation step apart (columns x and x + d, d % 4 == 0): their taps x + (k - C) d,
+// k = 0 .. TAPS, overlap in all but one vector each, so TAPS + 1 LDS.128 (and squarings) serve two outputs instead of
+// 2 TAPS -- the fused WOW kernel is limited by shared-memory wavefronts and LDS latency, not by arithmetic.  Every
+// output sums the same values in the same order as lean_row_pass: bit-identical planes.
+template <int TAPS, int OFF, bool SQUARE, bool MIRROR>
+__device__ __forceinline__ void lean_row_pass_pair(const uint32_t (&a)[TAPS + 1], unsigned rev, const PackedTaps<TAPS> &H,
+                                                   P4 &o0, P4 &o1) {
+    P4 t[TAPS + 1];
+#pragma unroll
+    for (int k = 0; k <= TAPS; ++k) {
+        t[k] = lds_p4_imm<OFF>(a[k]);
+        if constexpr (MIRROR) {
+            const bool m = (rev >> k) & 1u;
+            const P4 u = reverse_p4(t[k]);
+            t[k].lo = m ? u.lo : t[k].lo;
+            t[k].hi = m ? u.hi : t[k].hi;
+        }
+        if constexpr (SQUARE) {
+            t[k].lo = mul2(t[k].lo, t[k].lo);
+            t[k].hi = mul2(t[k].hi, t[k].hi);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TAPS; ++k) {
+        o0.lo = (k == 0) ? mul2(H.h[0], t[k].lo) : fma2(H.h[k], t[k].lo, o0.lo);
+        o0.hi = (k == 0) ? mul2(H.h[0], t[k].hi) : fma2(H.h[k], t[k].hi, o0.hi);
+        o1.lo = (k == 0) ? mul2(H.h[0], t[k + 1].lo) : fma2(H.h[k], t[k + 1].lo, o1.lo);
+        o1.hi = (k == 0) ? mul2(H.h[0], t[k + 1].hi) : fma2(H.h[k], t[k + 1].hi, o1.hi);
+    }
+}
+
 template <int I> struct IC { static constexpr int value = I; };
 
 // A value ptxas may not rematerialise: under register pressure it otherwise recomputes the reflected tap offsets

@@ -225,8 +225,13 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
 // ---------------------------------------------------------------------------------------------------------------
 // MODE: significance compiled into the epilogue (0 none, 1 soft, 2 hard); the step loop is small enough to stay in
 // the instruction cache only without the inlined erff of the modes that are not used.
-template <int TAPS, int DMODE, bool HINTS, int MODE>
+// PAIR (DMODE 0, d >= 32): a thread's two column vectors are one dilation step apart (x and x + d) instead of half a row
+// apart, so both row passes load TAPS + 1 tap vectors for the two of them instead of 2 TAPS (lean_row_pass_pair): 18
+// instead of 26 LDS/STS.128 per thread and step.  Vector v0 = (tid / dv) 2 dv + tid % dv with dv = d / 4 >= 8: eight
+// consecutive lanes still read eight consecutive vectors (conflict-free), a warp stores runs of >= 128 contiguous bytes.
+template <int TAPS, int DMODE, bool HINTS, int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams p) {
+    static_assert(!PAIR || DMODE == 0, "paired columns need d % 4 == 0");
     using T = float;
     constexpr int V = 4, NG = 2, NT = 512;
     constexpr int C = TAPS / 2;
@@ -292,35 +297,69 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
     const PackedTaps<TAPS> H;
 
     // per-thread addresses inside ring slot 0: own vector and taps, for both column groups
-    uint32_t own[NG], tap[NG][NV];
-    unsigned rev[NG];
+    constexpr int NTAP = PAIR ? 1 : NG, NPT = PAIR ? TAPS + 1 : 1;
+    uint32_t own[NG], tap[NTAP][NV], ptap[NPT];
+    unsigned rev[NG] = {0u, 0u};
     bool act[NG];
     int xg0 = 0;
-#pragma unroll
-    for (int q = 0; q < NG; ++q) {
-        int xg = (q * NT + tid) * V;
-        act[q] = xg < p.W;
-        // idle threads shadow a vector in the middle of the row (interior unless the dilation is huge); only their
-        // stores are masked
-        if (!act[q]) xg = (p.W / 2) & ~(V - 1);
-        if (q == 0) xg0 = xg;
-        own[q] = opaque_u32(in_base + (uint32_t)xg * (uint32_t)sizeof(T));
-        const TapPlan<NV> tp = make_tap_plan<V, NV>(xg, DMODE == 0 ? p.d : V, p.W, 0);
-#pragma unroll
-        for (int k = 0; k < NV; ++k) tap[q][k] = in_base + (uint32_t)tp.off[k] * (uint32_t)sizeof(T);
-        rev[q] = tp.rev;
-    }
-    const bool mirror_warp = __any_sync(0xffffffffu, (rev[0] | rev[1]) != 0);
-    if (mirror_warp) {
-#pragma unroll
-        for (int q = 0; q < NG; ++q) {
-#pragma unroll
-            for (int k = 0; k < NV; ++k) tap[q][k] = opaque_u32(tap[q][k]);
-            rev[q] = opaque_u32(rev[q]);
-        }
-    }
     // interior warps: tap k of a vector is its own address + (k - NV/2) * step bytes (nothing to hold per tap)
     const uint32_t tap_step = (uint32_t)(DMODE == 0 ? p.d : V) * (uint32_t)sizeof(T);
+    bool mirror_warp;
+    if constexpr (PAIR) {
+        const int dv = p.d >> 2, nvec = p.W >> 2;  // vectors per dilation step (a power of two >= 8), vectors per row
+        const int v0 = (tid / dv) * 2 * dv + (tid & (dv - 1));
+        act[0] = v0 < nvec;
+        act[1] = v0 + dv < nvec;
+        xg0 = act[0] ? v0 * V : 0;  // idle threads shadow the first pair of the row; only their stores are masked
+        own[0] = opaque_u32(in_base + (uint32_t)xg0 * (uint32_t)sizeof(T));
+        own[1] = opaque_u32(act[1] ? own[0] + tap_step : own[0]);
+        unsigned rv = 0;
+#pragma unroll
+        for (int k = 0; k <= TAPS; ++k) {
+            const int pc = xg0 + (k - C) * p.d;  // columns of tap k of the first vector = tap k - 1 of the second
+            const bool left = pc < 0, right = pc >= p.W;
+            int q = left ? (-V - pc) : (right ? (2 * p.W - V - pc) : pc);
+            if (q < 0 || q > p.W - V) q = 0;  // only taps of a masked second vector can land here
+            ptap[k] = in_base + (uint32_t)q * (uint32_t)sizeof(T);
+            if (left || right) rv |= 1u << k;
+        }
+        rev[0] = rv;
+        mirror_warp = __any_sync(0xffffffffu, rv != 0 || !act[0]);
+        if (mirror_warp) {
+#pragma unroll
+            for (int k = 0; k <= TAPS; ++k) ptap[k] = opaque_u32(ptap[k]);
+            rev[0] = opaque_u32(rev[0]);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+            int xg = (q * NT + tid) * V;
+            act[q] = xg < p.W;
+            // idle threads shadow a vector in the middle of the row (interior unless the dilation is huge); only their
+            // stores are masked
+            if (!act[q]) xg = (p.W / 2) & ~(V - 1);
+            if (q == 0) xg0 = xg;
+            own[q] = opaque_u32(in_base + (uint32_t)xg * (uint32_t)sizeof(T));
+            const TapPlan<NV> tp = make_tap_plan<V, NV>(xg, DMODE == 0 ? p.d : V, p.W, 0);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) tap[q][k] = in_base + (uint32_t)tp.off[k] * (uint32_t)sizeof(T);
+            rev[q] = tp.rev;
+        }
+        mirror_warp = __any_sync(0xffffffffu, (rev[0] | rev[1]) != 0);
+        if (mirror_warp) {
+#pragma unroll
+            for (int q = 0; q < NG; ++q) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) tap[q][k] = opaque_u32(tap[q][k]);
+                rev[q] = opaque_u32(rev[q]);
+            }
+        }
+    }
+    // the second column vector of a thread: one dilation step (PAIR) or half a ring slot (NT vectors) further
+    auto q_off = [&](int q) -> long long {
+        if constexpr (PAIR) return q ? (long long)p.d : 0LL;
+        else return (long long)q * (NT * V);
+    };
 
     u64 SA[NG][2][TAPS - 1], SB[NG][2][TAPS - 1];  // running column sums, one pixel pair per entry
 #pragma unroll
@@ -359,15 +398,28 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
 #pragma unroll
             for (int q = 0; q < NG; ++q) rawc[q] = lds_p4_imm<SC * RB>(own[q] + (other_half ? half_c : half));
             P4 cv[NG];
+            if constexpr (PAIR) {
+                uint32_t a[TAPS + 1];
 #pragma unroll
-            for (int q = 0; q < NG; ++q) {
-                uint32_t a[NV];
+                for (int k = 0; k <= TAPS; ++k) a[k] = (MIRROR ? ptap[k] : own[0] + (uint32_t)(k - C) * tap_step) + half;
+                P4 v[NG];
+                lean_row_pass_pair<TAPS, I * RB, false, MIRROR>(a, rev[0], H, v[0], v[1]);
 #pragma unroll
-                for (int k = 0; k < NV; ++k)
-                    a[k] = (MIRROR ? tap[q][k] : own[q] + (uint32_t)(k - NV / 2) * tap_step) + half;
-                const P4 v = lean_row_pass<TAPS, DMODE, I * RB, false, MIRROR>(a, rev[q], H);
-                cv[q].lo = col_feed_p<TAPS>(SA[q][0], v.lo, H);
-                cv[q].hi = col_feed_p<TAPS>(SA[q][1], v.hi, H);
+                for (int q = 0; q < NG; ++q) {
+                    cv[q].lo = col_feed_p<TAPS>(SA[q][0], v[q].lo, H);
+                    cv[q].hi = col_feed_p<TAPS>(SA[q][1], v[q].hi, H);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < NG; ++q) {
+                    uint32_t a[NV];
+#pragma unroll
+                    for (int k = 0; k < NV; ++k)
+                        a[k] = (MIRROR ? tap[q][k] : own[q] + (uint32_t)(k - NV / 2) * tap_step) + half;
+                    const P4 v = lean_row_pass<TAPS, DMODE, I * RB, false, MIRROR>(a, rev[q], H);
+                    cv[q].lo = col_feed_p<TAPS>(SA[q][0], v.lo, H);
+                    cv[q].hi = col_feed_p<TAPS>(SA[q][1], v.hi, H);
+                }
             }
             if (j >= 2 * C) {
                 constexpr int SW = (I - 2 * C + 8) & (kWRing - 1);  // w row j-2C
@@ -375,8 +427,8 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
                     if (store_c && act[q]) {
-                        if (HINTS) stg_p4_hint(c_ptr + q * (NT * V), cv[q], pol_keep);
-                        else stg_p4(c_ptr + q * (NT * V), cv[q]);
+                        if (HINTS) stg_p4_hint(c_ptr + q_off(q), cv[q], pol_keep);
+                        else stg_p4(c_ptr + q_off(q), cv[q]);
                     }
                     P4 raw = rawc[q];
                     raw.lo = sub2(raw.lo, cv[q].lo);
@@ -400,14 +452,27 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
 #pragma unroll
             for (int q = 0; q < NG; ++q) roww[q] = lds_p4_imm<W_OFF + SE * RB>(own[q]);
             P4 pw[NG];
+            if constexpr (PAIR) {
+                uint32_t a[TAPS + 1];
 #pragma unroll
-            for (int q = 0; q < NG; ++q) {
-                uint32_t a[NV];
+                for (int k = 0; k <= TAPS; ++k) a[k] = MIRROR ? ptap[k] : own[0] + (uint32_t)(k - C) * tap_step;
+                P4 v[NG];
+                lean_row_pass_pair<TAPS, W_OFF + SP * RB, true, MIRROR>(a, rev[0], H, v[0], v[1]);
 #pragma unroll
-                for (int k = 0; k < NV; ++k) a[k] = MIRROR ? tap[q][k] : own[q] + (uint32_t)(k - NV / 2) * tap_step;
-                const P4 v = lean_row_pass<TAPS, DMODE, W_OFF + SP * RB, true, MIRROR>(a, rev[q], H);
-                pw[q].lo = col_feed_p<TAPS>(SB[q][0], v.lo, H);
-                pw[q].hi = col_feed_p<TAPS>(SB[q][1], v.hi, H);
+                for (int q = 0; q < NG; ++q) {
+                    pw[q].lo = col_feed_p<TAPS>(SB[q][0], v[q].lo, H);
+                    pw[q].hi = col_feed_p<TAPS>(SB[q][1], v[q].hi, H);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < NG; ++q) {
+                    uint32_t a[NV];
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) a[k] = MIRROR ? tap[q][k] : own[q] + (uint32_t)(k - NV / 2) * tap_step;
+                    const P4 v = lean_row_pass<TAPS, DMODE, W_OFF + SP * RB, true, MIRROR>(a, rev[q], H);
+                    pw[q].lo = col_feed_p<TAPS>(SB[q][0], v.lo, H);
+                    pw[q].hi = col_feed_p<TAPS>(SB[q][1], v.hi, H);
+                }
             }
             if (j > 4 * C) {
 #pragma unroll
@@ -415,7 +480,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
                     P4 raw = roww[q];
                     raw.lo = epi.template apply2<MODE>(raw.lo, pw[q].lo);
                     raw.hi = epi.template apply2<MODE>(raw.hi, pw[q].hi);
-                    if (act[q]) stg_p4_cs(o_ptr + q * (NT * V), raw);
+                    if (act[q]) stg_p4_cs(o_ptr + q_off(q), raw);
                 }
                 o_ptr += o_step;
             }
@@ -520,9 +585,25 @@ static bool wow_packed_enabled() {
     return v != 0;
 }
 
+// WB_WOW_PAIR=0 in the environment keeps the half-row column groups at every dilation (A/B measurements).
+static bool wow_pair_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("WB_WOW_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 template <typename T, int TAPS, int DMODE, bool HINTS>
-static auto wow_kernel_for(bool packed, int sig_mode) -> void (*)(const ScaleParams) {
+static auto wow_kernel_for(bool packed, bool pair, int sig_mode) -> void (*)(const ScaleParams) {
     if constexpr (sizeof(T) == 4) {
+        if constexpr (DMODE == 0) {
+            if (packed && pair)
+                return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 0, true>
+                                     : (sig_mode == 1 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 1, true>
+                                                      : wow_rows_lean_kernel<TAPS, DMODE, HINTS, 2, true>);
+        }
         if (packed)
             return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 0>
                                  : (sig_mode == 1 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 1>
@@ -535,11 +616,14 @@ template <typename T, int TAPS, int DMODE, bool HINTS>
 static int launch_wow_h(const ScaleParams &p, int batch, const WowGeom &geo, cudaStream_t st) {
     // the lean kernel always runs 512 threads x 2 vectors on 16 KiB ring slots: use it when the row needs them
     const bool packed = sizeof(T) == 4 && p.W > 2048 && p.n_strips == 1 && wow_packed_enabled();
-    auto kern = wow_kernel_for<T, TAPS, DMODE, HINTS>(packed, p.sig_mode);
+    // paired columns (x, x + d) from d = 32 on: below that eight consecutive lanes would not read eight consecutive
+    // vectors (shared-memory bank conflicts eat the saved loads)
+    const bool pair = packed && DMODE == 0 && p.d >= 32 && (p.d & (p.d - 1)) == 0 && wow_pair_enabled();
+    auto kern = wow_kernel_for<T, TAPS, DMODE, HINTS>(packed, pair, p.sig_mode);
     const int nt = packed ? 512 : geo.nt;
     const size_t smem = packed ? (size_t)(kInRing + kWRing) * kLeanRB + 8 * (size_t)(kInRing + kWRing) : geo.smem;
-    static bool configured[4][64] = {};  // generic, lean x 3 significance modes; per device
-    const int kidx = packed ? 1 + p.sig_mode : 0;
+    static bool configured[7][64] = {};  // generic, lean x 3 significance modes, paired lean x 3; per device
+    const int kidx = packed ? 1 + p.sig_mode + (pair ? 3 : 0) : 0;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[kidx][dev]) {
