@@ -35,6 +35,21 @@ def main():
                                          args.reps), 2) for s in range(10)]
     res["fused_soft_us"] = [round(1e3 * timed(lambda: utils._wow_scale_fused(lib, src, c, o, s, sf, 1, 5.0, 0.2, nz, 1.0),
                                               args.reps), 2) for s in range(10)]
+    from wavelets_b200.wavelets import atrous_scale
+    w = torch.empty_like(src)
+    res["k1_us"] = [round(1e3 * timed(lambda: atrous_scale(src, s, sf, out_c=c, out_w=w), args.reps), 2) for s in range(10)]
+    res["k3_us"] = [round(1e3 * timed(lambda: utils._whiten_scale(lib, w, o, s, sf, 0, 0.0, 1.0, utils._Noise(), 1.0), args.reps), 2)
+                    for s in range(10)]
+    # kernel-switch cost: the same launches back to back, grouped by kernel (s4 x4, s5 x4) and alternating (s4, s5) x4
+    def seq(order):
+        for s in order:
+            atrous_scale(src, s, sf, out_c=c, out_w=w)
+    res["switch_us"] = {"grouped_4_5": round(1e3 * timed(lambda: seq([4] * 4 + [5] * 4), args.reps) / 8, 2),
+                        "alternating_4_5": round(1e3 * timed(lambda: seq([4, 5] * 4), args.reps) / 8, 2),
+                        "grouped_0_1_4_5": round(1e3 * timed(lambda: seq([0] * 2 + [1] * 2 + [4] * 2 + [5] * 2), args.reps) / 8, 2),
+                        "alternating_0_1_4_5": round(1e3 * timed(lambda: seq([0, 1, 4, 5] * 2), args.reps) / 8, 2)}
+    tr = wb.AtrousTransform(wb.B3spline)
+    res["transform_ms"] = round(timed(lambda: tr(img, 10), 100), 4)
     res["wow_ms"] = round(timed(lambda: wb.wow(img), args.reps), 4)
     res["wow_den_ms"] = round(timed(lambda: wb.wow(img, denoise_coefficients=[5, 2], noise=1.0), args.reps), 4)
     print(json.dumps(res), flush=True)

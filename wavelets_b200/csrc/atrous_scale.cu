@@ -199,8 +199,11 @@ static constexpr int kLeanSlots = 8;
 
 // OP_WHITEN (K3 of the two-pass WOW routes, MODE = significance compiled into the epilogue): the row pass filters the
 // SQUARES of the staged raw w_s rows and the epilogue whitens the raw centre value -- same pipeline, 2*T bytes per pixel.
-template <int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0>
+// PAIR = M > 0 (DMODE 0, d >= 8): a thread's two column vectors are M dilation steps apart (x, x + M d) and share
+// TAPS - M of their tap vectors (lean_row_pass_pair, see wow_rows_lean_kernel): 8 instead of 12 LDS.128 per step at M = 1.
+template <int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0, int PAIR = 0>
 __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams p) {
+    static_assert(PAIR == 0 || (DMODE == 0 && PAIR < TAPS), "paired columns need d % 4 == 0 and overlapping taps");
     using T = float;
     constexpr int V = 4, NG = 2;
     constexpr int C = TAPS / 2;
@@ -265,24 +268,41 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
     WhitenEpilogue<T> epi;
     if constexpr (OP == OP_WHITEN) epi.init(p, frame);
 
-    uint32_t own[NG], tap[NG][NV];
-    unsigned rev[NG];
+    constexpr int NTAP = PAIR ? 1 : NG, NPT = TAPS + PAIR;
+    uint32_t own[NG], tap[NTAP][NV], ptap[NPT];
+    unsigned rev[NG] = {0u, 0u};
     bool act[NG];
     int xg0 = 0;
+    bool mirror_warp;
+    if constexpr (PAIR) {
+        const int run = PAIR * (p.d >> 2), nvec = p.W >> 2;  // vectors between the two of a pair (>= 8), vectors per row
+        const int v0 = pair_first_vector(tid, run);
+        act[0] = v0 < nvec;
+        act[1] = v0 + run < nvec;
+        xg0 = act[0] ? v0 * V : 0;  // idle threads shadow the first pair of the row; only their stores are masked
+        own[0] = opaque_u32(in_base + (uint32_t)xg0 * (uint32_t)sizeof(T));
+        own[1] = opaque_u32(act[1] ? own[0] + (uint32_t)(PAIR * p.d) * (uint32_t)sizeof(T) : own[0]);
+        rev[0] = opaque_u32(make_pair_plan<TAPS, PAIR>(xg0, p.d, p.W, in_base, ptap));
 #pragma unroll
-    for (int q = 0; q < NG; ++q) {
-        int xg = (q * nt + tid) * V;
-        act[q] = xg < p.W;
-        if (!act[q]) xg = (p.W / 2) & ~(V - 1);  // idle threads shadow an interior vector; only their stores are masked
-        if (q == 0) xg0 = xg;
-        own[q] = opaque_u32(in_base + (uint32_t)xg * (uint32_t)sizeof(T));
-        const TapPlan<NV> tp = make_tap_plan<V, NV>(xg, DMODE == 0 ? p.d : V, p.W, 0);
+        for (int k = 0; k < TAPS + PAIR; ++k) ptap[k] = opaque_u32(ptap[k]);
+        mirror_warp = __any_sync(0xffffffffu, rev[0] != 0 || !act[0]);
+    } else {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) tap[q][k] = opaque_u32(in_base + (uint32_t)tp.off[k] * (uint32_t)sizeof(T));
-        rev[q] = opaque_u32(tp.rev);
+        for (int q = 0; q < NG; ++q) {
+            int xg = (q * nt + tid) * V;
+            act[q] = xg < p.W;
+            if (!act[q]) xg = (p.W / 2) & ~(V - 1);  // idle threads shadow an interior vector; only their stores are masked
+            if (q == 0) xg0 = xg;
+            own[q] = opaque_u32(in_base + (uint32_t)xg * (uint32_t)sizeof(T));
+            const TapPlan<NV> tp = make_tap_plan<V, NV>(xg, DMODE == 0 ? p.d : V, p.W, 0);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) tap[q][k] = opaque_u32(in_base + (uint32_t)tp.off[k] * (uint32_t)sizeof(T));
+            rev[q] = opaque_u32(tp.rev);
+        }
+        mirror_warp = __any_sync(0xffffffffu, (rev[0] | rev[1]) != 0);
     }
-    const bool mirror_warp = __any_sync(0xffffffffu, (rev[0] | rev[1]) != 0);
-    const long long q_off = (long long)nt * V;  // column group 1 is nt vectors further (when active)
+    // the second column vector of a thread: M dilation steps (PAIR) or nt vectors further (when active)
+    const long long q_off = PAIR ? (long long)PAIR * p.d : (long long)nt * V;
 
     u64 S[NG][2][TAPS - 1];  // running column sums, one pixel pair per entry
 #pragma unroll
@@ -311,11 +331,21 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
         if (j >= n_load) return;
         mbar_wait_imm<8 * I>(full0, par);
         P4 cv[NG];
+        if constexpr (PAIR) {
+            P4 v[NG];
+            lean_row_pass_pair<TAPS, PAIR, I * RB, OP == OP_WHITEN, MIRROR>(ptap, rev[0], H, v[0], v[1]);
 #pragma unroll
-        for (int q = 0; q < NG; ++q) {
-            const P4 v = lean_row_pass<TAPS, DMODE, I * RB, OP == OP_WHITEN, MIRROR>(tap[q], rev[q], H);
-            cv[q].lo = col_feed_p<TAPS>(S[q][0], v.lo, H);
-            cv[q].hi = col_feed_p<TAPS>(S[q][1], v.hi, H);
+            for (int q = 0; q < NG; ++q) {
+                cv[q].lo = col_feed_p<TAPS>(S[q][0], v[q].lo, H);
+                cv[q].hi = col_feed_p<TAPS>(S[q][1], v[q].hi, H);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NG; ++q) {
+                const P4 v = lean_row_pass<TAPS, DMODE, I * RB, OP == OP_WHITEN, MIRROR>(tap[q], rev[q], H);
+                cv[q].lo = col_feed_p<TAPS>(S[q][0], v.lo, H);
+                cv[q].hi = col_feed_p<TAPS>(S[q][1], v.hi, H);
+            }
         }
         constexpr int SC = (I - C + 8) & (kLeanSlots - 1);  // raw centre row j-C
         if (j >= 2 * C) {
@@ -450,9 +480,27 @@ static bool k1_lean_enabled() {
     return v != 0;
 }
 
-template <int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0>
+// WB_K1_PAIR in the environment (A/B measurements): 0 keeps the nt-vector column groups at every dilation, 1 (default) pairs
+// columns from d = 32 on (M = 1), 2 also at d = 16 (M = 2) and d = 8 (M = 4, B3spline) -- measured slower inside a cascade
+// (0.336 -> 0.358 ms per transform: two more distinct kernels per cascade, no gain per launch; profiles/r2_pair_levels.json).
+static int k1_pair_step(int taps, int d, int W, int nt) {
+    static int level = -1;
+    if (level < 0) {
+        const char *e = getenv("WB_K1_PAIR");
+        level = e ? atoi(e) : 1;
+    }
+    if (d < 8 || (d & (d - 1)) != 0 || level <= 0 || (level == 1 && d < 32)) return 0;
+    const int m = d >= 32 ? 1 : 32 / d;
+    if (m >= taps) return 0;
+    // thread t owns vectors (t / run) 2 run + t % run and + run: the consumer threads must cover every first vector
+    const int run = m * (d / 4), nvec = W / 4;
+    const int need = ((nvec + 2 * run - 1) / (2 * run)) * run;
+    return need <= nt ? m : 0;
+}
+
+template <int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0, int PAIR = 0>
 static int launch_rows_lean(const ScaleParams &p, int batch, int nt, cudaStream_t st) {
-    auto kern = atrous_rows_lean_kernel<TAPS, DMODE, HINTS, OP, MODE>;
+    auto kern = atrous_rows_lean_kernel<TAPS, DMODE, HINTS, OP, MODE, PAIR>;
     const size_t smem = (size_t)kLeanSlots * kLeanRB + 16 * (size_t)kLeanSlots;
     static bool configured[64] = {};  // per instantiation, per device
     int dev = 0;
@@ -478,6 +526,14 @@ static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
                 !(scale < 32 && g_override_set[scale])) {
 #define WB_LEAN(DM) (p.l2_hints ? launch_rows_lean<TAPS, DM, true>(p, batch, cfg.nt, st) \
                                 : launch_rows_lean<TAPS, DM, false>(p, batch, cfg.nt, st))
+                if (dmode == 0 && p.l2_hints) {
+                    const int pair = k1_pair_step(TAPS, p.d, p.W, cfg.nt);
+                    if (pair == 1) return launch_rows_lean<TAPS, 0, true, OP_TRANSFORM, 0, 1>(p, batch, cfg.nt, st);
+                    if (pair == 2) return launch_rows_lean<TAPS, 0, true, OP_TRANSFORM, 0, 2>(p, batch, cfg.nt, st);
+                    if constexpr (TAPS > 4) {
+                        if (pair == 4) return launch_rows_lean<TAPS, 0, true, OP_TRANSFORM, 0, 4>(p, batch, cfg.nt, st);
+                    }
+                }
                 if (dmode == 0) return WB_LEAN(0);
                 if (dmode == 1) return WB_LEAN(1);
                 if (dmode == 2) return WB_LEAN(2);
@@ -488,13 +544,23 @@ static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
             // the whitening pass of the two-pass WOW routes on whole-row strips: lean kernel, hints on
             if (p.n_strips == 1 && cfg.ng == 2 && p.W > 1024 && cfg.slots == kLeanSlots && k1_lean_enabled() &&
                 !(scale < 32 && g_override_set[scale])) {
-#define WB_LEANW(DM)                                                                                              \
-    (p.sig_mode == 0 ? launch_rows_lean<TAPS, DM, true, OP_WHITEN, 0>(p, batch, cfg.nt, st)                        \
-                     : (p.sig_mode == 1 ? launch_rows_lean<TAPS, DM, true, OP_WHITEN, 1>(p, batch, cfg.nt, st)     \
-                                        : launch_rows_lean<TAPS, DM, true, OP_WHITEN, 2>(p, batch, cfg.nt, st)))
+#define WB_LEANW_P(DM, PR)                                                                                        \
+    (p.sig_mode == 0 ? launch_rows_lean<TAPS, DM, true, OP_WHITEN, 0, PR>(p, batch, cfg.nt, st)                    \
+                     : (p.sig_mode == 1 ? launch_rows_lean<TAPS, DM, true, OP_WHITEN, 1, PR>(p, batch, cfg.nt, st) \
+                                        : launch_rows_lean<TAPS, DM, true, OP_WHITEN, 2, PR>(p, batch, cfg.nt, st)))
+#define WB_LEANW(DM) WB_LEANW_P(DM, 0)
+                if (dmode == 0) {
+                    const int pair = k1_pair_step(TAPS, p.d, p.W, cfg.nt);
+                    if (pair == 1) return WB_LEANW_P(0, 1);
+                    if (pair == 2) return WB_LEANW_P(0, 2);
+                    if constexpr (TAPS > 4) {
+                        if (pair == 4) return WB_LEANW_P(0, 4);
+                    }
+                }
                 if (dmode == 0) return WB_LEANW(0);
                 if (dmode == 1) return WB_LEANW(1);
                 if (dmode == 2) return WB_LEANW(2);
+#undef WB_LEANW_P
 #undef WB_LEANW
             }
         }

@@ -416,16 +416,16 @@ __device__ __forceinline__ P4 lean_row_pass(const uint32_t (&a)[PlanSize<TAPS, D
     return acc;
 }
 
-// Row pass of a PAIR of vectors one dilation step apart (columns x and x + d, d % 4 == 0): their taps x + (k - C) d,
-// k = 0 .. TAPS, overlap in all but one vector each, so TAPS + 1 LDS.128 (and squarings) serve two outputs instead of
-// 2 TAPS -- the fused WOW kernel is limited by shared-memory wavefronts and LDS latency, not by arithmetic.  Every
-// output sums the same values in the same order as lean_row_pass: bit-identical planes.
-template <int TAPS, int OFF, bool SQUARE, bool MIRROR>
-__device__ __forceinline__ void lean_row_pass_pair(const uint32_t (&a)[TAPS + 1], unsigned rev, const PackedTaps<TAPS> &H,
+// Row pass of a PAIR of vectors M dilation steps apart (columns x and x + M d, d % 4 == 0): their taps x + (k - C) d
+// overlap in TAPS - M vectors, so TAPS + M LDS.128 (and squarings) serve two outputs instead of 2 TAPS -- the lean
+// kernels are limited by shared-memory wavefronts and LDS latency before arithmetic.  Every output sums the same
+// values in the same order as lean_row_pass: bit-identical planes.
+template <int TAPS, int M, int OFF, bool SQUARE, bool MIRROR>
+__device__ __forceinline__ void lean_row_pass_pair(const uint32_t (&a)[TAPS + M], unsigned rev, const PackedTaps<TAPS> &H,
                                                    P4 &o0, P4 &o1) {
-    P4 t[TAPS + 1];
+    P4 t[TAPS + M];
 #pragma unroll
-    for (int k = 0; k <= TAPS; ++k) {
+    for (int k = 0; k < TAPS + M; ++k) {
         t[k] = lds_p4_imm<OFF>(a[k]);
         if constexpr (MIRROR) {
             const bool m = (rev >> k) & 1u;
@@ -442,9 +442,32 @@ __device__ __forceinline__ void lean_row_pass_pair(const uint32_t (&a)[TAPS + 1]
     for (int k = 0; k < TAPS; ++k) {
         o0.lo = (k == 0) ? mul2(H.h[0], t[k].lo) : fma2(H.h[k], t[k].lo, o0.lo);
         o0.hi = (k == 0) ? mul2(H.h[0], t[k].hi) : fma2(H.h[k], t[k].hi, o0.hi);
-        o1.lo = (k == 0) ? mul2(H.h[0], t[k + 1].lo) : fma2(H.h[k], t[k + 1].lo, o1.lo);
-        o1.hi = (k == 0) ? mul2(H.h[0], t[k + 1].hi) : fma2(H.h[k], t[k + 1].hi, o1.hi);
+        o1.lo = (k == 0) ? mul2(H.h[0], t[k + M].lo) : fma2(H.h[k], t[k + M].lo, o1.lo);
+        o1.hi = (k == 0) ? mul2(H.h[0], t[k + M].hi) : fma2(H.h[k], t[k + M].hi, o1.hi);
     }
+}
+
+// Thread -> first vector of its pair: runs of M dv consecutive vectors (dv = d / 4 vectors per dilation step) alternate
+// between first and second halves of the pairs.  M dv >= 8, so eight consecutive lanes read eight consecutive vectors
+// (conflict-free LDS.128) and a warp stores runs of >= 128 contiguous bytes.
+__device__ __forceinline__ int pair_first_vector(int tid, int run) { return (tid / run) * 2 * run + (tid % run); }
+
+// The TAPS + M tap addresses (slot 0) of a pair whose first vector starts at column x0, with the symmetric border:
+// returns the mirror bits.  Taps that belong only to a masked second vector may fall outside one reflection: clamped.
+template <int TAPS, int M>
+__device__ __forceinline__ unsigned make_pair_plan(int x0, int d, int W, uint32_t base, uint32_t (&a)[TAPS + M]) {
+    constexpr int C = TAPS / 2;
+    unsigned rv = 0;
+#pragma unroll
+    for (int k = 0; k < TAPS + M; ++k) {
+        const int pc = x0 + (k - C) * d;
+        const bool left = pc < 0, right = pc >= W;
+        int q = left ? (-4 - pc) : (right ? (2 * W - 4 - pc) : pc);
+        if (q < 0 || q > W - 4) q = 0;
+        a[k] = base + (uint32_t)q * 4u;
+        if (left || right) rv |= 1u << k;
+    }
+    return rv;
 }
 
 template <int I> struct IC { static constexpr int value = I; };

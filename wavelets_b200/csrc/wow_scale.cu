@@ -225,13 +225,13 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
 // ---------------------------------------------------------------------------------------------------------------
 // MODE: significance compiled into the epilogue (0 none, 1 soft, 2 hard); the step loop is small enough to stay in
 // the instruction cache only without the inlined erff of the modes that are not used.
-// PAIR (DMODE 0, d >= 32): a thread's two column vectors are one dilation step apart (x and x + d) instead of half a row
-// apart, so both row passes load TAPS + 1 tap vectors for the two of them instead of 2 TAPS (lean_row_pass_pair): 18
-// instead of 26 LDS/STS.128 per thread and step.  Vector v0 = (tid / dv) 2 dv + tid % dv with dv = d / 4 >= 8: eight
-// consecutive lanes still read eight consecutive vectors (conflict-free), a warp stores runs of >= 128 contiguous bytes.
-template <int TAPS, int DMODE, bool HINTS, int MODE, bool PAIR = false>
+// PAIR = M > 0 (DMODE 0, d >= 8): a thread's two column vectors are M dilation steps apart (x and x + M d) instead of
+// half a row apart, so both row passes load TAPS + M tap vectors for the two of them instead of 2 TAPS
+// (lean_row_pass_pair): with M = 1 (d >= 32) 18 instead of 26 LDS/STS.128 per thread and step; M = 2 for d = 16 (20), M = 4
+// for d = 8 (24) keep eight consecutive lanes on eight consecutive vectors (see pair_first_vector).
+template <int TAPS, int DMODE, bool HINTS, int MODE, int PAIR = 0>
 __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams p) {
-    static_assert(!PAIR || DMODE == 0, "paired columns need d % 4 == 0");
+    static_assert(PAIR == 0 || (DMODE == 0 && PAIR < TAPS), "paired columns need d % 4 == 0 and overlapping taps");
     using T = float;
     constexpr int V = 4, NG = 2, NT = 512;
     constexpr int C = TAPS / 2;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
     const PackedTaps<TAPS> H;
 
     // per-thread addresses inside ring slot 0: own vector and taps, for both column groups
-    constexpr int NTAP = PAIR ? 1 : NG, NPT = PAIR ? TAPS + 1 : 1;
+    constexpr int NTAP = PAIR ? 1 : NG, NPT = TAPS + PAIR;
     uint32_t own[NG], tap[NTAP][NV], ptap[NPT];
     unsigned rev[NG] = {0u, 0u};
     bool act[NG];
@@ -306,28 +306,19 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
     const uint32_t tap_step = (uint32_t)(DMODE == 0 ? p.d : V) * (uint32_t)sizeof(T);
     bool mirror_warp;
     if constexpr (PAIR) {
-        const int dv = p.d >> 2, nvec = p.W >> 2;  // vectors per dilation step (a power of two >= 8), vectors per row
-        const int v0 = (tid / dv) * 2 * dv + (tid & (dv - 1));
+        const int run = PAIR * (p.d >> 2), nvec = p.W >> 2;  // vectors between the two of a pair (>= 8), vectors per row
+        const int v0 = pair_first_vector(tid, run);
         act[0] = v0 < nvec;
-        act[1] = v0 + dv < nvec;
+        act[1] = v0 + run < nvec;
         xg0 = act[0] ? v0 * V : 0;  // idle threads shadow the first pair of the row; only their stores are masked
         own[0] = opaque_u32(in_base + (uint32_t)xg0 * (uint32_t)sizeof(T));
-        own[1] = opaque_u32(act[1] ? own[0] + tap_step : own[0]);
-        unsigned rv = 0;
-#pragma unroll
-        for (int k = 0; k <= TAPS; ++k) {
-            const int pc = xg0 + (k - C) * p.d;  // columns of tap k of the first vector = tap k - 1 of the second
-            const bool left = pc < 0, right = pc >= p.W;
-            int q = left ? (-V - pc) : (right ? (2 * p.W - V - pc) : pc);
-            if (q < 0 || q > p.W - V) q = 0;  // only taps of a masked second vector can land here
-            ptap[k] = in_base + (uint32_t)q * (uint32_t)sizeof(T);
-            if (left || right) rv |= 1u << k;
-        }
+        own[1] = opaque_u32(act[1] ? own[0] + PAIR * tap_step : own[0]);
+        const unsigned rv = make_pair_plan<TAPS, PAIR>(xg0, p.d, p.W, in_base, ptap);
         rev[0] = rv;
         mirror_warp = __any_sync(0xffffffffu, rv != 0 || !act[0]);
         if (mirror_warp) {
 #pragma unroll
-            for (int k = 0; k <= TAPS; ++k) ptap[k] = opaque_u32(ptap[k]);
+            for (int k = 0; k < TAPS + PAIR; ++k) ptap[k] = opaque_u32(ptap[k]);
             rev[0] = opaque_u32(rev[0]);
         }
     } else {
@@ -357,7 +348,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
     }
     // the second column vector of a thread: one dilation step (PAIR) or half a ring slot (NT vectors) further
     auto q_off = [&](int q) -> long long {
-        if constexpr (PAIR) return q ? (long long)p.d : 0LL;
+        if constexpr (PAIR) return q ? (long long)PAIR * p.d : 0LL;
         else return (long long)q * (NT * V);
     };
 
@@ -399,11 +390,11 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
             for (int q = 0; q < NG; ++q) rawc[q] = lds_p4_imm<SC * RB>(own[q] + (other_half ? half_c : half));
             P4 cv[NG];
             if constexpr (PAIR) {
-                uint32_t a[TAPS + 1];
+                uint32_t a[TAPS + PAIR];
 #pragma unroll
-                for (int k = 0; k <= TAPS; ++k) a[k] = (MIRROR ? ptap[k] : own[0] + (uint32_t)(k - C) * tap_step) + half;
+                for (int k = 0; k < TAPS + PAIR; ++k) a[k] = (MIRROR ? ptap[k] : own[0] + (uint32_t)(k - C) * tap_step) + half;
                 P4 v[NG];
-                lean_row_pass_pair<TAPS, I * RB, false, MIRROR>(a, rev[0], H, v[0], v[1]);
+                lean_row_pass_pair<TAPS, PAIR, I * RB, false, MIRROR>(a, rev[0], H, v[0], v[1]);
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
                     cv[q].lo = col_feed_p<TAPS>(SA[q][0], v[q].lo, H);
@@ -453,11 +444,11 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
             for (int q = 0; q < NG; ++q) roww[q] = lds_p4_imm<W_OFF + SE * RB>(own[q]);
             P4 pw[NG];
             if constexpr (PAIR) {
-                uint32_t a[TAPS + 1];
+                uint32_t a[TAPS + PAIR];
 #pragma unroll
-                for (int k = 0; k <= TAPS; ++k) a[k] = MIRROR ? ptap[k] : own[0] + (uint32_t)(k - C) * tap_step;
+                for (int k = 0; k < TAPS + PAIR; ++k) a[k] = MIRROR ? ptap[k] : own[0] + (uint32_t)(k - C) * tap_step;
                 P4 v[NG];
-                lean_row_pass_pair<TAPS, W_OFF + SP * RB, true, MIRROR>(a, rev[0], H, v[0], v[1]);
+                lean_row_pass_pair<TAPS, PAIR, W_OFF + SP * RB, true, MIRROR>(a, rev[0], H, v[0], v[1]);
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
                     pw[q].lo = col_feed_p<TAPS>(SB[q][0], v[q].lo, H);
@@ -585,24 +576,34 @@ static bool wow_packed_enabled() {
     return v != 0;
 }
 
-// WB_WOW_PAIR=0 in the environment keeps the half-row column groups at every dilation (A/B measurements).
-static bool wow_pair_enabled() {
+// WB_WOW_PAIR in the environment (A/B measurements): 0 keeps the half-row column groups at every dilation, 1 (default)
+// pairs columns from d = 32 on (M = 1), 2 also at d = 16 (M = 2) and d = 8 (M = 4).  Level 2 is measured and not the
+// default: stand-alone the d = 16 launch gains 7 us (48 -> 41), but inside wow() the two extra kernels cost more than
+// that -- every change of kernel inside a cascade starts with a cold instruction cache (profiles/r2_pair_levels.json).
+static int wow_pair_level() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("WB_WOW_PAIR");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = e ? atoi(e) : 1;
     }
-    return v != 0;
+    return v;
+}
+
+template <int TAPS, int M>
+static auto wow_pair_kernel(int sig_mode) -> void (*)(const ScaleParams) {
+    return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, 0, true, 0, M>
+                         : (sig_mode == 1 ? wow_rows_lean_kernel<TAPS, 0, true, 1, M> : wow_rows_lean_kernel<TAPS, 0, true, 2, M>);
 }
 
 template <typename T, int TAPS, int DMODE, bool HINTS>
-static auto wow_kernel_for(bool packed, bool pair, int sig_mode) -> void (*)(const ScaleParams) {
+static auto wow_kernel_for(bool packed, int pair, int sig_mode) -> void (*)(const ScaleParams) {
     if constexpr (sizeof(T) == 4) {
-        if constexpr (DMODE == 0) {
-            if (packed && pair)
-                return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 0, true>
-                                     : (sig_mode == 1 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 1, true>
-                                                      : wow_rows_lean_kernel<TAPS, DMODE, HINTS, 2, true>);
+        if constexpr (DMODE == 0 && HINTS) {
+            if (packed && pair == 1) return wow_pair_kernel<TAPS, 1>(sig_mode);
+            if (packed && pair == 2) return wow_pair_kernel<TAPS, 2>(sig_mode);
+            if constexpr (TAPS > 4) {
+                if (packed && pair == 4) return wow_pair_kernel<TAPS, 4>(sig_mode);
+            }
         }
         if (packed)
             return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 0>
@@ -612,18 +613,25 @@ static auto wow_kernel_for(bool packed, bool pair, int sig_mode) -> void (*)(con
     return wow_rows_kernel<T, TAPS, DMODE, 2, HINTS>;
 }
 
+// Paired columns (x, x + M d): M = 1 from d = 32 on, M = 2 at d = 16, M = 4 at d = 8 (B3spline only: M < taps) -- the runs
+// of M d / 4 >= 8 consecutive vectors keep the LDS.128 of eight consecutive lanes conflict-free; 0 = half-row groups.
+static int wow_pair_step(int taps, int d) {
+    const int level = wow_pair_level();
+    if (d < 8 || (d & (d - 1)) != 0 || level <= 0 || (level == 1 && d < 32)) return 0;
+    const int m = d >= 32 ? 1 : 32 / d;
+    return m < taps ? m : 0;
+}
+
 template <typename T, int TAPS, int DMODE, bool HINTS>
 static int launch_wow_h(const ScaleParams &p, int batch, const WowGeom &geo, cudaStream_t st) {
     // the lean kernel always runs 512 threads x 2 vectors on 16 KiB ring slots: use it when the row needs them
     const bool packed = sizeof(T) == 4 && p.W > 2048 && p.n_strips == 1 && wow_packed_enabled();
-    // paired columns (x, x + d) from d = 32 on: below that eight consecutive lanes would not read eight consecutive
-    // vectors (shared-memory bank conflicts eat the saved loads)
-    const bool pair = packed && DMODE == 0 && p.d >= 32 && (p.d & (p.d - 1)) == 0 && wow_pair_enabled();
+    const int pair = (packed && DMODE == 0 && HINTS) ? wow_pair_step(TAPS, p.d) : 0;
     auto kern = wow_kernel_for<T, TAPS, DMODE, HINTS>(packed, pair, p.sig_mode);
     const int nt = packed ? 512 : geo.nt;
     const size_t smem = packed ? (size_t)(kInRing + kWRing) * kLeanRB + 8 * (size_t)(kInRing + kWRing) : geo.smem;
-    static bool configured[7][64] = {};  // generic, lean x 3 significance modes, paired lean x 3; per device
-    const int kidx = packed ? 1 + p.sig_mode + (pair ? 3 : 0) : 0;
+    static bool configured[13][64] = {};  // generic, lean x 3 significance modes, paired lean (M = 1, 2, 4) x 3; per device
+    const int kidx = packed ? 1 + p.sig_mode + 3 * (pair == 4 ? 3 : pair) : 0;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[kidx][dev]) {
