@@ -48,6 +48,13 @@ def main():
                         "alternating_4_5": round(1e3 * timed(lambda: seq([4, 5] * 4), args.reps) / 8, 2),
                         "grouped_0_1_4_5": round(1e3 * timed(lambda: seq([0] * 2 + [1] * 2 + [4] * 2 + [5] * 2), args.reps) / 8, 2),
                         "alternating_0_1_4_5": round(1e3 * timed(lambda: seq([0, 1, 4, 5] * 2), args.reps) / 8, 2)}
+    def fseq(order):
+        for s in order:
+            utils._wow_scale_fused(lib, src, c, o, s, sf, 0, 0.0, 1.0, utils._Noise(), 1.0)
+    res["switch_fused_us"] = {"grouped_0_1_4_5": round(1e3 * timed(lambda: fseq([0] * 2 + [1] * 2 + [4] * 2 + [5] * 2), args.reps) / 8, 2),
+                              "alternating_0_1_4_5": round(1e3 * timed(lambda: fseq([0, 1, 4, 5] * 2), args.reps) / 8, 2),
+                              "grouped_4_5": round(1e3 * timed(lambda: fseq([4] * 4 + [5] * 4), args.reps) / 8, 2),
+                              "alternating_4_5": round(1e3 * timed(lambda: fseq([4, 5] * 4), args.reps) / 8, 2)}
     tr = wb.AtrousTransform(wb.B3spline)
     res["transform_ms"] = round(timed(lambda: tr(img, 10), 100), 4)
     res["wow_ms"] = round(timed(lambda: wb.wow(img), args.reps), 4)

@@ -201,9 +201,13 @@ static constexpr int kLeanSlots = 8;
 // SQUARES of the staged raw w_s rows and the epilogue whitens the raw centre value -- same pipeline, 2*T bytes per pixel.
 // PAIR = M > 0 (DMODE 0, d >= 8): a thread's two column vectors are M dilation steps apart (x, x + M d) and share
 // TAPS - M of their tap vectors (lean_row_pass_pair, see wow_rows_lean_kernel): 8 instead of 12 LDS.128 per step at M = 1.
-template <int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0, int PAIR = 0>
+// UNROLL: steps per iteration of the step loop, 8 (= the ring: every slot offset an immediate) or 4 (the ring's two
+// halves alternate: one more address term per access, HALF the code -- a 60 KB kernel does not fit the 32 KB
+// instruction cache level, and every change of kernel inside a cascade starts cold).
+template <int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0, int PAIR = 0, int UNROLL = 8>
 __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams p) {
     static_assert(PAIR == 0 || (DMODE == 0 && PAIR < TAPS), "paired columns need d % 4 == 0 and overlapping taps");
+    static_assert(UNROLL == 8 || UNROLL == 4, "the step loop is unrolled by the ring or by half of it");
     using T = float;
     constexpr int V = 4, NG = 2;
     constexpr int C = TAPS / 2;
@@ -323,17 +327,21 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
     const bool pushing = (p.push_up != nullptr) | (p.push_dn != nullptr);
     int out_row = (int)orow;  // band row of the next output
 
-    // Step j = 8 u + I: input row j lands -> row pass -> column feed -> c row j-C; w = raw centre row - c; release the
-    // centre row's slot.
-    auto step = [&](auto ic, auto mirror, const int j, const uint32_t par) {
+    // Step j = UNROLL u + I: input row j lands (ring slot j % 8 = I + (half ? 4 : 0)) -> row pass -> column feed -> c row
+    // j-C; w = raw centre row - c; release the centre row's slot.  `half` / `half_c`: byte offset (0 or 4 RB) of the ring
+    // half this iteration's rows land in / of the other half (UNROLL == 4; both 0 when the loop is unrolled by the ring).
+    auto step = [&](auto ic, auto mirror, const int j, const uint32_t par, const uint32_t half, const uint32_t half_c) {
         constexpr int I = decltype(ic)::value;
         constexpr bool MIRROR = decltype(mirror)::value != 0;
         if (j >= n_load) return;
-        mbar_wait_imm<8 * I>(full0, par);
+        mbar_wait_imm<8 * I>(full0 + (half >> 11), par);  // 8 bytes of barrier per 16 KiB slot
         P4 cv[NG];
         if constexpr (PAIR) {
+            uint32_t a[TAPS + PAIR];
+#pragma unroll
+            for (int k = 0; k < TAPS + PAIR; ++k) a[k] = ptap[k] + half;
             P4 v[NG];
-            lean_row_pass_pair<TAPS, PAIR, I * RB, OP == OP_WHITEN, MIRROR>(ptap, rev[0], H, v[0], v[1]);
+            lean_row_pass_pair<TAPS, PAIR, I * RB, OP == OP_WHITEN, MIRROR>(a, rev[0], H, v[0], v[1]);
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
                 cv[q].lo = col_feed_p<TAPS>(S[q][0], v[q].lo, H);
@@ -342,17 +350,22 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
         } else {
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
-                const P4 v = lean_row_pass<TAPS, DMODE, I * RB, OP == OP_WHITEN, MIRROR>(tap[q], rev[q], H);
+                uint32_t a[NV];
+#pragma unroll
+                for (int k = 0; k < NV; ++k) a[k] = tap[q][k] + half;
+                const P4 v = lean_row_pass<TAPS, DMODE, I * RB, OP == OP_WHITEN, MIRROR>(a, rev[q], H);
                 cv[q].lo = col_feed_p<TAPS>(S[q][0], v.lo, H);
                 cv[q].hi = col_feed_p<TAPS>(S[q][1], v.hi, H);
             }
         }
-        constexpr int SC = (I - C + 8) & (kLeanSlots - 1);  // raw centre row j-C
+        // raw centre row j-C: slot (I - C) mod UNROLL of this half, or of the other half when the index wraps
+        constexpr int SC = (I - C + UNROLL) & (UNROLL - 1);
+        const uint32_t hc = (UNROLL == 4 && I < C) ? half_c : half;
         if (j >= 2 * C) {
             if constexpr (OP == OP_WHITEN) {
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
-                    P4 raw = lds_p4_imm<SC * RB>(own[q]);
+                    P4 raw = lds_p4_imm<SC * RB>(own[q] + hc);
                     raw.lo = epi.template apply2<MODE>(raw.lo, cv[q].lo);
                     raw.hi = epi.template apply2<MODE>(raw.hi, cv[q].hi);
                     if (act[q]) stg_p4_cs(w_ptr + q * q_off, raw);
@@ -367,7 +380,7 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
                     if (pushing) push_store(p, c_ptr + q * q_off, c_base, out_row, cv[q]);
                 }
                 if (has_w) {
-                    P4 raw = lds_p4_imm<SC * RB>(own[q]);
+                    P4 raw = lds_p4_imm<SC * RB>(own[q] + hc);
                     raw.lo = sub2(raw.lo, cv[q].lo);
                     raw.hi = sub2(raw.hi, cv[q].hi);
                     if (act[q]) stg_p4_cs(w_ptr + q * q_off, raw);
@@ -381,21 +394,25 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
         if (j >= C) {
             // the raw row j-C is not needed any more: hand its slot back to the producer
             __syncwarp();
-            if (lane == 0) mbar_arrive_imm<8 * SC>(empty0);
+            if (lane == 0) mbar_arrive_imm<8 * SC>(empty0 + (hc >> 11));
         }
     };
     auto run = [&](auto mirror) {
 #pragma unroll 1
-        for (int jb = 0; jb < n_load; jb += 8) {
+        for (int jb = 0; jb < n_load; jb += UNROLL) {
             const uint32_t par = (uint32_t)(jb >> 3) & 1u;
-            step(IC<0>{}, mirror, jb + 0, par);
-            step(IC<1>{}, mirror, jb + 1, par);
-            step(IC<2>{}, mirror, jb + 2, par);
-            step(IC<3>{}, mirror, jb + 3, par);
-            step(IC<4>{}, mirror, jb + 4, par);
-            step(IC<5>{}, mirror, jb + 5, par);
-            step(IC<6>{}, mirror, jb + 6, par);
-            step(IC<7>{}, mirror, jb + 7, par);
+            const uint32_t half = (UNROLL == 4 && (jb & 4)) ? 4u * RB : 0u;
+            const uint32_t half_c = (UNROLL == 4) ? (half ^ (4u * RB)) : 0u;
+            step(IC<0>{}, mirror, jb + 0, par, half, half_c);
+            step(IC<1>{}, mirror, jb + 1, par, half, half_c);
+            step(IC<2>{}, mirror, jb + 2, par, half, half_c);
+            step(IC<3>{}, mirror, jb + 3, par, half, half_c);
+            if constexpr (UNROLL == 8) {
+                step(IC<4>{}, mirror, jb + 4, par, half, half_c);
+                step(IC<5>{}, mirror, jb + 5, par, half, half_c);
+                step(IC<6>{}, mirror, jb + 6, par, half, half_c);
+                step(IC<7>{}, mirror, jb + 7, par, half, half_c);
+            }
         }
     };
     if (mirror_warp) run(IC<1>{});
@@ -498,17 +515,29 @@ static int k1_pair_step(int taps, int d, int W, int nt) {
     return need <= nt ? m : 0;
 }
 
+// WB_K1_UNROLL=8 in the environment selects the step loop unrolled by the whole ring (A/B measurements).
+static int k1_unroll() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("WB_K1_UNROLL");
+        v = (e && atoi(e) == 8) ? 8 : 4;
+    }
+    return v;
+}
+
 template <int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0, int PAIR = 0>
 static int launch_rows_lean(const ScaleParams &p, int batch, int nt, cudaStream_t st) {
-    auto kern = atrous_rows_lean_kernel<TAPS, DMODE, HINTS, OP, MODE, PAIR>;
+    const bool u8 = k1_unroll() == 8;
+    auto kern = u8 ? atrous_rows_lean_kernel<TAPS, DMODE, HINTS, OP, MODE, PAIR, 8>
+                   : atrous_rows_lean_kernel<TAPS, DMODE, HINTS, OP, MODE, PAIR, 4>;
     const size_t smem = (size_t)kLeanSlots * kLeanRB + 16 * (size_t)kLeanSlots;
-    static bool configured[64] = {};  // per instantiation, per device
+    static bool configured[2][64] = {};  // per instantiation, per unroll, per device
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
+    if (dev < 0 || dev >= 64 || !configured[u8][dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
         if (e != cudaSuccess) return (int)e;
-        if (dev >= 0 && dev < 64) configured[dev] = true;
+        if (dev >= 0 && dev < 64) configured[u8][dev] = true;
     }
     dim3 grid((unsigned)((long long)p.d * p.n_seg), (unsigned)batch);
     return launch_pdl<ScaleParams>(kern, grid, dim3((unsigned)(nt + 32)), smem, st, p);
