@@ -497,22 +497,22 @@ static bool k1_lean_enabled() {
     return v != 0;
 }
 
-// WB_K1_PAIR in the environment (A/B measurements): 0 keeps the nt-vector column groups at every dilation, 1 (default) pairs
-// columns from d = 32 on (M = 1), 2 also at d = 16 (M = 2) and d = 8 (M = 4, B3spline) -- measured slower inside a cascade
-// (0.336 -> 0.358 ms per transform: two more distinct kernels per cascade, no gain per launch; profiles/r2_pair_levels.json).
+// Paired columns (x, x + M d) with M = 1 from d = 32 on; WB_K1_PAIR=0 in the environment keeps the nt-vector column
+// groups at every dilation (A/B measurements).  M = 2 at d = 16 and M = 4 at d = 8 were built and measured (the kernel
+// template takes them): no gain per launch and two more distinct kernels per cascade (0.336 -> 0.358 ms per transform
+// with the step loop unrolled by 8, profiles/r2_pair_levels.json) -- not instantiated.
 static int k1_pair_step(int taps, int d, int W, int nt) {
     static int level = -1;
     if (level < 0) {
         const char *e = getenv("WB_K1_PAIR");
         level = e ? atoi(e) : 1;
     }
-    if (d < 8 || (d & (d - 1)) != 0 || level <= 0 || (level == 1 && d < 32)) return 0;
-    const int m = d >= 32 ? 1 : 32 / d;
-    if (m >= taps) return 0;
+    (void)taps;
+    if (d < 32 || (d & (d - 1)) != 0 || level <= 0) return 0;
     // thread t owns vectors (t / run) 2 run + t % run and + run: the consumer threads must cover every first vector
-    const int run = m * (d / 4), nvec = W / 4;
+    const int run = d / 4, nvec = W / 4;
     const int need = ((nvec + 2 * run - 1) / (2 * run)) * run;
-    return need <= nt ? m : 0;
+    return need <= nt ? 1 : 0;
 }
 
 // WB_K1_UNROLL=8 in the environment selects the step loop unrolled by the whole ring (A/B measurements).
@@ -558,10 +558,6 @@ static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
                 if (dmode == 0 && p.l2_hints) {
                     const int pair = k1_pair_step(TAPS, p.d, p.W, cfg.nt);
                     if (pair == 1) return launch_rows_lean<TAPS, 0, true, OP_TRANSFORM, 0, 1>(p, batch, cfg.nt, st);
-                    if (pair == 2) return launch_rows_lean<TAPS, 0, true, OP_TRANSFORM, 0, 2>(p, batch, cfg.nt, st);
-                    if constexpr (TAPS > 4) {
-                        if (pair == 4) return launch_rows_lean<TAPS, 0, true, OP_TRANSFORM, 0, 4>(p, batch, cfg.nt, st);
-                    }
                 }
                 if (dmode == 0) return WB_LEAN(0);
                 if (dmode == 1) return WB_LEAN(1);
@@ -581,10 +577,6 @@ static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
                 if (dmode == 0) {
                     const int pair = k1_pair_step(TAPS, p.d, p.W, cfg.nt);
                     if (pair == 1) return WB_LEANW_P(0, 1);
-                    if (pair == 2) return WB_LEANW_P(0, 2);
-                    if constexpr (TAPS > 4) {
-                        if (pair == 4) return WB_LEANW_P(0, 4);
-                    }
                 }
                 if (dmode == 0) return WB_LEANW(0);
                 if (dmode == 1) return WB_LEANW(1);

@@ -1020,6 +1020,7 @@ __global__ void __launch_bounds__(288, 2) bilateral_lean_kernel(const BilateralP
     const uint32_t sbase = opaque_u32(rows0);
     const uint32_t own = opaque_u32(colb[NL / 2]);
     const uint32_t tstep = opaque_u32((uint32_t)(DMODE == 0 ? p.d : 2) * 4u);
+    const int tstep_u = p.d * 4;  // the same stride as a launch constant (LD == -2)
     const bool mirror_warp = __any_sync(0xffffffffu, rev != 0);
     if (mirror_warp) {
 #pragma unroll
@@ -1058,6 +1059,11 @@ __global__ void __launch_bounds__(288, 2) bilateral_lean_kernel(const BilateralP
             mbar_wait_imm<FULL_OFF + 8 * I>(sbase, parity);
             if constexpr (DMODE == 0 && !MIRROR && LD >= 0) {
                 lean_load_taps<TAPS, I * RB, (LD >= 0 ? LD : 0)>(own, X[WS], std::make_integer_sequence<int, TAPS>{});
+            } else if constexpr (DMODE == 0 && !MIRROR && LD == -2) {
+                // the tap offsets (k - C) * stride are the same in every thread: left to ptxas as warp-uniform values they
+                // become the uniform-register term of LDS [R + UR + imm] -- one kernel for every dilation
+#pragma unroll
+                for (int k = 0; k < TAPS; ++k) X[WS][k] = lds64_imm<I * RB>(own + (uint32_t)((k - C) * tstep_u));
             } else if constexpr (DMODE == 0) {
 #pragma unroll
                 for (int k = 0; k < TAPS; ++k) {
@@ -1542,6 +1548,14 @@ static int launch_bilateral_pairs(const BilateralParams &bp, int batch, cudaStre
     int wm = k2_mode_for(TAPS, bp.sp.d);
     if (wm == 2) {
         if (k2_lean_ok(bp.sp)) {
+            if constexpr (DMODE == 0) {
+                static int uni = -1;  // WB_K2_UNIFORM=1: one kernel for every dilation (uniform-register tap offsets)
+                if (uni < 0) {
+                    const char *e = getenv("WB_K2_UNIFORM");
+                    uni = (e && e[0] == '1') ? 1 : 0;
+                }
+                if (uni) return launch_bilateral_lean<TAPS, DMODE, -2>(bp, batch, st);
+            }
             if constexpr (TAPS == 5 && DMODE == 0) {
                 // the B3spline scales of a dyadic cascade: dilation as a template parameter (immediate tap offsets)
                 switch (bp.sp.d) {

@@ -229,7 +229,11 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
 // half a row apart, so both row passes load TAPS + M tap vectors for the two of them instead of 2 TAPS
 // (lean_row_pass_pair): with M = 1 (d >= 32) 18 instead of 26 LDS/STS.128 per thread and step; M = 2 for d = 16 (20), M = 4
 // for d = 8 (24) keep eight consecutive lanes on eight consecutive vectors (see pair_first_vector).
-template <int TAPS, int DMODE, bool HINTS, int MODE, int PAIR = 0>
+// DYN: the step loop is NOT unrolled -- ring slots and barrier parities are computed from the step index (warp-uniform
+// values: one more address term per shared-memory access) and the kernel is a quarter of the code.  The unrolled
+// kernel (60 - 90 KB) does not fit the instruction cache levels below L2, and every change of kernel inside a cascade
+// starts cold (see atrous_rows_lean_kernel).
+template <int TAPS, int DMODE, bool HINTS, int MODE, int PAIR = 0, bool DYN = false>
 __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams p) {
     static_assert(PAIR == 0 || (DMODE == 0 && PAIR < TAPS), "paired columns need d % 4 == 0 and overlapping taps");
     using T = float;
@@ -379,22 +383,34 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
         constexpr int I = decltype(ic)::value;
         constexpr bool MIRROR = decltype(mirror)::value != 0;
         if (j > n_load) return;
+        // ring slots touched by this step, as [dynamic byte offset] + immediate: unrolled loop -> the immediates carry the
+        // slot and only the input ring has a dynamic part (its half); DYN -> everything from j, immediates 0
+        constexpr int SCs = (I - C + 4) & 3;                             // raw centre row j-C (input ring)
+        constexpr bool other_half = I < C;
+        constexpr int SWs = (I - 2 * C + 8) & (kWRing - 1);              // w row j-2C, written by part A
+        constexpr int SPs = (I - 1 - 2 * C + 16) & (kWRing - 1);         // w row j-1-2C (all threads' columns), part B
+        constexpr int SEs = (I - 1 - 3 * C + 16) & (kWRing - 1);         // own raw w of the P row completed in this step
+        constexpr int IMM_IN = DYN ? 0 : I * RB, IMM_C = DYN ? 0 : SCs * RB, IMM_SW = DYN ? 0 : SWs * RB;
+        constexpr int IMM_SP = DYN ? 0 : SPs * RB, IMM_SE = DYN ? 0 : SEs * RB;
+        const uint32_t o_in = DYN ? ((uint32_t)j & (kInRing - 1)) * RB : half;
+        const uint32_t o_c = DYN ? ((uint32_t)(j - C) & (kInRing - 1)) * RB : (other_half ? half_c : half);
+        const uint32_t o_sw = DYN ? ((uint32_t)(j - 2 * C) & (kWRing - 1)) * RB : 0u;
+        const uint32_t o_sp = DYN ? ((uint32_t)(j - 1 - 2 * C) & (kWRing - 1)) * RB : 0u;
+        const uint32_t o_se = DYN ? ((uint32_t)(j - 1 - 3 * C) & (kWRing - 1)) * RB : 0u;
         if (j < n_load) {
-            mbar_wait_imm<8 * I>(full0 + (half >> 11), par_in);  // barrier of slot I + 4 (u & 1): 8 bytes per slot
-            // raw centre row j-C (slot (I - C) mod 4 of the half that row was loaded into), requested first so that its
-            // latency hides behind the row pass
-            constexpr int SC = (I - C + 4) & 3;
-            constexpr bool other_half = I < C;
+            // barrier of the input slot: 8 bytes per 16 KiB slot
+            mbar_wait_imm<IMM_IN / RB * 8>(full0 + (o_in >> 11), DYN ? ((uint32_t)j >> 3) & 1u : par_in);
+            // raw centre row j-C, requested first so that its latency hides behind the row pass
             P4 rawc[NG];
 #pragma unroll
-            for (int q = 0; q < NG; ++q) rawc[q] = lds_p4_imm<SC * RB>(own[q] + (other_half ? half_c : half));
+            for (int q = 0; q < NG; ++q) rawc[q] = lds_p4_imm<IMM_C>(own[q] + o_c);
             P4 cv[NG];
             if constexpr (PAIR) {
                 uint32_t a[TAPS + PAIR];
 #pragma unroll
-                for (int k = 0; k < TAPS + PAIR; ++k) a[k] = (MIRROR ? ptap[k] : own[0] + (uint32_t)(k - C) * tap_step) + half;
+                for (int k = 0; k < TAPS + PAIR; ++k) a[k] = (MIRROR ? ptap[k] : own[0] + (uint32_t)(k - C) * tap_step) + o_in;
                 P4 v[NG];
-                lean_row_pass_pair<TAPS, PAIR, I * RB, false, MIRROR>(a, rev[0], H, v[0], v[1]);
+                lean_row_pass_pair<TAPS, PAIR, IMM_IN, false, MIRROR>(a, rev[0], H, v[0], v[1]);
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
                     cv[q].lo = col_feed_p<TAPS>(SA[q][0], v[q].lo, H);
@@ -406,14 +422,13 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
                     uint32_t a[NV];
 #pragma unroll
                     for (int k = 0; k < NV; ++k)
-                        a[k] = (MIRROR ? tap[q][k] : own[q] + (uint32_t)(k - NV / 2) * tap_step) + half;
-                    const P4 v = lean_row_pass<TAPS, DMODE, I * RB, false, MIRROR>(a, rev[q], H);
+                        a[k] = (MIRROR ? tap[q][k] : own[q] + (uint32_t)(k - NV / 2) * tap_step) + o_in;
+                    const P4 v = lean_row_pass<TAPS, DMODE, IMM_IN, false, MIRROR>(a, rev[q], H);
                     cv[q].lo = col_feed_p<TAPS>(SA[q][0], v.lo, H);
                     cv[q].hi = col_feed_p<TAPS>(SA[q][1], v.hi, H);
                 }
             }
             if (j >= 2 * C) {
-                constexpr int SW = (I - 2 * C + 8) & (kWRing - 1);  // w row j-2C
                 const bool store_c = (j >= 3 * C) && (j < j_store_end);
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
@@ -424,31 +439,29 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
                     P4 raw = rawc[q];
                     raw.lo = sub2(raw.lo, cv[q].lo);
                     raw.hi = sub2(raw.hi, cv[q].hi);
-                    if (act[q]) sts_p4_imm<W_OFF + SW * RB>(own[q], raw);
+                    if (act[q]) sts_p4_imm<W_OFF + IMM_SW>(own[q] + o_sw, raw);
                 }
                 c_ptr += c_step;
                 __syncwarp();
-                if (lane == 0) mbar_arrive_imm<8 * SW>(wbar0);
+                if (lane == 0) mbar_arrive_imm<IMM_SW / RB * 8>(wbar0 + (o_sw >> 11));
             }
         }
         if (j > 2 * C) {
-            constexpr int SP = (I - 1 - 2 * C + 16) & (kWRing - 1);  // w row j-1-2C (all threads' columns)
-            mbar_wait_imm<8 * SP>(wbar0, ((uint32_t)(j - 1 - 2 * C) >> 2) & 1u);
+            mbar_wait_imm<IMM_SP / RB * 8>(wbar0 + (o_sp >> 11), ((uint32_t)(j - 1 - 2 * C) >> 2) & 1u);
             if (tid == 0) {
                 // every warp is past part A of step j-1: input rows <= j-1-C are free
                 while (next_load < n_load && next_load - kInRing <= j - 1 - C) issue_load();
             }
-            constexpr int SE = (I - 1 - 3 * C + 16) & (kWRing - 1);  // own raw w of the P row completed in this step
             P4 roww[NG];
 #pragma unroll
-            for (int q = 0; q < NG; ++q) roww[q] = lds_p4_imm<W_OFF + SE * RB>(own[q]);
+            for (int q = 0; q < NG; ++q) roww[q] = lds_p4_imm<W_OFF + IMM_SE>(own[q] + o_se);
             P4 pw[NG];
             if constexpr (PAIR) {
                 uint32_t a[TAPS + PAIR];
 #pragma unroll
-                for (int k = 0; k < TAPS + PAIR; ++k) a[k] = MIRROR ? ptap[k] : own[0] + (uint32_t)(k - C) * tap_step;
+                for (int k = 0; k < TAPS + PAIR; ++k) a[k] = (MIRROR ? ptap[k] : own[0] + (uint32_t)(k - C) * tap_step) + o_sp;
                 P4 v[NG];
-                lean_row_pass_pair<TAPS, PAIR, W_OFF + SP * RB, true, MIRROR>(a, rev[0], H, v[0], v[1]);
+                lean_row_pass_pair<TAPS, PAIR, W_OFF + IMM_SP, true, MIRROR>(a, rev[0], H, v[0], v[1]);
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
                     pw[q].lo = col_feed_p<TAPS>(SB[q][0], v[q].lo, H);
@@ -459,8 +472,9 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
                 for (int q = 0; q < NG; ++q) {
                     uint32_t a[NV];
 #pragma unroll
-                    for (int k = 0; k < NV; ++k) a[k] = MIRROR ? tap[q][k] : own[q] + (uint32_t)(k - NV / 2) * tap_step;
-                    const P4 v = lean_row_pass<TAPS, DMODE, W_OFF + SP * RB, true, MIRROR>(a, rev[q], H);
+                    for (int k = 0; k < NV; ++k)
+                        a[k] = (MIRROR ? tap[q][k] : own[q] + (uint32_t)(k - NV / 2) * tap_step) + o_sp;
+                    const P4 v = lean_row_pass<TAPS, DMODE, W_OFF + IMM_SP, true, MIRROR>(a, rev[q], H);
                     pw[q].lo = col_feed_p<TAPS>(SB[q][0], v.lo, H);
                     pw[q].hi = col_feed_p<TAPS>(SB[q][1], v.hi, H);
                 }
@@ -478,6 +492,11 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
         }
     };
     auto run = [&](auto mirror) {
+        if constexpr (DYN) {
+#pragma unroll 1
+            for (int j = 0; j <= n_load; ++j) step(IC<0>{}, mirror, j, 0u, 0u, 0u);
+            return;
+        }
 #pragma unroll 1
         for (int jb = 0; jb <= n_load; jb += 4) {
             const uint32_t half = (jb & 4) ? 4u * RB : 0u;   // input slots 4..7 on odd iterations
@@ -576,10 +595,7 @@ static bool wow_packed_enabled() {
     return v != 0;
 }
 
-// WB_WOW_PAIR in the environment (A/B measurements): 0 keeps the half-row column groups at every dilation, 1 (default)
-// pairs columns from d = 32 on (M = 1), 2 also at d = 16 (M = 2) and d = 8 (M = 4).  Level 2 is measured and not the
-// default: stand-alone the d = 16 launch gains 7 us (48 -> 41), but inside wow() the two extra kernels cost more than
-// that -- every change of kernel inside a cascade starts with a cold instruction cache (profiles/r2_pair_levels.json).
+// WB_WOW_PAIR=0 in the environment keeps the half-row column groups at every dilation (A/B measurements).
 static int wow_pair_level() {
     static int v = -1;
     if (v < 0) {
@@ -589,37 +605,53 @@ static int wow_pair_level() {
     return v;
 }
 
-template <int TAPS, int M>
-static auto wow_pair_kernel(int sig_mode) -> void (*)(const ScaleParams) {
-    return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, 0, true, 0, M>
-                         : (sig_mode == 1 ? wow_rows_lean_kernel<TAPS, 0, true, 1, M> : wow_rows_lean_kernel<TAPS, 0, true, 2, M>);
+// Which lean kernels run with the step loop NOT unrolled (DYN).  Measured at 4096^2 (profiles/r2_fused_dyn.json): not
+// unrolled, a kernel is 22 - 33 KB instead of 54 - 92 KB and a change of kernel inside a cascade no longer costs ~5 us of
+// cold instruction cache, but the plain d % 4 == 0 kernels lose 2 us per launch in the steady state (47.1 -> 49.7,
+// 41.5 -> 43.4 us: no scheduling across steps); the d = 1 / d = 2 kernels lose nothing (39.8 us) and the kernels with
+// an inlined erff / hard threshold are faster (scales 0 / 1: 55.8 -> 52.3 us, paired: 65.5 -> 62.8 us).  Default: not
+// unrolled unless the kernel is the plain d % 4 == 0 one; WB_WOW_DYN=0 / 1 in the environment: never / always.
+static bool wow_dyn_for(int dmode, int sig_mode) {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("WB_WOW_DYN");
+        v = e ? (e[0] == '0' ? 0 : 1) : 2;
+    }
+    if (v < 2) return v != 0;
+    return dmode != 0 || sig_mode != 0;
+}
+
+template <int TAPS, int DMODE, bool HINTS, int M, bool DYN>
+static auto wow_lean_kernel_mode(int sig_mode) -> void (*)(const ScaleParams) {
+    return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 0, M, DYN>
+                         : (sig_mode == 1 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 1, M, DYN>
+                                          : wow_rows_lean_kernel<TAPS, DMODE, HINTS, 2, M, DYN>);
 }
 
 template <typename T, int TAPS, int DMODE, bool HINTS>
-static auto wow_kernel_for(bool packed, int pair, int sig_mode) -> void (*)(const ScaleParams) {
+static auto wow_kernel_for(bool packed, int pair, bool dyn, int sig_mode) -> void (*)(const ScaleParams) {
     if constexpr (sizeof(T) == 4) {
-        if constexpr (DMODE == 0 && HINTS) {
-            if (packed && pair == 1) return wow_pair_kernel<TAPS, 1>(sig_mode);
-            if (packed && pair == 2) return wow_pair_kernel<TAPS, 2>(sig_mode);
-            if constexpr (TAPS > 4) {
-                if (packed && pair == 4) return wow_pair_kernel<TAPS, 4>(sig_mode);
+        if constexpr (HINTS) {
+            if constexpr (DMODE == 0) {
+                if (packed && pair == 1)
+                    return dyn ? wow_lean_kernel_mode<TAPS, 0, true, 1, true>(sig_mode)
+                               : wow_lean_kernel_mode<TAPS, 0, true, 1, false>(sig_mode);
             }
+            if (packed && dyn) return wow_lean_kernel_mode<TAPS, DMODE, true, 0, true>(sig_mode);
         }
-        if (packed)
-            return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 0>
-                                 : (sig_mode == 1 ? wow_rows_lean_kernel<TAPS, DMODE, HINTS, 1>
-                                                  : wow_rows_lean_kernel<TAPS, DMODE, HINTS, 2>);
+        if (packed) return wow_lean_kernel_mode<TAPS, DMODE, HINTS, 0, false>(sig_mode);
     }
     return wow_rows_kernel<T, TAPS, DMODE, 2, HINTS>;
 }
 
-// Paired columns (x, x + M d): M = 1 from d = 32 on, M = 2 at d = 16, M = 4 at d = 8 (B3spline only: M < taps) -- the runs
-// of M d / 4 >= 8 consecutive vectors keep the LDS.128 of eight consecutive lanes conflict-free; 0 = half-row groups.
+// Paired columns (x, x + M d): M = 1 from d = 32 on (runs of d / 4 >= 8 consecutive vectors keep the LDS.128 of eight
+// consecutive lanes conflict-free).  M = 2 at d = 16 and M = 4 at d = 8 were built and measured (the kernel template
+// takes them): alone the d = 16 launch gains 7 us (48 -> 41), inside wow() the two additional kernels per cascade cost
+// more than that (0.611 -> 0.619 ms, profiles/r2_pair_levels.json) -- not instantiated.
 static int wow_pair_step(int taps, int d) {
-    const int level = wow_pair_level();
-    if (d < 8 || (d & (d - 1)) != 0 || level <= 0 || (level == 1 && d < 32)) return 0;
-    const int m = d >= 32 ? 1 : 32 / d;
-    return m < taps ? m : 0;
+    (void)taps;
+    if (d < 32 || (d & (d - 1)) != 0 || wow_pair_level() <= 0) return 0;
+    return 1;
 }
 
 template <typename T, int TAPS, int DMODE, bool HINTS>
@@ -627,11 +659,12 @@ static int launch_wow_h(const ScaleParams &p, int batch, const WowGeom &geo, cud
     // the lean kernel always runs 512 threads x 2 vectors on 16 KiB ring slots: use it when the row needs them
     const bool packed = sizeof(T) == 4 && p.W > 2048 && p.n_strips == 1 && wow_packed_enabled();
     const int pair = (packed && DMODE == 0 && HINTS) ? wow_pair_step(TAPS, p.d) : 0;
-    auto kern = wow_kernel_for<T, TAPS, DMODE, HINTS>(packed, pair, p.sig_mode);
+    const bool dyn = packed && HINTS && wow_dyn_for(DMODE, p.sig_mode);
+    auto kern = wow_kernel_for<T, TAPS, DMODE, HINTS>(packed, pair, dyn, p.sig_mode);
     const int nt = packed ? 512 : geo.nt;
     const size_t smem = packed ? (size_t)(kInRing + kWRing) * kLeanRB + 8 * (size_t)(kInRing + kWRing) : geo.smem;
-    static bool configured[13][64] = {};  // generic, lean x 3 significance modes, paired lean (M = 1, 2, 4) x 3; per device
-    const int kidx = packed ? 1 + p.sig_mode + 3 * (pair == 4 ? 3 : pair) : 0;
+    static bool configured[13][64] = {};  // generic, lean x 3 significance modes x {plain, paired} x {unrolled, not}; per device
+    const int kidx = packed ? 1 + p.sig_mode + 3 * pair + 6 * (dyn ? 1 : 0) : 0;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[kidx][dev]) {
