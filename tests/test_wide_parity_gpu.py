@@ -209,21 +209,28 @@ def test_lean_fused_wow_scale_vs_oracle(dt):
     report(f"lean fused wow scale {np.dtype(dt).name}: all dilations within tolerance")
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("sf", ["b3spline", "triangle"])
-def test_lean_k1_k3_every_dilation_vs_oracle(sf):
-    """The lean K1 (one cascade scale) and K3 (whitening of a raw detail plane) kernels on short frames of 1032 .. 4096
-    columns at EVERY dilation the single-reflection limit allows: from d = 32 on a thread's two column vectors are one
-    dilation step apart (paired columns), with partial pair blocks and masked second vectors at widths that are not a
-    multiple of 2 d (3000, 3592, 1032), and mirrored taps on both sides at the deep scales."""
+def test_lean_k1_k3_every_dilation_vs_oracle(sf, dt):
+    """The lean K1 (one cascade scale) and K3 (whitening of a raw detail plane) kernels on short frames of 1032 .. 11264
+    columns at EVERY dilation the single-reflection limit allows: from d = 32 (fp32) / 16 (fp64) on a thread's two column
+    vectors are one dilation step apart (paired columns), with partial pair blocks and masked second vectors at widths
+    that are not a multiple of 2 d (3000, 3592, 1032), and mirrored taps on both sides at the deep scales; rows wider
+    than one ring slot (8192, 11264 fp32; 2304 .. 4096 fp64) run as column strips with halo columns, the last strip
+    partial."""
     import wavelets_b200 as wb
     from wavelets_b200 import _lib, utils
     from scipy.special import erf
     lib = _lib.load(require_cuda=True)
     sfn = _sf(sf)(2)
     c_taps = len(sfn.coefficients_1d) // 2
+    f32 = dt == np.float32
     worst_c = worst_w = worst_k3 = 0.0
-    for (h, w) in ((40, 4096), (44, 3000), (36, 3592), (52, 2304), (33, 1032)):
-        img = smooth_field(h, w, 11 + w, np.float32)
+    shapes = ((40, 4096), (44, 3000), (36, 3592), (52, 2304), (33, 1032), (24, 8192), (20, 11264), (22, 6000))
+    for (h, w) in shapes:
+        if not f32 and w > 6000:
+            continue
+        img = smooth_field(h, w, 11 + w, dt)
         dev = torch.from_numpy(img).cuda()
         img64 = img.astype(np.float64)
         for s in range(0, 12):
@@ -232,7 +239,7 @@ def test_lean_k1_k3_every_dilation_vs_oracle(sf):
             c1, w1 = wb.atrous_scale(dev, s, sfn)
             c64 = orc.smooth(img64, sf, s, backend="numpy")
             ec, ew = orc.emax(c1.cpu().numpy(), c64), orc.emax(w1.cpu().numpy(), img64 - c64)
-            assert ec <= 1e-6 and ew <= 5e-6, (sf, w, s, ec, ew)
+            assert ec <= (1e-6 if f32 else 1e-14) and ew <= (5e-6 if f32 else 1e-13), (sf, w, s, ec, ew)
             # K3 on the raw plane this launch wrote: w' = w * erf(|w| / (sigma noise sigma_e)) * weight / sqrt(P)
             out = torch.empty_like(w1).unsqueeze(0)
             utils._whiten_scale(lib, w1.unsqueeze(0), out, s, sfn, 1, 2.0, 0.4, utils._Noise(host=0.9), 1.5)
@@ -241,10 +248,10 @@ def test_lean_k1_k3_every_dilation_vs_oracle(sf):
             p64[p64 <= 0] = 1e-15
             want = wr * erf(np.abs(wr / (2.0 * 0.9 * 0.4))) * (1.5 / np.sqrt(p64))
             ek = orc.emax(out[0].cpu().numpy(), want)
-            assert ek <= 1e-5, (sf, w, s, ek)
+            assert ek <= (1e-5 if f32 else 1e-12), (sf, w, s, ek)
             worst_c, worst_w, worst_k3 = max(worst_c, ec), max(worst_w, ew), max(worst_k3, ek)
-    report(f"lean K1 / K3 {sf} float32, every dilation, W in 1032..4096: worst E_max c {worst_c:.2e}  w {worst_w:.2e}  "
-           f"whitened {worst_k3:.2e}")
+    report(f"lean K1 / K3 {sf} {np.dtype(dt).name}, every dilation, W in 1032..11264: worst E_max c {worst_c:.2e}  "
+           f"w {worst_w:.2e}  whitened {worst_k3:.2e}")
 
 
 @pytest.mark.parametrize("sf", ["b3spline", "triangle"])

@@ -21,20 +21,24 @@ def main():
     ap.add_argument("--side", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=30)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--dtype", default="f32")
     args = ap.parse_args()
     lib = _lib.load(require_cuda=True)
     n = args.side
-    img = solar_like_device(n, torch.float32)
+    tdt = torch.float32 if args.dtype == "f32" else torch.float64
+    img = solar_like_device(n, tdt)
     sf = wb.B3spline(2)
     src = img.unsqueeze(0)
     c = torch.empty_like(src)
     o = torch.empty_like(src)
     nz = utils._Noise(dev=torch.tensor([1.0], dtype=torch.float64, device="cuda"))
-    res = {"tag": args.tag, "side": n, "env": {k: v for k, v in os.environ.items() if k.startswith("WB_")}}
-    res["fused_us"] = [round(1e3 * timed(lambda: utils._wow_scale_fused(lib, src, c, o, s, sf, 0, 0.0, 1.0, utils._Noise(), 1.0),
-                                         args.reps), 2) for s in range(10)]
-    res["fused_soft_us"] = [round(1e3 * timed(lambda: utils._wow_scale_fused(lib, src, c, o, s, sf, 1, 5.0, 0.2, nz, 1.0),
-                                              args.reps), 2) for s in range(10)]
+    res = {"tag": args.tag, "side": n, "dtype": args.dtype, "env": {k: v for k, v in os.environ.items() if k.startswith("WB_")}}
+    fusable = bool(utils._wow_scale_fused(lib, src, c, o, 3, sf, 0, 0.0, 1.0, utils._Noise(), 1.0))
+    if fusable:
+        res["fused_us"] = [round(1e3 * timed(lambda: utils._wow_scale_fused(lib, src, c, o, s, sf, 0, 0.0, 1.0, utils._Noise(), 1.0),
+                                             args.reps), 2) for s in range(10)]
+        res["fused_soft_us"] = [round(1e3 * timed(lambda: utils._wow_scale_fused(lib, src, c, o, s, sf, 1, 5.0, 0.2, nz, 1.0),
+                                                  args.reps), 2) for s in range(10)]
     from wavelets_b200.wavelets import atrous_scale
     w = torch.empty_like(src)
     res["k1_us"] = [round(1e3 * timed(lambda: atrous_scale(src, s, sf, out_c=c, out_w=w), args.reps), 2) for s in range(10)]
@@ -48,10 +52,13 @@ def main():
                         "alternating_4_5": round(1e3 * timed(lambda: seq([4, 5] * 4), args.reps) / 8, 2),
                         "grouped_0_1_4_5": round(1e3 * timed(lambda: seq([0] * 2 + [1] * 2 + [4] * 2 + [5] * 2), args.reps) / 8, 2),
                         "alternating_0_1_4_5": round(1e3 * timed(lambda: seq([0, 1, 4, 5] * 2), args.reps) / 8, 2)}
+    res["k3_soft_us"] = [round(1e3 * timed(lambda: utils._whiten_scale(lib, w, o, s, sf, 1, 5.0, 0.2, nz, 1.0), args.reps), 2)
+                         for s in range(10)]
+
     def fseq(order):
         for s in order:
             utils._wow_scale_fused(lib, src, c, o, s, sf, 0, 0.0, 1.0, utils._Noise(), 1.0)
-    res["switch_fused_us"] = {"grouped_0_1_4_5": round(1e3 * timed(lambda: fseq([0] * 2 + [1] * 2 + [4] * 2 + [5] * 2), args.reps) / 8, 2),
+    res["switch_fused_us"] = {} if not fusable else {"grouped_0_1_4_5": round(1e3 * timed(lambda: fseq([0] * 2 + [1] * 2 + [4] * 2 + [5] * 2), args.reps) / 8, 2),
                               "alternating_0_1_4_5": round(1e3 * timed(lambda: fseq([0, 1, 4, 5] * 2), args.reps) / 8, 2),
                               "grouped_4_5": round(1e3 * timed(lambda: fseq([4] * 4 + [5] * 4), args.reps) / 8, 2),
                               "alternating_4_5": round(1e3 * timed(lambda: fseq([4, 5] * 4), args.reps) / 8, 2)}

@@ -204,15 +204,20 @@ static constexpr int kLeanSlots = 8;
 // UNROLL: steps per iteration of the step loop, 8 (= the ring: every slot offset an immediate) or 4 (the ring's two
 // halves alternate: one more address term per access, HALF the code -- a 60 KB kernel does not fit the 32 KB
 // instruction cache level, and every change of kernel inside a cascade starts cold).
-template <int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0, int PAIR = 0, int UNROLL = 8>
+// T / RBK (round 2): float64 rows (one double per 64-bit lane: DFMA instead of FFMA2, see Lane<T>) and COLUMN STRIPS -- a
+// block stages columns [x0 - halo, x0 + wt + halo) of its strip in ring slots of RBK KiB (16: whole rows of <= 4096 fp32
+// columns, the geometry the kernel was written for; 24: strips of 4096 fp32 / 2048 fp64 columns with up to 1024 / 512
+// halo columns per side, i.e. rows wider than one slot at every dilation up to 512 / 256).
+template <typename T, int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0, int PAIR = 0, int UNROLL = 8,
+          int RBK = 16>
 __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams p) {
-    static_assert(PAIR == 0 || (DMODE == 0 && PAIR < TAPS), "paired columns need d % 4 == 0 and overlapping taps");
+    static_assert(PAIR == 0 || (DMODE == 0 && PAIR < TAPS), "paired columns need d % V == 0 and overlapping taps");
     static_assert(UNROLL == 8 || UNROLL == 4, "the step loop is unrolled by the ring or by half of it");
-    using T = float;
-    constexpr int V = 4, NG = 2;
+    constexpr int V = VecOf<T>::V, NG = 2;
     constexpr int C = TAPS / 2;
     constexpr int NV = PlanSize<TAPS, DMODE>::NV;
-    constexpr int RB = (int)kLeanRB;
+    constexpr int RB = RBK * 1024;
+    using L = Lane<T>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t in_base = smem_u32(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kLeanSlots * RB);
@@ -226,7 +231,10 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
+    // block -> (strip, chain residue r, segment g); whole-row launches have one strip
     int bx = blockIdx.x;
+    const int strip = bx % p.n_strips;
+    bx /= p.n_strips;
     const int r = bx % p.d;
     const int g = bx / p.d;
     const int frame = blockIdx.y;
@@ -236,7 +244,10 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
     const int n_out = min(p.seg, n_chain - i0);
     if (n_out <= 0) return;
     const int n_load = n_out + 2 * C;
-    const uint32_t row_bytes = (uint32_t)p.W * (uint32_t)sizeof(T);
+    const int x0 = strip * p.wt;
+    const int lo = max(0, x0 - p.halo_al);
+    const int hi = min(p.W, x0 + p.wt + p.halo_al);
+    const uint32_t row_bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(T);
 
     if (tid == 0) {
         for (int s = 0; s < kLeanSlots; ++s) {
@@ -251,7 +262,7 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
     if (warp == nwc) {
         // ---------------- producer warp: one lane streams the chain rows into the ring ----------------
         if (lane == 0) {
-            const long long foff = (long long)frame * p.in_bstride;
+            const long long foff = (long long)frame * p.in_bstride + lo;
             const uint64_t pol_in = policy_evict_first();  // c_s is dead once this launch has read it
             for (int j = 0; j < n_load; ++j) {
                 const int slot = j & (kLeanSlots - 1);
@@ -267,7 +278,7 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
     }
 
     // ---------------- consumer warps ----------------
-    const PackedTaps<TAPS> H;
+    const PackedTaps<TAPS, T> H;
     const uint64_t pol_keep = policy_evict_last();  // c_{s+1}: the next scale reads it back
     WhitenEpilogue<T> epi;
     if constexpr (OP == OP_WHITEN) epi.init(p, frame);
@@ -278,27 +289,30 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
     bool act[NG];
     int xg0 = 0;
     bool mirror_warp;
+    const int x_end = min(p.W, x0 + p.wt);  // columns [x0, x_end) are this block's
     if constexpr (PAIR) {
-        const int run = PAIR * (p.d >> 2), nvec = p.W >> 2;  // vectors between the two of a pair (>= 8), vectors per row
-        const int v0 = pair_first_vector(tid, run);
-        act[0] = v0 < nvec;
-        act[1] = v0 + run < nvec;
-        xg0 = act[0] ? v0 * V : 0;  // idle threads shadow the first pair of the row; only their stores are masked
-        own[0] = opaque_u32(in_base + (uint32_t)xg0 * (uint32_t)sizeof(T));
+        const int run = PAIR * (p.d / V);  // vectors between the two of a pair (>= 8)
+        const int xa = x0 + pair_first_vector(tid, run) * V, xb = xa + PAIR * p.d;
+        act[0] = xa < x_end;
+        act[1] = xb < x_end;
+        xg0 = act[0] ? xa : x0;  // idle threads shadow the first pair of the strip; only their stores are masked
+        own[0] = opaque_u32(in_base + (uint32_t)(xg0 - lo) * (uint32_t)sizeof(T));
         own[1] = opaque_u32(act[1] ? own[0] + (uint32_t)(PAIR * p.d) * (uint32_t)sizeof(T) : own[0]);
-        rev[0] = opaque_u32(make_pair_plan<TAPS, PAIR>(xg0, p.d, p.W, in_base, ptap));
+        rev[0] = opaque_u32(make_pair_plan<TAPS, PAIR, V>(xg0, p.d, p.W, lo, in_base, ptap));
 #pragma unroll
         for (int k = 0; k < TAPS + PAIR; ++k) ptap[k] = opaque_u32(ptap[k]);
         mirror_warp = __any_sync(0xffffffffu, rev[0] != 0 || !act[0]);
     } else {
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
-            int xg = (q * nt + tid) * V;
-            act[q] = xg < p.W;
-            if (!act[q]) xg = (p.W / 2) & ~(V - 1);  // idle threads shadow an interior vector; only their stores are masked
+            int xg = x0 + (q * nt + tid) * V;
+            act[q] = xg < x_end;
+            // idle threads shadow an interior vector of the strip (its middle for whole rows, where the dilation can be
+            // half the width; its first vector otherwise); only their stores are masked
+            if (!act[q]) xg = (p.n_strips == 1) ? ((p.W / 2) & ~(V - 1)) : x0;
             if (q == 0) xg0 = xg;
-            own[q] = opaque_u32(in_base + (uint32_t)xg * (uint32_t)sizeof(T));
-            const TapPlan<NV> tp = make_tap_plan<V, NV>(xg, DMODE == 0 ? p.d : V, p.W, 0);
+            own[q] = opaque_u32(in_base + (uint32_t)(xg - lo) * (uint32_t)sizeof(T));
+            const TapPlan<NV> tp = make_tap_plan<V, NV>(xg, DMODE == 0 ? p.d : V, p.W, lo);
 #pragma unroll
             for (int k = 0; k < NV; ++k) tap[q][k] = opaque_u32(in_base + (uint32_t)tp.off[k] * (uint32_t)sizeof(T));
             rev[q] = opaque_u32(tp.rev);
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
         constexpr int I = decltype(ic)::value;
         constexpr bool MIRROR = decltype(mirror)::value != 0;
         if (j >= n_load) return;
-        mbar_wait_imm<8 * I>(full0 + (half >> 11), par);  // 8 bytes of barrier per 16 KiB slot
+        mbar_wait_imm<8 * I>(full0 + (half ? 32u : 0u), par);  // 8 bytes of barrier per slot: the second half starts at 32
         P4 cv[NG];
         if constexpr (PAIR) {
             uint32_t a[TAPS + PAIR];
@@ -366,8 +380,8 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
                     P4 raw = lds_p4_imm<SC * RB>(own[q] + hc);
-                    raw.lo = epi.template apply2<MODE>(raw.lo, cv[q].lo);
-                    raw.hi = epi.template apply2<MODE>(raw.hi, cv[q].hi);
+                    raw.lo = epi.template apply_lane<MODE>(raw.lo, cv[q].lo);
+                    raw.hi = epi.template apply_lane<MODE>(raw.hi, cv[q].hi);
                     if (act[q]) stg_p4_cs(w_ptr + q * q_off, raw);
                 }
                 w_ptr += w_step;
@@ -381,8 +395,8 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
                 }
                 if (has_w) {
                     P4 raw = lds_p4_imm<SC * RB>(own[q] + hc);
-                    raw.lo = sub2(raw.lo, cv[q].lo);
-                    raw.hi = sub2(raw.hi, cv[q].hi);
+                    raw.lo = L::sub(raw.lo, cv[q].lo);
+                    raw.hi = L::sub(raw.hi, cv[q].hi);
                     if (act[q]) stg_p4_cs(w_ptr + q * q_off, raw);
                 }
             }
@@ -394,7 +408,7 @@ __global__ void __launch_bounds__(544) atrous_rows_lean_kernel(const ScaleParams
         if (j >= C) {
             // the raw row j-C is not needed any more: hand its slot back to the producer
             __syncwarp();
-            if (lane == 0) mbar_arrive_imm<8 * SC>(empty0 + (hc >> 11));
+            if (lane == 0) mbar_arrive_imm<8 * SC>(empty0 + (hc ? 32u : 0u));
         }
     };
     auto run = [&](auto mirror) {
@@ -501,16 +515,18 @@ static bool k1_lean_enabled() {
 // groups at every dilation (A/B measurements).  M = 2 at d = 16 and M = 4 at d = 8 were built and measured (the kernel
 // template takes them): no gain per launch and two more distinct kernels per cascade (0.336 -> 0.358 ms per transform
 // with the step loop unrolled by 8, profiles/r2_pair_levels.json) -- not instantiated.
-static int k1_pair_step(int taps, int d, int W, int nt) {
+static int k1_pair_step(int taps, int d, int cols, int nt, int V = 4) {
     static int level = -1;
     if (level < 0) {
         const char *e = getenv("WB_K1_PAIR");
         level = e ? atoi(e) : 1;
     }
     (void)taps;
-    if (d < 32 || (d & (d - 1)) != 0 || level <= 0) return 0;
-    // thread t owns vectors (t / run) 2 run + t % run and + run: the consumer threads must cover every first vector
-    const int run = d / 4, nvec = W / 4;
+    // runs of d / V >= 8 consecutive vectors: eight consecutive lanes read eight consecutive vectors
+    if (d < 8 * V || (d & (d - 1)) != 0 || level <= 0) return 0;
+    // thread t owns vectors (t / run) 2 run + t % run and + run of its strip: the consumer threads must cover every first
+    // vector of the `cols` columns a block owns
+    const int run = d / V, nvec = cols / V;
     const int need = ((nvec + 2 * run - 1) / (2 * run)) * run;
     return need <= nt ? 1 : 0;
 }
@@ -528,8 +544,8 @@ static int k1_unroll() {
 template <int TAPS, int DMODE, bool HINTS, int OP = OP_TRANSFORM, int MODE = 0, int PAIR = 0>
 static int launch_rows_lean(const ScaleParams &p, int batch, int nt, cudaStream_t st) {
     const bool u8 = k1_unroll() == 8;
-    auto kern = u8 ? atrous_rows_lean_kernel<TAPS, DMODE, HINTS, OP, MODE, PAIR, 8>
-                   : atrous_rows_lean_kernel<TAPS, DMODE, HINTS, OP, MODE, PAIR, 4>;
+    auto kern = u8 ? atrous_rows_lean_kernel<float, TAPS, DMODE, HINTS, OP, MODE, PAIR, 8>
+                   : atrous_rows_lean_kernel<float, TAPS, DMODE, HINTS, OP, MODE, PAIR, 4>;
     const size_t smem = (size_t)kLeanSlots * kLeanRB + 16 * (size_t)kLeanSlots;
     static bool configured[2][64] = {};  // per instantiation, per unroll, per device
     int dev = 0;
@@ -539,8 +555,49 @@ static int launch_rows_lean(const ScaleParams &p, int batch, int nt, cudaStream_
         if (e != cudaSuccess) return (int)e;
         if (dev >= 0 && dev < 64) configured[u8][dev] = true;
     }
-    dim3 grid((unsigned)((long long)p.d * p.n_seg), (unsigned)batch);
+    dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
     return launch_pdl<ScaleParams>(kern, grid, dim3((unsigned)(nt + 32)), smem, st, p);
+}
+
+// The lean kernel on column strips / float64 rows: ring slots of 24 KiB (a strip of 16 KiB plus the halo columns of
+// both sides), L2 hints on, step loop unrolled by half the ring.
+static constexpr int kLeanStripKiB = 24;
+
+// WB_K1_LEAN_STRIPS=0 in the environment keeps the generic kernel for float64 and for rows wider than one ring slot.
+static bool k1_lean_strips_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("WB_K1_LEAN_STRIPS");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+template <typename T, int TAPS, int DMODE, int OP, int MODE, int PAIR>
+static int launch_rows_lean_strip_m(const ScaleParams &p, int batch, int nt, cudaStream_t st) {
+    auto kern = atrous_rows_lean_kernel<T, TAPS, DMODE, true, OP, MODE, PAIR, 4, kLeanStripKiB>;
+    const size_t smem = (size_t)kLeanSlots * kLeanStripKiB * 1024 + 16 * (size_t)kLeanSlots;
+    static bool configured[64] = {};  // per instantiation, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
+    return launch_pdl<ScaleParams>(kern, grid, dim3((unsigned)(nt + 32)), smem, st, p);
+}
+
+template <typename T, int TAPS, int DMODE, int OP, int PAIR>
+static int launch_rows_lean_strip(const ScaleParams &p, int batch, int nt, cudaStream_t st) {
+    if constexpr (OP == OP_WHITEN) {
+        if constexpr (sizeof(T) == 4) {
+            if (p.sig_mode == 1) return launch_rows_lean_strip_m<T, TAPS, DMODE, OP, 1, PAIR>(p, batch, nt, st);
+        }
+        if (p.sig_mode == 2) return launch_rows_lean_strip_m<T, TAPS, DMODE, OP, 2, PAIR>(p, batch, nt, st);
+    }
+    return launch_rows_lean_strip_m<T, TAPS, DMODE, OP, 0, PAIR>(p, batch, nt, st);
 }
 
 template <typename T, int TAPS, int OP>
@@ -583,6 +640,31 @@ static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
                 if (dmode == 2) return WB_LEANW(2);
 #undef WB_LEANW_P
 #undef WB_LEANW
+            }
+        }
+        // float64 rows, and fp32 rows wider than one 16 KiB ring slot (column strips): the lean kernel on 24 KiB slots when a
+        // staged row (strip + halo columns) fits one.  These launches stream footprints far beyond L2 and sit at what a
+        // 1-read : 2-write stream reaches there (5.4 - 5.5 TB/s) with either kernel; measured (profiles/r2_wide_rows.json):
+        // fp32 strips 2 - 11 % faster at d >= 4 (kept; d < 4 keeps the generic kernel), float64 K1 equal within 2 % except
+        // with paired columns (d >= 16: 1 - 5 us faster, kept), float64 K3 12 - 22 us faster per 4096^2 plane except with
+        // the soft threshold (the inlined double-precision erf: 10 us slower, generic kept).
+        if ((sizeof(T) == 8 || p.n_strips > 1) && cfg.ng == 2 && cfg.slots == kLeanSlots && p.l2_hints &&
+            (long long)p.row_stride * (long long)sizeof(T) <= (long long)kLeanStripKiB * 1024 &&
+            (long long)p.row_stride * (long long)sizeof(T) > 8 * 1024 && k1_lean_enabled() && k1_lean_strips_enabled() &&
+            !(scale < 32 && g_override_set[scale])) {
+            const int cols = p.n_strips == 1 ? p.W : p.wt;
+            const bool pair = dmode == 0 && k1_pair_step(TAPS, p.d, cols, cfg.nt, V) == 1;
+            if constexpr (sizeof(T) == 4) {
+                if (pair) return launch_rows_lean_strip<T, TAPS, 0, OP, 1>(p, batch, cfg.nt, st);
+                if (dmode == 0) return launch_rows_lean_strip<T, TAPS, 0, OP, 0>(p, batch, cfg.nt, st);
+            } else if constexpr (OP == OP_TRANSFORM) {
+                if (pair) return launch_rows_lean_strip<T, TAPS, 0, OP, 1>(p, batch, cfg.nt, st);
+            } else {
+                if (p.sig_mode != 1) {
+                    if (pair) return launch_rows_lean_strip<T, TAPS, 0, OP, 1>(p, batch, cfg.nt, st);
+                    if (dmode == 0) return launch_rows_lean_strip<T, TAPS, 0, OP, 0>(p, batch, cfg.nt, st);
+                    if (dmode == 1) return launch_rows_lean_strip<T, TAPS, 1, OP, 0>(p, batch, cfg.nt, st);
+                }
             }
         }
 #define WB_LAUNCH(DM)                                                                   \

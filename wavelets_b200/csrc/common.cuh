@@ -186,18 +186,38 @@ __device__ __forceinline__ P4 lds_p4(uint32_t a) {
 __device__ __forceinline__ void sts_p4(uint32_t a, const P4 &v) {
     asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(v.lo), "l"(v.hi) : "memory");
 }
-__device__ __forceinline__ void stg_p4(float *p, const P4 &v) {
+__device__ __forceinline__ void stg_p4(void *p, const P4 &v) {
     asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(v.lo), "l"(v.hi) : "memory");
 }
-__device__ __forceinline__ void stg_p4_cs(float *p, const P4 &v) {
+__device__ __forceinline__ void stg_p4_cs(void *p, const P4 &v) {
     asm volatile("st.global.cs.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(v.lo), "l"(v.hi) : "memory");
 }
-__device__ __forceinline__ void stg_p4_hint(float *p, const P4 &v, uint64_t policy) {
+__device__ __forceinline__ void stg_p4_hint(void *p, const P4 &v, uint64_t policy) {
     asm volatile("st.global.L2::cache_hint.v2.b64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(v.lo), "l"(v.hi), "l"(policy)
                  : "memory");
 }
 // the mirrored vector read backwards
 __device__ __forceinline__ P4 reverse_p4(const P4 &t) { return P4{swap2(t.hi), swap2(t.lo)}; }
+
+// Lane arithmetic of the lean kernels: a 16-byte vector travels as two 64-bit registers -- two packed fp32 pixels each
+// (float: FFMA2 / FMUL2 / FADD2) or one double each (DFMA / DMUL / DADD).  Same operations, same order, per dtype.
+template <typename T> struct Lane;
+template <> struct Lane<float> {
+    static __device__ __forceinline__ u64 mul(u64 a, u64 b) { return mul2(a, b); }
+    static __device__ __forceinline__ u64 fma(u64 a, u64 b, u64 c) { return fma2(a, b, c); }
+    static __device__ __forceinline__ u64 sub(u64 a, u64 b) { return sub2(a, b); }
+    static __device__ __forceinline__ u64 bcast(float h) { return pk2(h, h); }
+    static __device__ __forceinline__ P4 reverse(const P4 &t) { return reverse_p4(t); }
+};
+template <> struct Lane<double> {
+    static __device__ __forceinline__ double d(u64 a) { return __longlong_as_double((long long)a); }
+    static __device__ __forceinline__ u64 u(double a) { return (u64)__double_as_longlong(a); }
+    static __device__ __forceinline__ u64 mul(u64 a, u64 b) { return u(__dmul_rn(d(a), d(b))); }
+    static __device__ __forceinline__ u64 fma(u64 a, u64 b, u64 c) { return u(__fma_rn(d(a), d(b), d(c))); }
+    static __device__ __forceinline__ u64 sub(u64 a, u64 b) { return u(__dsub_rn(d(a), d(b))); }
+    static __device__ __forceinline__ u64 bcast(double h) { return u(h); }
+    static __device__ __forceinline__ P4 reverse(const P4 &t) { return P4{t.hi, t.lo}; }
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // Programmatic dependent launch: the scale kernels of a cascade are launched back to back on one stream, each one

@@ -267,11 +267,11 @@ __device__ __forceinline__ T col_feed(T (&S)[TAPS - 1], T v) {
 // Packed fp32x2 forms of the row pass and of the running column sums (fp32, DMODE 0 or 2: every tap of a pixel pair
 // is again an aligned pair).  Same operations in the same order as row_pass_b / col_feed, two pixels per issue slot.
 // ---------------------------------------------------------------------------------------------------------------
-template <int TAPS> struct PackedTaps {
+template <int TAPS, typename T = float> struct PackedTaps {
     u64 h[TAPS];
     __device__ __forceinline__ PackedTaps() {
 #pragma unroll
-        for (int k = 0; k < TAPS; ++k) h[k] = pk2(Taps<float, TAPS>::h(k), Taps<float, TAPS>::h(k));
+        for (int k = 0; k < TAPS; ++k) h[k] = Lane<T>::bcast(Taps<T, TAPS>::h(k));
     }
 };
 
@@ -314,12 +314,12 @@ __device__ __forceinline__ P4 row_pass_p(uint32_t base, const BytePlan<PlanSize<
     return row_pass_p_impl<TAPS, DMODE, true>(base, tp, H);
 }
 
-template <int TAPS>
-__device__ __forceinline__ u64 col_feed_p(u64 (&S)[TAPS - 1], u64 v, const PackedTaps<TAPS> &H) {
-    const u64 out = fma2(H.h[TAPS - 1], v, S[0]);
+template <int TAPS, typename T>
+__device__ __forceinline__ u64 col_feed_p(u64 (&S)[TAPS - 1], u64 v, const PackedTaps<TAPS, T> &H) {
+    const u64 out = Lane<T>::fma(H.h[TAPS - 1], v, S[0]);
 #pragma unroll
-    for (int t = 0; t + 2 < TAPS; ++t) S[t] = fma2(H.h[TAPS - 2 - t], v, S[t + 1]);
-    S[TAPS - 2] = mul2(H.h[0], v);
+    for (int t = 0; t + 2 < TAPS; ++t) S[t] = Lane<T>::fma(H.h[TAPS - 2 - t], v, S[t + 1]);
+    S[TAPS - 2] = Lane<T>::mul(H.h[0], v);
     return out;
 }
 
@@ -357,9 +357,10 @@ template <int OFF> __device__ __forceinline__ void mbar_arrive_imm(uint32_t bar0
 // SQUARE filters the squares of the staged values (the local power reads the raw w_s rows).  MIRROR (warp-uniform
 // variant for warps that own border columns): a reflected tap is the mirrored vector read backwards -- a per-thread
 // select, no branch.
-template <int TAPS, int DMODE, int OFF, bool SQUARE, bool MIRROR>
+template <int TAPS, int DMODE, int OFF, bool SQUARE, bool MIRROR, typename T>
 __device__ __forceinline__ P4 lean_row_pass(const uint32_t (&a)[PlanSize<TAPS, DMODE>::NV], unsigned rev,
-                                            const PackedTaps<TAPS> &H) {
+                                            const PackedTaps<TAPS, T> &H) {
+    using L = Lane<T>;
     constexpr int C = TAPS / 2;
     constexpr int NV = PlanSize<TAPS, DMODE>::NV;
     P4 t[NV];
@@ -368,21 +369,31 @@ __device__ __forceinline__ P4 lean_row_pass(const uint32_t (&a)[PlanSize<TAPS, D
         t[k] = lds_p4_imm<OFF>(a[k]);
         if constexpr (MIRROR) {
             const bool m = (rev >> k) & 1u;
-            const P4 u = reverse_p4(t[k]);
+            const P4 u = L::reverse(t[k]);
             t[k].lo = m ? u.lo : t[k].lo;
             t[k].hi = m ? u.hi : t[k].hi;
         }
         if constexpr (SQUARE) {
-            t[k].lo = mul2(t[k].lo, t[k].lo);
-            t[k].hi = mul2(t[k].hi, t[k].hi);
+            t[k].lo = L::mul(t[k].lo, t[k].lo);
+            t[k].hi = L::mul(t[k].hi, t[k].hi);
         }
     }
     P4 acc;
     if constexpr (DMODE == 0) {
 #pragma unroll
         for (int k = 0; k < TAPS; ++k) {
-            acc.lo = (k == 0) ? mul2(H.h[0], t[k].lo) : fma2(H.h[k], t[k].lo, acc.lo);
-            acc.hi = (k == 0) ? mul2(H.h[0], t[k].hi) : fma2(H.h[k], t[k].hi, acc.hi);
+            acc.lo = (k == 0) ? L::mul(H.h[0], t[k].lo) : L::fma(H.h[k], t[k].lo, acc.lo);
+            acc.hi = (k == 0) ? L::mul(H.h[0], t[k].hi) : L::fma(H.h[k], t[k].hi, acc.hi);
+        }
+    } else if constexpr (sizeof(T) == 8) {
+        // float64, d == 1: previous, current, next vector as six doubles; tap k of element e is win[2 + e + (k - C)]
+        static_assert(DMODE == 1, "float64 vectors hold two elements: d == 1 is the only dilation below the vector width");
+        const u64 win[6] = {t[0].lo, t[0].hi, t[1].lo, t[1].hi, t[2].lo, t[2].hi};
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            const int i = 2 + (k - C);
+            acc.lo = (k == 0) ? L::mul(H.h[0], win[i]) : L::fma(H.h[k], win[i], acc.lo);
+            acc.hi = (k == 0) ? L::mul(H.h[0], win[i + 1]) : L::fma(H.h[k], win[i + 1], acc.hi);
         }
     } else if constexpr (DMODE == 2) {
         // d == 2: previous, current, next vector as six pixel pairs; every tap of a pair is again an aligned pair
@@ -420,30 +431,31 @@ __device__ __forceinline__ P4 lean_row_pass(const uint32_t (&a)[PlanSize<TAPS, D
 // overlap in TAPS - M vectors, so TAPS + M LDS.128 (and squarings) serve two outputs instead of 2 TAPS -- the lean
 // kernels are limited by shared-memory wavefronts and LDS latency before arithmetic.  Every output sums the same
 // values in the same order as lean_row_pass: bit-identical planes.
-template <int TAPS, int M, int OFF, bool SQUARE, bool MIRROR>
-__device__ __forceinline__ void lean_row_pass_pair(const uint32_t (&a)[TAPS + M], unsigned rev, const PackedTaps<TAPS> &H,
+template <int TAPS, int M, int OFF, bool SQUARE, bool MIRROR, typename T>
+__device__ __forceinline__ void lean_row_pass_pair(const uint32_t (&a)[TAPS + M], unsigned rev, const PackedTaps<TAPS, T> &H,
                                                    P4 &o0, P4 &o1) {
+    using L = Lane<T>;
     P4 t[TAPS + M];
 #pragma unroll
     for (int k = 0; k < TAPS + M; ++k) {
         t[k] = lds_p4_imm<OFF>(a[k]);
         if constexpr (MIRROR) {
             const bool m = (rev >> k) & 1u;
-            const P4 u = reverse_p4(t[k]);
+            const P4 u = L::reverse(t[k]);
             t[k].lo = m ? u.lo : t[k].lo;
             t[k].hi = m ? u.hi : t[k].hi;
         }
         if constexpr (SQUARE) {
-            t[k].lo = mul2(t[k].lo, t[k].lo);
-            t[k].hi = mul2(t[k].hi, t[k].hi);
+            t[k].lo = L::mul(t[k].lo, t[k].lo);
+            t[k].hi = L::mul(t[k].hi, t[k].hi);
         }
     }
 #pragma unroll
     for (int k = 0; k < TAPS; ++k) {
-        o0.lo = (k == 0) ? mul2(H.h[0], t[k].lo) : fma2(H.h[k], t[k].lo, o0.lo);
-        o0.hi = (k == 0) ? mul2(H.h[0], t[k].hi) : fma2(H.h[k], t[k].hi, o0.hi);
-        o1.lo = (k == 0) ? mul2(H.h[0], t[k + M].lo) : fma2(H.h[k], t[k + M].lo, o1.lo);
-        o1.hi = (k == 0) ? mul2(H.h[0], t[k + M].hi) : fma2(H.h[k], t[k + M].hi, o1.hi);
+        o0.lo = (k == 0) ? L::mul(H.h[0], t[k].lo) : L::fma(H.h[k], t[k].lo, o0.lo);
+        o0.hi = (k == 0) ? L::mul(H.h[0], t[k].hi) : L::fma(H.h[k], t[k].hi, o0.hi);
+        o1.lo = (k == 0) ? L::mul(H.h[0], t[k + M].lo) : L::fma(H.h[k], t[k + M].lo, o1.lo);
+        o1.hi = (k == 0) ? L::mul(H.h[0], t[k + M].hi) : L::fma(H.h[k], t[k + M].hi, o1.hi);
     }
 }
 
@@ -452,19 +464,20 @@ __device__ __forceinline__ void lean_row_pass_pair(const uint32_t (&a)[TAPS + M]
 // (conflict-free LDS.128) and a warp stores runs of >= 128 contiguous bytes.
 __device__ __forceinline__ int pair_first_vector(int tid, int run) { return (tid / run) * 2 * run + (tid % run); }
 
-// The TAPS + M tap addresses (slot 0) of a pair whose first vector starts at column x0, with the symmetric border:
-// returns the mirror bits.  Taps that belong only to a masked second vector may fall outside one reflection: clamped.
-template <int TAPS, int M>
-__device__ __forceinline__ unsigned make_pair_plan(int x0, int d, int W, uint32_t base, uint32_t (&a)[TAPS + M]) {
+// The TAPS + M tap addresses (slot 0; the staged row starts at column lo) of a pair whose first vector starts at
+// column x0, with the symmetric border: returns the mirror bits.  V = elements per 16-byte vector.  Taps that belong
+// only to a masked second vector may fall outside one reflection: clamped.
+template <int TAPS, int M, int V = 4>
+__device__ __forceinline__ unsigned make_pair_plan(int x0, int d, int W, int lo, uint32_t base, uint32_t (&a)[TAPS + M]) {
     constexpr int C = TAPS / 2;
     unsigned rv = 0;
 #pragma unroll
     for (int k = 0; k < TAPS + M; ++k) {
         const int pc = x0 + (k - C) * d;
         const bool left = pc < 0, right = pc >= W;
-        int q = left ? (-4 - pc) : (right ? (2 * W - 4 - pc) : pc);
-        if (q < 0 || q > W - 4) q = 0;
-        a[k] = base + (uint32_t)q * 4u;
+        int q = left ? (-V - pc) : (right ? (2 * W - V - pc) : pc);
+        if (q < lo || q > W - V) q = lo;
+        a[k] = base + (uint32_t)(q - lo) * (uint32_t)(16 / V);
         if (left || right) rv |= 1u << k;
     }
     return rv;

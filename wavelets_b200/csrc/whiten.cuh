@@ -80,6 +80,20 @@ template <typename T> struct WhitenEpilogue {
         }
         return mul2(w2, g2);
     }
+    // One 64-bit lane of a lean kernel: two packed fp32 pixels (apply2) or one double (apply with the compiled-in mode).
+    template <int MODE>
+    __device__ __forceinline__ u64 apply_lane(u64 w, u64 power) const {
+        if constexpr (sizeof(T) == 4) {
+            return apply2<MODE>(w, power);
+        } else {
+            double x = Lane<double>::d(w), pw = Lane<double>::d(power);
+            pw = (pw <= 0.0) ? 1e-15 : pw;
+            const double g = weight * rsqrt(pw);
+            if (MODE == 1 && mode == 1) x = x * erf(fabs(x * inv_thr));
+            else if (MODE == 2 && mode == 2) x = (fabs(x) > thr_cmp) ? x : 0.0;
+            return Lane<double>::u(x * g);
+        }
+    }
 };
 
 }  // namespace wb

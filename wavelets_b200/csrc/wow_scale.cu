@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
         xg0 = act[0] ? v0 * V : 0;  // idle threads shadow the first pair of the row; only their stores are masked
         own[0] = opaque_u32(in_base + (uint32_t)xg0 * (uint32_t)sizeof(T));
         own[1] = opaque_u32(act[1] ? own[0] + PAIR * tap_step : own[0]);
-        const unsigned rv = make_pair_plan<TAPS, PAIR>(xg0, p.d, p.W, in_base, ptap);
+        const unsigned rv = make_pair_plan<TAPS, PAIR>(xg0, p.d, p.W, 0, in_base, ptap);
         rev[0] = rv;
         mirror_warp = __any_sync(0xffffffffu, rv != 0 || !act[0]);
         if (mirror_warp) {
