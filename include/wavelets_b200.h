@@ -314,6 +314,31 @@ int wb_synthesis(const void *planes, int nplanes, long long plane_stride, long l
                  long long in_bstride, void *out, long long out_bstride, int dtype, void *stream);
 
 /*
+ * The whole WOW pipeline of a stack of frames in one call -- the loop of `wow` (plain or bilateral cascade) with whitening
+ * (watroo/utils.py:172-205: per scale the smooth + detail of watroo/wavelets.py:35-45,:442, the local power, the
+ * significance and the weighting; np.std and the rescale of the residual plane, :185-189,:203; np.sum, :205): per scale
+ * wb_wow_scale, or wb_atrous_scale [+ wb_abs_median] + wb_wow_whiten_scale where the fused kernel declines the shape or
+ * the MAD noise must first be estimated from the raw w_0; then wb_plane_moments + wb_residual_rescale + wb_synthesis.
+ * Bit-identical to issuing those calls one by one; it exists for frames small enough that a host-language loop is
+ * slower than the device (interpreter + FFI time per launch).
+ *   planes  (batch, n_scales+1, H, W) contiguous: the whitened coefficients (out)
+ *   scratch (3, batch, H, W): two ping-pong smooth planes and one raw detail plane
+ *   recon   (batch, H, W): the sum of the planes (out)
+ *   weights[n_scales+1], sigmas[n_scales] (denoise coefficient per scale, 0 = no threshold), sigma_e[n_scales]: HOST arrays
+ *   var_factors: NULL = plain cascade; else HOST array [n_scales] of the bilateral variance factors of
+ *   wb_atrous_scale_bilateral (watroo/wavelets.py:433-440): every scale then runs K2 + the whitening pass
+ *   soft != 0: erf significance, else hard masks.  Noise: estimate_noise == 0 -> noise_dev[frame] when non-NULL, else
+ *   noise_host; estimate_noise != 0 -> the MAD estimate is written to noise_dev[batch] at the first scale that
+ *   thresholds (from the raw w_0 at scale 0, from the already whitened plane 0 later: watroo/wavelets.py:131-132).
+ *   workspace: wb_wow_cascade_workspace_bytes(dtype, batch, H*W) bytes of device memory.
+ */
+size_t wb_wow_cascade_workspace_bytes(int dtype, int batch, long long n);
+int wb_wow_cascade(const void *in, long long in_pitch, long long in_bstride, void *planes, void *scratch, void *recon,
+                   int batch, int H, int W, int n_scales, int taps, int dtype, const double *weights, const double *sigmas,
+                   const double *sigma_e, const double *var_factors, int soft, double noise_host, double *noise_dev,
+                   int estimate_noise, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
  * n standard-normal float32 samples (Philox4x32-10 + Box-Muller), the device stand-in for
  * np.random.normal(...).astype(np.float32) of compute_noise_weights (watroo/wavelets.py:225).
  * `offset` advances the counter so that successive calls with one seed give independent fields.

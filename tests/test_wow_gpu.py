@@ -240,6 +240,50 @@ def test_wow_batch_matches_single_frames():
     assert np.array_equal(rb[0].cpu().numpy(), r0)
 
 
+def test_wow_c_cascade_equals_python_loop():
+    """wb_wow_cascade (the whole WOW pipeline, plain or bilateral, in one library call) against the Python loop over the same entry
+    points, bit for bit: default, MAD noise from the raw w_0 (scale 0) and from the whitened plane 0 (first threshold at
+    scale 1), given noise (host scalar and device scalar), hard thresholds, weights, Triangle, float64, shapes the fused
+    kernel declines (two-pass inside the call), batches."""
+    import wavelets_b200 as wb
+    from wavelets_b200 import utils
+    cases = [((256, 256), np.float32, {}), ((256, 256), np.float32, {"denoise_coefficients": [5, 2]}),
+             ((192, 320), np.float32, {"denoise_coefficients": [0, 3, 1]}),
+             ((130, 1024), np.float32, {"denoise_coefficients": [4, 2], "noise": 0.7}),
+             ((128, 2304), np.float32, {"denoise_coefficients": [4], "soft_threshold": False, "weights": [0.5, 2, 1.5]}),
+             ((96, 201), np.float32, {"denoise_coefficients": [3, 1]}),                       # W % 4 != 0: generic kernels
+             ((160, 160), np.float64, {"denoise_coefficients": [5, 2], "scaling_function": wb.Triangle}),
+             ((64, 2560), np.float64, {"denoise_coefficients": [2]}),                         # fp64 beyond the fused kernel
+             ((256, 256), np.float32, {"bilateral": 1, "denoise_coefficients": [5, 2]}),
+             ((96, 1536), np.float32, {"bilateral": [1, 2], "denoise_coefficients": [0, 3], "bilateral_scaling": True}),
+             ((128, 128), np.float64, {"bilateral": 1, "noise": 0.5, "denoise_coefficients": [4, 1]})]
+    try:
+        for shape, dt, kw in cases:
+            img = orc.solar_like(max(shape), seed=3, flux=0.05, dtype=dt)[:shape[0], :shape[1]].copy()
+            dev = torch.from_numpy(img).cuda()
+            utils.C_CASCADE = True
+            r1, c1 = wb.wow(dev, **kw)
+            utils.C_CASCADE = False
+            r0, c0 = wb.wow(dev, **kw)
+            assert torch.equal(r1, r0) and torch.equal(c1.data, c0.data), (shape, dt, kw)
+            assert (c1.noise is None and c0.noise is None) or c1.noise == c0.noise, (shape, kw)
+        dev_noise = torch.tensor([0.7], dtype=torch.float64, device="cuda")
+        img = torch.from_numpy(orc.solar_like(256, seed=5, flux=0.05, dtype=np.float32)).cuda()
+        utils.C_CASCADE = True
+        r1, c1 = wb.wow(img, denoise_coefficients=[4, 2], noise=dev_noise)
+        utils.C_CASCADE = False
+        r0, c0 = wb.wow(img, denoise_coefficients=[4, 2], noise=dev_noise)
+        assert torch.equal(r1, r0) and torch.equal(c1.data, c0.data)
+        frames = np.stack([orc.solar_like(256, seed=s, flux=0.05, dtype=np.float32) for s in (1, 2, 3)])
+        utils.C_CASCADE = True
+        rb1, pb1, nb1 = wb.wow_batch(frames, denoise_coefficients=[5, 2])
+        utils.C_CASCADE = False
+        rb0, pb0, nb0 = wb.wow_batch(frames, denoise_coefficients=[5, 2])
+        assert torch.equal(rb1, rb0) and torch.equal(pb1, pb0) and torch.equal(nb1, nb0)
+    finally:
+        utils.C_CASCADE = True
+
+
 def test_wow_stream_of_host_frames_matches_per_frame_calls():
     """wow_stream(): host frames in, host reconstructions out on three streams with one set of device buffers per frame
     in flight; every frame must equal wow(frame)[0] bit for bit, for the fused options (planned once), for the options

@@ -71,6 +71,10 @@ SIGNATURES = {
     "wb_residual_rescale": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_int, _c_vp, _c_dbl, _c_vp]),
     "wb_synthesis": (_c_int, [_c_vp, _c_int, _c_ll, _c_ll, _c_int, _c_ll, _c_vp, _c_ll, _c_int, _c_vp]),
     "wb_randn_f32": (_c_int, [_c_vp, _c_ll, _c_ull, _c_ull, _c_vp]),
+    "wb_wow_cascade_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_ll]),
+    "wb_wow_cascade": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                ctypes.POINTER(_c_dbl), ctypes.POINTER(_c_dbl), ctypes.POINTER(_c_dbl),
+                                ctypes.POINTER(_c_dbl), _c_int, _c_dbl, _c_vp, _c_int, _c_vp, _c_sz, _c_vp]),
     "wb_filter2d": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_ll, _c_ll, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "wb_atrous_axis": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_ll, _c_ll, _c_ll, _c_int, _c_int, _c_int, _c_int, _c_vp]),
 }

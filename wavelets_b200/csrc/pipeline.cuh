@@ -563,18 +563,22 @@ inline bool plan_fast(ScaleParams &p, int taps, int esize, int batch, int scale,
     int seg = cfg.seg;
     if (seg <= 0) {
         // One full wave: as many equal segments as there are block slots (SMs x resident blocks), so that no SM
-        // idles in a partial last wave, but never shorter than 4x the (taps-1)-row halo.
+        // idles in a partial last wave, but never shorter than the taps.
         const long long chains = (long long)p.n_strips * (p.d < p.H ? p.d : p.H) * batch;
         const size_t smem = (size_t)slots * p.row_stride * esize + 16 * (size_t)slots;
         int occ = (int)(kMaxSmem / (smem + 1024));
         const int occ_regs = 65536 / ((cfg.nt + 32) * kRegsPerThread);
         if (occ > occ_regs) occ = occ_regs;
+        // the lean fp32 kernels (whole rows wider than 1024 columns, see dispatch in atrous_scale.cu) always stage 16 KiB
+        // ring slots: one block per SM whatever the row width
+        if (esize == 4 && p.n_strips == 1 && p.W > 1024 && cfg.ng == 2 && slots == 8) occ = 1;
         if (occ < 1) occ = 1;
         const long long slots_total = (long long)device_sm_count() * occ;
         long long per_chain = slots_total / chains;  // segments per chain that still fit in one wave
         if (per_chain < 1) per_chain = 1;
         seg = (int)((n_max + per_chain - 1) / per_chain);
-        if (seg < 8 * c) seg = 8 * c;
+        // (never shorter than the taps; small frames are bound by the number of steps per block, not by the halo bytes)
+        if (seg < 2 * c) seg = 2 * c;
     }
     if (seg > n_max) seg = n_max;
     p.seg = seg;

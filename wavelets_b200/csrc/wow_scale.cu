@@ -233,15 +233,19 @@ __global__ void __launch_bounds__(512, 1) wow_rows_kernel(const ScaleParams p) {
 // values: one more address term per shared-memory access) and the kernel is a quarter of the code.  The unrolled
 // kernel (60 - 90 KB) does not fit the instruction cache levels below L2, and every change of kernel inside a cascade
 // starts cold (see atrous_rows_lean_kernel).
-template <int TAPS, int DMODE, bool HINTS, int MODE, int PAIR = 0, bool DYN = false>
-__global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams p) {
+// NTK: threads per block = half the vectors of the widest row the instantiation takes -- 512 (rows of 2049 .. 4096
+// columns, 16 KiB ring slots, one block per SM) or 256 (1025 .. 2048 columns, 8 KiB slots, two blocks per SM).
+template <int TAPS, int DMODE, bool HINTS, int MODE, int PAIR = 0, bool DYN = false, int NTK = 512>
+__global__ void __launch_bounds__(NTK, NTK == 512 ? 1 : 2) wow_rows_lean_kernel(const ScaleParams p) {
     static_assert(PAIR == 0 || (DMODE == 0 && PAIR < TAPS), "paired columns need d % 4 == 0 and overlapping taps");
+    static_assert(NTK == 512 || NTK == 256, "block sizes the ring geometry was laid out for");
     using T = float;
-    constexpr int V = 4, NG = 2, NT = 512;
+    constexpr int V = 4, NG = 2, NT = NTK;
     constexpr int C = TAPS / 2;
     constexpr int NV = PlanSize<TAPS, DMODE>::NV;
-    constexpr int RB = (int)kLeanRB;
+    constexpr int RB = NT * NG * V * (int)sizeof(T);  // bytes per ring slot: one row of the widest frame the block takes
     constexpr int W_OFF = kInRing * RB;  // the w ring follows the input ring
+    constexpr int BSH = (RB == 16384) ? 11 : 10;  // slot byte offset >> BSH = byte offset of the slot's 8-byte barrier
     static_assert(kInRing == 8 && kWRing == 4, "the step loop is unrolled by the w ring; the input ring is twice that");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t in_base = smem_u32(smem_raw);
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
         const uint32_t o_se = DYN ? ((uint32_t)(j - 1 - 3 * C) & (kWRing - 1)) * RB : 0u;
         if (j < n_load) {
             // barrier of the input slot: 8 bytes per 16 KiB slot
-            mbar_wait_imm<IMM_IN / RB * 8>(full0 + (o_in >> 11), DYN ? ((uint32_t)j >> 3) & 1u : par_in);
+            mbar_wait_imm<IMM_IN / RB * 8>(full0 + (o_in >> BSH), DYN ? ((uint32_t)j >> 3) & 1u : par_in);
             // raw centre row j-C, requested first so that its latency hides behind the row pass
             P4 rawc[NG];
 #pragma unroll
@@ -443,11 +447,11 @@ __global__ void __launch_bounds__(512, 1) wow_rows_lean_kernel(const ScaleParams
                 }
                 c_ptr += c_step;
                 __syncwarp();
-                if (lane == 0) mbar_arrive_imm<IMM_SW / RB * 8>(wbar0 + (o_sw >> 11));
+                if (lane == 0) mbar_arrive_imm<IMM_SW / RB * 8>(wbar0 + (o_sw >> BSH));
             }
         }
         if (j > 2 * C) {
-            mbar_wait_imm<IMM_SP / RB * 8>(wbar0 + (o_sp >> 11), ((uint32_t)(j - 1 - 2 * C) >> 2) & 1u);
+            mbar_wait_imm<IMM_SP / RB * 8>(wbar0 + (o_sp >> BSH), ((uint32_t)(j - 1 - 2 * C) >> 2) & 1u);
             if (tid == 0) {
                 // every warp is past part A of step j-1: input rows <= j-1-C are free
                 while (next_load < n_load && next_load - kInRing <= j - 1 - C) issue_load();
@@ -575,7 +579,10 @@ static bool plan_wow(ScaleParams &p, int taps, int esize, int batch, WowGeom *ge
     long long per_chain = slots_total / chains;
     if (per_chain < 1) per_chain = 1;
     int seg = (int)((n_max + per_chain - 1) / per_chain);
-    if (seg < 12 * c) seg = 12 * c;
+    // never shorter than the taps: a step costs ~1 us of latency whatever the row width, so small frames want MANY short
+    // segments (512^2: 12 steps per block instead of 32) and pay the 4c warm-up rows in bytes they do not miss; large
+    // frames never get here (4096^2: 28-row segments fill one wave)
+    if (seg < 2 * c) seg = 2 * c;
     if (seg > n_max) seg = n_max;
     p.seg = seg;
     p.n_seg = (n_max + seg - 1) / seg;
@@ -654,17 +661,44 @@ static int wow_pair_step(int taps, int d) {
     return 1;
 }
 
+// Rows of 1025 .. 2048 columns: 256-thread blocks on 8 KiB slots, two per SM, with the default choice of not-unrolled /
+// unrolled kernels only (hints on).
+template <int TAPS, int DMODE>
+static auto wow_lean256_kernel(int pair, int sig_mode) -> void (*)(const ScaleParams) {
+    if constexpr (DMODE == 0) {
+        if (pair == 1)
+            return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, 0, true, 0, 1, false, 256>
+                                 : (sig_mode == 1 ? wow_rows_lean_kernel<TAPS, 0, true, 1, 1, true, 256>
+                                                  : wow_rows_lean_kernel<TAPS, 0, true, 2, 1, true, 256>);
+        return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, 0, true, 0, 0, false, 256>
+                             : (sig_mode == 1 ? wow_rows_lean_kernel<TAPS, 0, true, 1, 0, true, 256>
+                                              : wow_rows_lean_kernel<TAPS, 0, true, 2, 0, true, 256>);
+    } else {
+        return sig_mode == 0 ? wow_rows_lean_kernel<TAPS, DMODE, true, 0, 0, true, 256>
+                             : (sig_mode == 1 ? wow_rows_lean_kernel<TAPS, DMODE, true, 1, 0, true, 256>
+                                              : wow_rows_lean_kernel<TAPS, DMODE, true, 2, 0, true, 256>);
+    }
+}
+
 template <typename T, int TAPS, int DMODE, bool HINTS>
 static int launch_wow_h(const ScaleParams &p, int batch, const WowGeom &geo, cudaStream_t st) {
-    // the lean kernel always runs 512 threads x 2 vectors on 16 KiB ring slots: use it when the row needs them
-    const bool packed = sizeof(T) == 4 && p.W > 2048 && p.n_strips == 1 && wow_packed_enabled();
-    const int pair = (packed && DMODE == 0 && HINTS) ? wow_pair_step(TAPS, p.d) : 0;
+    // the lean kernel runs 512 threads x 2 vectors on 16 KiB ring slots (rows of 2049 .. 4096 columns) or 256 threads on
+    // 8 KiB slots (1025 .. 2048 columns; hints on); narrower rows and float64 keep the generic kernel
+    const bool lean_ok = sizeof(T) == 4 && p.n_strips == 1 && wow_packed_enabled();
+    const bool packed = lean_ok && p.W > 2048;
+    const bool packed256 = lean_ok && HINTS && p.W > 1024 && p.W <= 2048 && geo.ng == 2;
+    const int pair = ((packed || packed256) && DMODE == 0 && HINTS) ? wow_pair_step(TAPS, p.d) : 0;
     const bool dyn = packed && HINTS && wow_dyn_for(DMODE, p.sig_mode);
-    auto kern = wow_kernel_for<T, TAPS, DMODE, HINTS>(packed, pair, dyn, p.sig_mode);
-    const int nt = packed ? 512 : geo.nt;
-    const size_t smem = packed ? (size_t)(kInRing + kWRing) * kLeanRB + 8 * (size_t)(kInRing + kWRing) : geo.smem;
-    static bool configured[13][64] = {};  // generic, lean x 3 significance modes x {plain, paired} x {unrolled, not}; per device
-    const int kidx = packed ? 1 + p.sig_mode + 3 * pair + 6 * (dyn ? 1 : 0) : 0;
+    void (*kern)(const ScaleParams) = nullptr;
+    if constexpr (sizeof(T) == 4 && HINTS) {
+        if (packed256) kern = wow_lean256_kernel<TAPS, DMODE>(pair, p.sig_mode);
+    }
+    if (!kern) kern = wow_kernel_for<T, TAPS, DMODE, HINTS>(packed, pair, dyn, p.sig_mode);
+    const int nt = packed ? 512 : (packed256 ? 256 : geo.nt);
+    const size_t smem = (packed || packed256) ? (size_t)(kInRing + kWRing) * (size_t)nt * 32 + 8 * (size_t)(kInRing + kWRing) : geo.smem;
+    // generic, lean x 3 significance modes x {plain, paired} x {unrolled, not}, lean-256 x 3 x {plain, paired}; per device
+    static bool configured[19][64] = {};
+    const int kidx = packed ? 1 + p.sig_mode + 3 * pair + 6 * (dyn ? 1 : 0) : (packed256 ? 13 + p.sig_mode + 3 * pair : 0);
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[kidx][dev]) {

@@ -22,9 +22,14 @@ __all__ = ["denoise", "wow", "wow_batch", "wow_stream", "generalized_anscombe", 
 
 # Development switch (tests compare the fused one-pass WOW scales against the two-pass route bit for bit).
 FUSED_WOW = True
-# Bilateral WOW: run the memory-bound half of every scale (exact median, whitening K3) on a high-priority side stream
-# while the compute-bound bilateral kernel K2 of the next scale runs on the caller's stream (A/B switch).
-OVERLAP_BILATERAL = os.environ.get("WB_OVERLAP_BILATERAL", "1") != "0"
+# The cascade with whitening in ONE library call (wb_wow_cascade) instead of a Python loop over the scales: the same
+# launches, without the interpreter / ctypes time per launch (tests switch it off to compare the two bit for bit).
+C_CASCADE = os.environ.get("WB_C_CASCADE", "1") != "0"
+# Bilateral WOW, Python loop only: run the memory-bound half of every scale (exact median, whitening K3) on a
+# high-priority side stream while the compute-bound bilateral kernel K2 of the next scale runs on the caller's stream.
+# Measured: 1 % on 4096^2 fp32 frames (K2 is issue-bound: a co-resident kernel is paid in full) against 0.4 ms of host
+# time per frame on small ones -- off by default (WB_OVERLAP_BILATERAL=1 turns it on and bypasses wb_wow_cascade).
+OVERLAP_BILATERAL = os.environ.get("WB_OVERLAP_BILATERAL", "0") != "0"
 _SIDE_STREAMS: dict = {}
 
 
@@ -193,6 +198,37 @@ def _wow_stack(stack, scaling_function_class, n_scales, wts, dns, sigma_bilatera
     factors = transform.var_factors(L) if bilateral is not None else [None] * L
     if L == 0:
         planes[:, 0].copy_(stack)
+    # (bilateral cascades: in one call unless the side-stream overlap of K3 with K2 is asked for -- it gains 1 % on 4096^2
+    # frames and costs 0.4 ms of host time on small ones)
+    if C_CASCADE and FUSED_WOW and whitening and (bilateral is None or not OVERLAP_BILATERAL) and L >= 1 and \
+            dev.type == "cuda":
+        # one call: wb_wow_cascade issues exactly the launches of the loop below
+        import ctypes
+        scratch3 = buffer("scratch3", (3, b, h, w))
+        recon = buffer("recon", (b, h, w))
+        code = _lib.dtype_code(dt)
+        ws_bytes = lib.wb_wow_cascade_workspace_bytes(code, b, h * w)
+        ws = buffers.get("cascade_ws")
+        if ws is None or ws.numel() < ws_bytes or ws.device != dev:
+            ws = buffers["cascade_ws"] = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        any_sig = any(d != 0 for d in dns[:L])
+        estimate = noise is None and any_sig
+        nz = noise
+        if estimate:
+            nz = _Noise(dev=torch.empty(b, dtype=torch.float64, device=dev))
+        use = nz if nz is not None else _Noise()
+        arr = ctypes.c_double * (L + 1)
+        _, _, _, pitch, bstride = _frame_layout(stack)
+        with torch.cuda.device(dev):
+            _lib.check(lib.wb_wow_cascade(stack.data_ptr(), pitch, bstride, planes.data_ptr(), scratch3.data_ptr(),
+                                          recon.data_ptr(), b, h, w, L, sf.taps_code, code,
+                                          arr(*[float(x) for x in wts[:L + 1]]),
+                                          arr(*([float(x) for x in dns[:L]] + [0.0])),
+                                          arr(*([float(x) for x in sigma_e[:L]] + [0.0])),
+                                          None if bilateral is None else arr(*([float(x) for x in factors[:L]] + [0.0])),
+                                          1 if soft_threshold else 0, float(use.host), use.dev_ptr, 1 if estimate else 0,
+                                          ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)))
+        return recon, planes, nz
     scratch = buffer("scratch", (2, b, h, w)) if L > 1 else None
     raw_planes = None  # scratch for the raw w_s of the two-pass route, allocated on first use
     nz = noise  # _Noise or None
