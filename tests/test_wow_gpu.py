@@ -177,7 +177,7 @@ def test_wow_golden(dt):
                 frac = (np.abs(recon - ref64) > 1e-4 * np.abs(ref64).max()).mean()
                 assert frac < (5e-3 if dt == "float32" else 1e-9), (tag, key, frac)
                 continue
-            tol = dual_tol(ref, ref64, dt, fp64_tol=1e-9 if bil else 1e-11)
+            tol = dual_tol(ref, ref64, dt, fp64_tol=1e-12)  # measured (float64): <= 1.1e-15 plain, <= 1.7e-14 bilateral
             e = orc.emax(recon, ref64)
             report.append((tag, key, e, tol))
             assert e <= tol, (tag, key, e, tol)
@@ -186,7 +186,7 @@ def test_wow_golden(dt):
                 got = co.data.cpu().numpy()
                 assert got.shape == rp.shape and got.dtype == rp.dtype
                 for p in range(len(rp)):
-                    tp = dual_tol(rp[p], planes64[p], dt, fp64_tol=1e-8 if bil else 1e-10, base=2e-5)
+                    tp = dual_tol(rp[p], planes64[p], dt, fp64_tol=1e-11 if bil else 1e-12, base=2e-5)
                     assert orc.emax(got[p], planes64[p]) <= tp, (tag, key, p, orc.emax(got[p], planes64[p]), tp)
     print("\nwow parity (E_max vs float64 oracle, tolerance):")
     for row in report:
@@ -463,10 +463,10 @@ def test_wow_options_golden(dt):
             got = co.data.cpu().numpy()
             assert got.shape == rp.shape and got.dtype == rp.dtype
             ref64, planes64, _ = orc.wow(img64, backend="numpy", **kw)
-            tol = dual_tol(ref, ref64, dt, fp64_tol=1e-11)
+            tol = dual_tol(ref, ref64, dt, fp64_tol=1e-12)
             assert orc.emax(recon, ref64) <= tol, (tag, key, orc.emax(recon, ref64), tol)
             for p in range(len(rp)):
-                tp = dual_tol(rp[p], planes64[p], dt, fp64_tol=1e-10, base=2e-5)
+                tp = dual_tol(rp[p], planes64[p], dt, fp64_tol=1e-12, base=2e-5)
                 assert orc.emax(got[p], planes64[p]) <= tp, (tag, key, p, orc.emax(got[p], planes64[p]), tp)
     # Coefficients in -> whitened in place, same result as the image call
     img = g["solar_in"]
@@ -505,10 +505,10 @@ def test_wow_nd_golden(dt):
             assert (np.abs(recon - r64) > 1e-4 * np.abs(r64).max()).mean() < (5e-3 if dt == "float32" else 1e-9)
             continue
         bil = "bilateral" in kw
-        tol_r = dual_tol(ref_r, r64, dt, fp64_tol=1e-10 if bil else 1e-12)
+        tol_r = dual_tol(ref_r, r64, dt, fp64_tol=1e-11 if bil else 1e-12)
         assert orc.emax(recon, r64) <= tol_r, (k, orc.emax(recon, r64), tol_r)
         for p in range(len(ref_p)):
-            tp = dual_tol(ref_p[p], p64[p], dt, fp64_tol=1e-10 if bil else 1e-12, base=2e-5)
+            tp = dual_tol(ref_p[p], p64[p], dt, fp64_tol=1e-11 if bil else 1e-12, base=2e-5)
             assert orc.emax(got[p], p64[p]) <= tp, (k, p, orc.emax(got[p], p64[p]), tp)
 
 
