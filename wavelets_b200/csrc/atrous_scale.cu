@@ -650,7 +650,9 @@ static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
         // the soft threshold (the inlined double-precision erf: 10 us slower, generic kept).
         if ((sizeof(T) == 8 || p.n_strips > 1) && cfg.ng == 2 && cfg.slots == kLeanSlots && p.l2_hints &&
             (long long)p.row_stride * (long long)sizeof(T) <= (long long)kLeanStripKiB * 1024 &&
-            (long long)p.row_stride * (long long)sizeof(T) > 8 * 1024 && k1_lean_enabled() && k1_lean_strips_enabled() &&
+            // (only where the planner laid the segments out for ONE block per SM, which is what 24 KiB slots give)
+            2 * ((long long)kLeanSlots * p.row_stride * (long long)sizeof(T) + 16 * kLeanSlots + 1024) > (long long)kMaxSmem &&
+            k1_lean_enabled() && k1_lean_strips_enabled() &&
             !(scale < 32 && g_override_set[scale])) {
             const int cols = p.n_strips == 1 ? p.W : p.wt;
             const bool pair = dmode == 0 && k1_pair_step(TAPS, p.d, cols, cfg.nt, V) == 1;

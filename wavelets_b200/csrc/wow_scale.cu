@@ -574,6 +574,8 @@ static bool plan_wow(ScaleParams &p, int taps, int esize, int batch, WowGeom *ge
     int occ = (int)(kMaxSmem / (smem + 1024));
     const int occ_regs = 65536 / (nt * 128);
     if (occ > occ_regs) occ = occ_regs;
+    // the 256-thread lean kernel (fp32 rows of 1025 .. 2048 columns, see launch_wow_h) runs two blocks per SM
+    if (esize == 4 && p.n_strips == 1 && p.W > 1024 && p.W <= 2048 && occ > 2) occ = 2;
     if (occ < 1) occ = 1;
     const long long slots_total = (long long)device_sm_count() * occ;
     long long per_chain = slots_total / chains;
