@@ -43,6 +43,15 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.wb_atrous_transform(None, ok, ok, 1, 8, 8, 8, 0, 2, 5, 0, None) == -5
     assert lib.wb_wow_whiten_scale(ok, ok, 1, 8, 8, 8, 0, 8, 0, 0, 5, 0, 0, 0.0, 1.0, 0.0, None, 1.0, None) == -5
     assert lib.wb_abs_median(ok, 0, 1, 0, 0, ok, None, 1.0, ok, 1 << 20, None) == -3
+    # the whole-cascade entry validates everything before its first launch
+    arr = (ctypes.c_double * 3)(1.0, 1.0, 1.0)
+    ws = lib.wb_wow_cascade_workspace_bytes(0, 1, 64)
+    assert ws >= lib.wb_abs_median_workspace_bytes(0, 1, 64) + lib.wb_plane_moments_workspace_bytes(1)
+    assert lib.wb_wow_cascade(ok, 8, 0, ok, ok, ok, 1, 8, 8, 2, 5, 7, arr, arr, arr, None, 1, 0.0, None, 0, ok, ws, None) == -1
+    assert lib.wb_wow_cascade(ok, 8, 0, ok, ok, ok, 1, 8, 8, 0, 5, 0, arr, arr, arr, None, 1, 0.0, None, 0, ok, ws, None) == -4
+    assert lib.wb_wow_cascade(ok, 8, 0, None, ok, ok, 1, 8, 8, 2, 5, 0, arr, arr, arr, None, 1, 0.0, None, 0, ok, ws, None) == -5
+    assert lib.wb_wow_cascade(ok, 8, 0, ok, ok, ok, 1, 8, 8, 2, 5, 0, arr, arr, arr, None, 1, 0.0, None, 1, ok, ws, None) == -5
+    assert lib.wb_wow_cascade(ok, 8, 0, ok, ok, ok, 1, 8, 8, 2, 5, 0, arr, arr, arr, None, 1, 0.0, None, 0, ok, 16, None) == -6
     assert b"dtype" in lib.wb_error_string(-1)
     assert lib.wb_abs_median_workspace_bytes(0, 2, 0) >= 2 * lib.wb_abs_median_workspace_bytes(0, 1, 0) - 512
     # + a quarter of the plane per frame for the filter pass
