@@ -559,6 +559,24 @@ static int launch_rows_lean(const ScaleParams &p, int batch, int nt, cudaStream_
     return launch_pdl<ScaleParams>(kern, grid, dim3((unsigned)(nt + 32)), smem, st, p);
 }
 
+// The cascade kernel on whole fp32 rows of 1025 .. 2048 columns: 8 KiB ring slots, two blocks per SM (a 2048^2 frame then
+// runs 296 segments of 7 rows instead of 148 of 14: the launch is bound by the number of steps per block).
+template <int TAPS, int DMODE, int PAIR>
+static int launch_rows_lean_small(const ScaleParams &p, int batch, int nt, cudaStream_t st) {
+    auto kern = atrous_rows_lean_kernel<float, TAPS, DMODE, true, OP_TRANSFORM, 0, PAIR, 4, 8>;
+    const size_t smem = (size_t)kLeanSlots * 8 * 1024 + 16 * (size_t)kLeanSlots;
+    static bool configured[64] = {};  // per instantiation, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    dim3 grid((unsigned)((long long)p.n_strips * p.d * p.n_seg), (unsigned)batch);
+    return launch_pdl<ScaleParams>(kern, grid, dim3((unsigned)(nt + 32)), smem, st, p);
+}
+
 // The lean kernel on column strips / float64 rows: ring slots of 24 KiB (a strip of 16 KiB plus the halo columns of
 // both sides), L2 hints on, step loop unrolled by half the ring.
 static constexpr int kLeanStripKiB = 24;
@@ -604,7 +622,7 @@ template <typename T, int TAPS, int OP>
 static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
     constexpr int V = VecOf<T>::V;
     K1Config cfg;
-    if (fast_path_ok(p, TAPS, (int)sizeof(T)) && plan_fast(p, TAPS, (int)sizeof(T), batch, scale, &cfg)) {
+    if (fast_path_ok(p, TAPS, (int)sizeof(T)) && plan_fast(p, TAPS, (int)sizeof(T), batch, scale, &cfg, OP == OP_TRANSFORM)) {
         const int dmode = (p.d % V == 0) ? 0 : p.d;
         if constexpr (sizeof(T) == 4 && OP == OP_TRANSFORM) {
             // whole-row strips with two vectors per thread and the default ring: the lean kernel
@@ -612,6 +630,13 @@ static int dispatch(ScaleParams &p, int batch, int scale, cudaStream_t st) {
                 !(scale < 32 && g_override_set[scale])) {
 #define WB_LEAN(DM) (p.l2_hints ? launch_rows_lean<TAPS, DM, true>(p, batch, cfg.nt, st) \
                                 : launch_rows_lean<TAPS, DM, false>(p, batch, cfg.nt, st))
+                if (p.W <= 2048 && p.l2_hints) {  // (the planner counted on two blocks per SM: plan_fast)
+                    if (dmode == 0 && k1_pair_step(TAPS, p.d, p.W, cfg.nt) == 1)
+                        return launch_rows_lean_small<TAPS, 0, 1>(p, batch, cfg.nt, st);
+                    if (dmode == 0) return launch_rows_lean_small<TAPS, 0, 0>(p, batch, cfg.nt, st);
+                    if (dmode == 1) return launch_rows_lean_small<TAPS, 1, 0>(p, batch, cfg.nt, st);
+                    if (dmode == 2) return launch_rows_lean_small<TAPS, 2, 0>(p, batch, cfg.nt, st);
+                }
                 if (dmode == 0 && p.l2_hints) {
                     const int pair = k1_pair_step(TAPS, p.d, p.W, cfg.nt);
                     if (pair == 1) return launch_rows_lean<TAPS, 0, true, OP_TRANSFORM, 0, 1>(p, batch, cfg.nt, st);

@@ -530,7 +530,8 @@ inline bool fast_path_ok(const ScaleParams &p, int taps, int esize) {
 }
 
 // Fill in the strip/segment/ring geometry.  Returns false if no geometry fits in shared memory.
-inline bool plan_fast(ScaleParams &p, int taps, int esize, int batch, int scale, K1Config *cfg_out) {
+inline bool plan_fast(ScaleParams &p, int taps, int esize, int batch, int scale, K1Config *cfg_out,
+                      bool transform_op = true) {
     const int V = 16 / esize;
     const int c = taps / 2;
     K1Config cfg;
@@ -571,7 +572,9 @@ inline bool plan_fast(ScaleParams &p, int taps, int esize, int batch, int scale,
         if (occ > occ_regs) occ = occ_regs;
         // the lean fp32 kernels (whole rows wider than 1024 columns, see dispatch in atrous_scale.cu) always stage 16 KiB
         // ring slots: one block per SM whatever the row width
-        if (esize == 4 && p.n_strips == 1 && p.W > 1024 && cfg.ng == 2 && slots == 8) occ = 1;
+        // -- except the cascade kernel on rows of <= 2048 columns, which has an 8 KiB-slot form (two blocks per SM)
+        if (esize == 4 && p.n_strips == 1 && p.W > 1024 && cfg.ng == 2 && slots == 8)
+            occ = (transform_op && p.W <= 2048 && p.l2_hints) ? 2 : 1;
         if (occ < 1) occ = 1;
         const long long slots_total = (long long)device_sm_count() * occ;
         long long per_chain = slots_total / chains;  // segments per chain that still fit in one wave
