@@ -522,6 +522,10 @@ __global__ void __launch_bounds__(NTK, NTK == 512 ? 1 : 2) wow_rows_lean_kernel(
 // ---------------------------------------------------------------------------------------------------------------
 struct WowGeom { int nt, ng; size_t smem; };
 
+// narrowest rows the 256-thread lean kernel takes (below that most of its threads would idle; the generic kernel sizes its
+// blocks to the row)
+static constexpr int kLean256MinW = 512;
+
 // WB_WOW_STRIPS=k in the environment forces k column strips (>= 2) where the whole row would fit (A/B measurements).
 static int wow_forced_strips() {
     const char *e = getenv("WB_WOW_STRIPS");
@@ -575,7 +579,7 @@ static bool plan_wow(ScaleParams &p, int taps, int esize, int batch, WowGeom *ge
     const int occ_regs = 65536 / (nt * 128);
     if (occ > occ_regs) occ = occ_regs;
     // the 256-thread lean kernel (fp32 rows of 1025 .. 2048 columns, see launch_wow_h) runs two blocks per SM
-    if (esize == 4 && p.n_strips == 1 && p.W > 1024 && p.W <= 2048 && occ > 2) occ = 2;
+    if (esize == 4 && p.n_strips == 1 && p.W > kLean256MinW && p.W <= 2048 && occ > 2) occ = 2;
     if (occ < 1) occ = 1;
     const long long slots_total = (long long)device_sm_count() * occ;
     long long per_chain = slots_total / chains;
@@ -688,7 +692,7 @@ static int launch_wow_h(const ScaleParams &p, int batch, const WowGeom &geo, cud
     // 8 KiB slots (1025 .. 2048 columns; hints on); narrower rows and float64 keep the generic kernel
     const bool lean_ok = sizeof(T) == 4 && p.n_strips == 1 && wow_packed_enabled();
     const bool packed = lean_ok && p.W > 2048;
-    const bool packed256 = lean_ok && HINTS && p.W > 1024 && p.W <= 2048 && geo.ng == 2;
+    const bool packed256 = lean_ok && HINTS && p.W > kLean256MinW && p.W <= 2048 && geo.ng == 2;
     const int pair = ((packed || packed256) && DMODE == 0 && HINTS) ? wow_pair_step(TAPS, p.d) : 0;
     const bool dyn = packed && HINTS && wow_dyn_for(DMODE, p.sig_mode);
     void (*kern)(const ScaleParams) = nullptr;
